@@ -1,0 +1,326 @@
+#!/usr/bin/env python
+"""bench.py — particle-updates/sec of the step hot path on synthetic 3D dam-break scenes.
+
+Contract (driver):  python bench.py --gpus N --steps K --warmup W  [--impl reference]
+One JSON line on stdout (rank 0).
+
+  step      one `step()` call = config.iterations (31) substeps of
+            clear -> p2g 1 -> p2g 2 -> update -> g2p over every particle (3d:110-134)
+  value     particle-updates/s with the state resident in HBM (CUDA events, max over ranks)
+  e2e       same metric through the public C ABI with HOST buffers: every step uploads the
+            particle records from pinned host memory, runs step(), reads every record back
+  roofline  dominant kernel: algorithmic bytes per launch / CUDA-event duration, over the
+            timed region, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline  the CPU oracle (a C++ restatement of the reference, "port", 1 thread because the
+            reference is single-threaded) on a bounded sample of the same workload
+
+Workload: N=1 -> BASELINE config 4 (3D dam break, 2^24 particles); N GPUs -> 2^24 particles per
+GPU in z-slabs (N=8 is BASELINE config 5, 2^27 particles): weak scaling.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "particle-updates/sec (3D WCSPH-reference step: MLS-MPM substeps)"
+UNIT = "particle-updates/s"
+
+# Algorithmic bytes per particle-substep, SURVEY.md section 8(d) (3D, A/N = 1):
+#   p2g 1: 64 B particle read + 32 B node RMW; p2g 2: 52 B + 12 B mass read... per-phase split
+ALG_BYTES = {"clear": 16.0, "p2g 1": 64.0 + 32.0, "p2g 2": 52.0 + 28.0, "update": 0.0, "g2p": 72.0 + 16.0}
+ALG_BYTES_STEP = 280.0     # sum of the above = 188 + 92
+
+
+def measured_peaks():
+    f = ROOT / "MEASURED_PEAKS.json"
+    if f.exists():
+        d = json.loads(f.read_text())
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.gpu)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in Path(self.path).read_text().splitlines():
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_info():
+    model = "unknown"
+    try:
+        for line in Path("/proc/cpuinfo").read_text().splitlines():
+            if line.startswith("model name"):
+                model = line.split(":", 1)[1].strip()
+                break
+    except OSError:
+        pass
+    return model, os.cpu_count()
+
+
+def oracle_sample(scenes, seconds_target: float = 15.0):
+    """Time the CPU oracle on a scaled-down dam break of the same construction (1 thread)."""
+    from oracle import oracle
+    oracle.build()
+    sc = scenes.dam_break_3d(64, 64, 64)          # 262,144 particles, same column shape as 256^3
+    sim = oracle.OracleSim(sc.cfg)
+    sim.add_particles(sc.records())
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    sim.substeps(2)                                # warm: first touch of the grid
+    t0 = time.perf_counter()
+    sim.substeps(2)
+    per = (time.perf_counter() - t0) / 2
+    n_sub = max(4, min(62, int(seconds_target / max(per, 1e-6))))
+    t0 = time.perf_counter()
+    sim.substeps(n_sub)
+    dt = time.perf_counter() - t0
+    phases = sim.phase_seconds()
+    sim.close()
+    return sc, n_sub, dt, sc.n * n_sub / dt, phases
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The Rust binary cannot
+    be built here (no rustc), so this is the oracle port: same five phases, same order, 1 thread
+    (the reference has no parallel loops — SURVEY.md section 0.2)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import fluidpkg
+    scenes = fluidpkg.load().scenes
+    from oracle import oracle
+    oracle.build()
+    sc = scenes.dam_break_3d(64, 64, 64)
+    sim = oracle.OracleSim(sc.cfg)
+    sim.add_particles(sc.records())
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    # one step = one step() of the bounded sample = 31 substeps x 262,144 particles (~11 s)
+    for _ in range(args.warmup):
+        sim.substeps(2)                            # warm-up is shortened: nothing to warm on a CPU but caches
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sim.step()
+    dt = time.perf_counter() - t0
+    value = sc.n * sc.cfg["iterations"] * args.steps / dt
+    model, cores = cpu_info()
+    full = scenes.dam_break_for_gpus(args.gpus)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": dict(full.describe(), substeps_per_step=sc.cfg["iterations"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+                         "sample": f"{sc.name}: {sc.n} particles x {sc.cfg['iterations']} substeps per step "
+                                   f"(1/64 of the 2^24-particle column, same construction)",
+                         "host_cpu": model, "host_cores": cores},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import fluidpkg
+    pkg = fluidpkg.load()
+    scenes = pkg.scenes
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — this engine has no CPU path (use --impl reference "
+                         "for the CPU oracle)")
+    if args.gpus != world and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        raise SystemExit("multi-GPU slab decomposition is not wired into bench.py yet")
+
+    sc = scenes.dam_break_for_gpus(args.gpus) if not args.scene else getattr(scenes, args.scene)()
+    iters = sc.cfg["iterations"]
+    rf = scenes.rec_floats(3)
+
+    # host records in pinned memory (also the e2e upload source)
+    host = torch.empty((sc.n, rf), dtype=torch.float32, pin_memory=True)
+    hnp = host.numpy()
+    chunk = 1 << 21
+    for s in range(0, sc.n, chunk):
+        c = min(chunk, sc.n - s)
+        hnp[s:s + c] = sc.records(s, c)
+    back = torch.empty((sc.n, rf), dtype=torch.float32, pin_memory=True)
+
+    stream = torch.cuda.current_stream()
+    sim = pkg.Simulation.new(sc.cfg, device=local_rank)
+    sim.set_stream(stream.cuda_stream)
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    sim.add_particles_pinned(host.data_ptr(), sc.n)
+    sim.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------------------
+    for _ in range(args.warmup):
+        sim.step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sim.launch_count()
+    sim.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    for _ in range(args.steps):
+        sim.step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    prof = sim.profile_read()
+    sim.profile(False)
+    launches = sim.launch_count() - launches0
+    clocks = sampler.stop()
+    counts = sim.particle_counts()
+    assert counts["active"] == sc.n, counts
+    value = sc.n * iters * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------
+    peak, peak_src = measured_peaks()
+    nsub = max(prof["substeps"], 1)
+    per_phase_ms = {k: prof[k] / nsub * 1e3 for k in ("sort", "clear", "p2g 1", "p2g 2", "update", "g2p")}
+    dom = max(("clear", "p2g 1", "p2g 2", "g2p"), key=lambda k: per_phase_ms[k])
+    achieved = ALG_BYTES[dom] * sc.n / (per_phase_ms[dom] * 1e-3) / 1e9
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "alg_bytes_per_particle": ALG_BYTES[dom], "ms_per_launch": per_phase_ms[dom],
+        "step_frac": value * ALG_BYTES_STEP / 1e9 / peak,
+        "per_phase_ms": per_phase_ms,
+    }
+
+    # ---- end to end through the C ABI with host buffers -----------------------------------------
+    e2e_steps = max(2, min(args.steps, 4))
+
+    def e2e_step():
+        sim.clear_particles()
+        sim.add_particles_pinned(host.data_ptr(), sc.n)           # H2D from pinned memory
+        sim.step()
+        n = sim.read_particles_into(back.data_ptr(), sc.n)        # D2H of every record
+        assert n == sc.n
+
+    e2e_step()                                                    # warm-up
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    e2e_value = sc.n * iters * e2e_steps / e2e_s
+    rec_bytes = sc.n * rf * 4
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
+    cpu = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu:
+        bsc, n_sub, dt, cpu_value, phases = oracle_sample(scenes)
+        model, cores = cpu_info()
+        cpu = {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
+               "sample": f"{bsc.name}: {bsc.n} particles x {n_sub} substeps in {dt:.1f} s "
+                         f"(1/64 of the 2^24-particle column, same construction)",
+               "host_cpu": model, "host_cores": cores,
+               "phase_seconds_last_substep": phases}
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(sc.describe(), substeps_per_step=iters,
+                       l2="inputs larger than L2 (particle state 1.1 GB, node grid 1.2 GB per GPU)",
+                       parallelism=f"z-slabs x{args.gpus}" if args.gpus > 1 else "single GPU"),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes,
+                "d2h_bytes_per_step": rec_bytes, "steps": e2e_steps,
+                "what": "clear + add_particles(pinned host records) + step() + read_particles(all records)"},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "ms_per_substep": ms / args.steps / iters,
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    sim.close()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scene", default="", help="scene function in scenes.py (default: dam break for --gpus)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,133 @@
+// common.cuh — geometry, integer cell/key rules and the quadratic stencil shared by all kernels.
+//
+// Reference: GossiperLoturot/fluid-rs src/3d_multi.rs ("3d:") and src/2d_multi.rs ("2d:").
+// Integer outputs (cell = floor(pos) 3d:153, block key = div_euclid 3d:398-401) follow the
+// reference bit for bit: IEEE division and fmodf, no fast-math.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace fluid {
+
+// Tile of cells that one warp owns in the tiled kernels and that defines the sort order.
+// 3D: 8 x 8 x 4 cells, 2D: 16 x 16 cells — 256 cells either way.
+template <int DIM> struct Tile;
+template <> struct Tile<3> { static constexpr int X = 8, Y = 8, Z = 4, CELLS = 256; };
+template <> struct Tile<2> { static constexpr int X = 16, Y = 16, Z = 1, CELLS = 256; };
+
+struct Geo {
+    int dim;
+    int org[3];        // grid origin cell = p_rect.0 * grid_res            (3d:169)
+    int size[3];       // grid size in cells = (p_rect.1 - p_rect.0) * res  (3d:94)
+    int a_lo[3], a_hi[3], p_lo[3], p_hi[3];   // block-key rects (3d:80-86)
+    int tdim[3];       // tiles per axis (size rounded up to the tile shape)
+    int n_tiles;
+    int n_cells_pad;   // n_tiles * 256: length of the tiled cell index space
+    int guard;         // guard nodes before/after the grid array (zero-weight overreach)
+    int slab_lo, slab_hi;   // owned cell range along the last axis (world cells); open if unset
+    float res_f;       // grid_res as f32 (3d:399)
+    float dt, rest_density, mu, stiffness, power, mouse_r2, pclamp;
+    float dtg[3];      // dt * gravity (3d:255)
+    float clip_lo[3], clip_hi[3];
+    float wall_lo[3], wall_hi[3];   // clip +- damp (3d:321-324)
+};
+
+// ---- exact integer rules ----------------------------------------------------------------
+
+// Rust `f as i32`: truncating, saturating, NaN -> 0.  __float2int_rz saturates and maps NaN to 0.
+__device__ __forceinline__ int rust_as_i32(float f) { return __float2int_rz(f); }
+
+// f32::div_euclid (3d:399): q = trunc(a / b); if a % b < 0 { q - 1 } (b > 0 here).
+__device__ __forceinline__ float rust_div_euclid(float a, float b) {
+    float q = truncf(__fdiv_rn(a, b));
+    if (fmodf(a, b) < 0.0f) q = (b > 0.0f) ? q - 1.0f : q + 1.0f;
+    return q;
+}
+
+__device__ __forceinline__ int block_key(float p, float res_f) {
+    return rust_as_i32(rust_div_euclid(p, res_f));
+}
+
+enum ParticleClass : int { CLS_ACTIVE = 0, CLS_FROZEN = 1, CLS_LIMBO = 2, CLS_DROPPED = 3 };
+
+// Class of a particle from its position alone: the reference stores a particle in the block
+// whose key is key_from_pos(pos) (3d:104-108, 347-366), advances a_rect blocks (3d:263),
+// deposits p_rect blocks (3d:149) and never touches the rest.
+template <int DIM>
+__device__ __forceinline__ int classify(const Geo& g, const float* pos, int* key) {
+    bool in_a = true, in_p = true;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+        int k = block_key(pos[a], g.res_f);
+        key[a] = k;
+        in_a = in_a && (k >= g.a_lo[a]) && (k < g.a_hi[a]);
+        in_p = in_p && (k >= g.p_lo[a]) && (k < g.p_hi[a]);
+    }
+    return in_a ? CLS_ACTIVE : (in_p ? CLS_FROZEN : CLS_LIMBO);
+}
+
+// Tiled cell index (sort key).  rel = cell - origin, clamped into the grid by the caller.
+template <int DIM>
+__device__ __forceinline__ int tiled_cell_index(const Geo& g, const int* rel) {
+    using T = Tile<DIM>;
+    int tx = rel[0] / T::X, lx = rel[0] - tx * T::X;
+    int ty = rel[1] / T::Y, ly = rel[1] - ty * T::Y;
+    if (DIM == 2) {
+        return (ty * g.tdim[0] + tx) * T::CELLS + ly * T::X + lx;
+    }
+    int tz = rel[2] / T::Z, lz = rel[2] - tz * T::Z;
+    return ((tz * g.tdim[1] + ty) * g.tdim[0] + tx) * T::CELLS + (lz * T::Y + ly) * T::X + lx;
+}
+
+// Reference linear node index x + y*sx + z*sx*sy (3d:169-172).
+template <int DIM>
+__device__ __forceinline__ int ref_cell_index(const Geo& g, const int* rel) {
+    int idx = rel[0] + rel[1] * g.size[0];
+    if (DIM == 3) idx += rel[2] * g.size[0] * g.size[1];
+    return idx;
+}
+
+// ---- quadratic stencil (3d:153-161, 390-396) ----------------------------------------------
+
+template <int DIM>
+struct Stencil {
+    int base[DIM];      // node of offset 0, relative to the grid origin: cell - 1 - org
+    float w[DIM][3];    // per-axis weights, zeroed where the node is outside the p_rect grid
+    float d[DIM][3];    // x_node - x_particle per axis = (o - 1) - c
+};
+
+template <int DIM>
+__device__ __forceinline__ void make_stencil(const Geo& g, const float* pos, Stencil<DIM>& s) {
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+        float fl = floorf(pos[a]);
+        int cell = rust_as_i32(fl);
+        float c = pos[a] - (fl + 0.5f);
+        float m = 0.5f - c, p = 0.5f + c;
+        s.w[a][0] = 0.5f * m * m;
+        s.w[a][1] = 0.75f - c * c;
+        s.w[a][2] = 0.5f * p * p;
+        s.d[a][0] = -1.0f - c;
+        s.d[a][1] = -c;
+        s.d[a][2] = 1.0f - c;
+        int b = cell - 1 - g.org[a];
+        s.base[a] = b;
+        // The reference skips nodes outside the p_rect grid (3d:166-168); a zero weight drops
+        // the same terms from every sum.
+#pragma unroll
+        for (int o = 0; o < 3; ++o) {
+            int n = b + o;
+            if (n < 0 || n >= g.size[a]) s.w[a][o] = 0.0f;
+        }
+    }
+}
+
+// Tait pressure with the reference's lower clamp (3d:217-220): max(clamp, B*((rho/rho0)^g - 1)).
+__device__ __forceinline__ float tait_pressure(const Geo& g, float density) {
+    float eos = g.stiffness * (powf(__fdiv_rn(density, g.rest_density), g.power) - 1.0f);
+    return fmaxf(g.pclamp, eos);
+}
+
+}  // namespace fluid

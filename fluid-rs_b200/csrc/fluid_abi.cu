@@ -1,0 +1,911 @@
+// fluid_abi.cu — C ABI (include/fluid_b200.h) and host orchestration of the step engine.
+//
+// Drop-in for fluid-rs's `Simulation` (src/3d_multi.rs:50-134,383-387; 2d_multi.rs same
+// lines).  All state is device resident; the host only sequences kernels on one stream.
+// There is no CPU fallback: without a CUDA device fluid_create fails with FLUID_ERR_NO_DEVICE.
+#include "../../include/fluid_b200.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+#include "phases_generic.cuh"
+#include "sort.cuh"
+
+using namespace fluid;
+
+namespace {
+
+thread_local std::string g_last_error;
+
+fluid_status fail(fluid_status st, const std::string& msg) {
+    g_last_error = msg;
+    return st;
+}
+
+#define CU_TRY(expr)                                                                      \
+    do {                                                                                  \
+        cudaError_t _e = (expr);                                                          \
+        if (_e != cudaSuccess) {                                                          \
+            (void)cudaGetLastError();                                                     \
+            return fail(_e == cudaErrorMemoryAllocation ? FLUID_ERR_OUT_OF_MEMORY         \
+                                                        : FLUID_ERR_CUDA,                 \
+                        std::string(#expr) + ": " + cudaGetErrorString(_e));              \
+        }                                                                                 \
+    } while (0)
+
+#define ST_TRY(expr)                          \
+    do {                                      \
+        fluid_status _s = (expr);             \
+        if (_s != FLUID_OK) return _s;        \
+    } while (0)
+
+inline int rec_floats(int dim) { return 2 * dim + dim * dim + 1; }
+inline unsigned blocks_for(int64_t n, int threads) {
+    return static_cast<unsigned>((n + threads - 1) / threads);
+}
+
+// host copy of the device integer rules (set_rect needs key_from_pos on the host, 3d:80-81)
+int host_block_key(float p, float res) {
+    float q = std::trunc(p / res);
+    if (std::fmod(p, res) < 0.0f) q = res > 0.0f ? q - 1.0f : q + 1.0f;
+    if (q != q) return 0;
+    if (q >= 2147483648.0f) return INT_MAX;
+    if (q <= -2147483648.0f) return INT_MIN;
+    return static_cast<int>(q);
+}
+
+constexpr int N_EVENTS = 6;   // sort | clear | p2g1 | p2g2 | g2p | end
+constexpr int PROFILE_POOL = 256;
+
+}  // namespace
+
+struct fluid_sim {
+    fluid_config cfg{};
+    int dim = 3;
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+
+    Geo geo{};
+    bool rect_set = false;
+
+    int64_t n = 0;          // particle slots in use (live + not yet compacted tombstones)
+    int64_t cap = 0;
+    Particles buf[2]{};
+    int cur = 0;
+    int* cell_idx = nullptr;
+    int* rank = nullptr;
+
+    int* count = nullptr;    // n_cells_pad + 2 buckets
+    int* start = nullptr;    // n_cells_pad + 3 (exclusive scan + total)
+    int64_t bucket_len = 0;
+    int* block_sums = nullptr;
+    int64_t n_scan_blocks = 0;
+    int* class_count = nullptr;   // 4 ints (device)
+
+    float4* grid = nullptr;
+    int64_t grid_nodes = 0;      // reference node count (without guards)
+    float* d_mouse = nullptr;
+
+    float* d_stage = nullptr;    // staging for host<->device record copies
+    int64_t stage_floats = 0;
+    int* d_stage_ids = nullptr;
+    int64_t stage_ids = 0;
+    int* d_counter = nullptr;
+
+    cudaEvent_t ev[N_EVENTS]{};
+    bool timers_recorded = false;
+    cudaEvent_t* last_ev = nullptr;    // event set of the last timed substep
+    // profile mode: a pool of event sets, drained into sums when full or when read
+    bool profiling = false;
+    std::vector<cudaEvent_t> pool;     // PROFILE_POOL * N_EVENTS
+    int pool_used = 0;
+    double prof_sum[N_EVENTS - 1] = {0, 0, 0, 0, 0};
+    int64_t prof_substeps = 0;
+
+    int64_t launches = 0;
+    int32_t next_id = 0;
+    int64_t dropped_total = 0;
+    int slab_lo = INT_MIN, slab_hi = INT_MAX;
+};
+
+namespace {
+
+void free_particles(Particles& p) {
+    cudaFree(p.P);
+    cudaFree(p.V);
+    cudaFree(p.CA);
+    cudaFree(p.CB);
+    cudaFree(p.CC);
+    p = Particles{};
+}
+
+fluid_status alloc_particles(Particles& p, int64_t cap) {
+    CU_TRY(cudaMalloc(&p.P, cap * sizeof(float4)));
+    CU_TRY(cudaMalloc(&p.V, cap * sizeof(float4)));
+    CU_TRY(cudaMalloc(&p.CA, cap * sizeof(float4)));
+    CU_TRY(cudaMalloc(&p.CB, cap * sizeof(float4)));
+    CU_TRY(cudaMalloc(&p.CC, cap * sizeof(float)));
+    return FLUID_OK;
+}
+
+fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
+    if (want <= s->cap) return FLUID_OK;
+    if (want > INT_MAX - 1024) return fail(FLUID_ERR_INVALID_ARG, "more than 2^31 particles per handle");
+    int64_t cap = std::max<int64_t>(want, s->cap + s->cap / 2);
+    cap = std::min<int64_t>((cap + 1023) / 1024 * 1024, INT_MAX - 1024);
+    Particles nb[2]{};
+    for (int b = 0; b < 2; ++b) ST_TRY(alloc_particles(nb[b], cap));
+    if (s->n > 0) {
+        const Particles& o = s->buf[s->cur];
+        CU_TRY(cudaMemcpyAsync(nb[0].P, o.P, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(cudaMemcpyAsync(nb[0].V, o.V, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(cudaMemcpyAsync(nb[0].CA, o.CA, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(cudaMemcpyAsync(nb[0].CB, o.CB, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
+        CU_TRY(cudaMemcpyAsync(nb[0].CC, o.CC, s->n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
+    cudaFree(s->cell_idx);
+    cudaFree(s->rank);
+    s->cell_idx = s->rank = nullptr;
+    s->buf[0] = nb[0];
+    s->buf[1] = nb[1];
+    s->cur = 0;
+    CU_TRY(cudaMalloc(&s->cell_idx, cap * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->rank, cap * sizeof(int)));
+    s->cap = cap;
+    return FLUID_OK;
+}
+
+fluid_status ensure_stage(fluid_sim* s, int64_t floats, int64_t ids) {
+    if (floats > s->stage_floats) {
+        cudaFree(s->d_stage);
+        s->d_stage = nullptr;
+        s->stage_floats = 0;
+        CU_TRY(cudaMalloc(&s->d_stage, floats * sizeof(float)));
+        s->stage_floats = floats;
+    }
+    if (ids > s->stage_ids) {
+        cudaFree(s->d_stage_ids);
+        s->d_stage_ids = nullptr;
+        s->stage_ids = 0;
+        CU_TRY(cudaMalloc(&s->d_stage_ids, ids * sizeof(int)));
+        s->stage_ids = ids;
+    }
+    return FLUID_OK;
+}
+
+// ---- small utility kernels -------------------------------------------------------------
+
+template <int DIM>
+__global__ void k_unpack_records(const float* __restrict__ rec, const int* __restrict__ ids,
+                                 int base_id, int n, Particles dst, int offset) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    constexpr int RF = 2 * DIM + DIM * DIM + 1;
+    const float* r = rec + static_cast<int64_t>(i) * RF;
+    int id = ids ? ids[i] : base_id + i;
+    int d = offset + i;
+    if (DIM == 3) {
+        dst.P[d] = make_float4(r[0], r[1], r[2], r[15]);
+        dst.V[d] = make_float4(r[3], r[4], r[5], __int_as_float(id));
+        dst.CA[d] = make_float4(r[6], r[7], r[8], r[9]);
+        dst.CB[d] = make_float4(r[10], r[11], r[12], r[13]);
+        dst.CC[d] = r[14];
+    } else {
+        dst.P[d] = make_float4(r[0], r[1], 0.0f, r[8]);
+        dst.V[d] = make_float4(r[2], r[3], 0.0f, __int_as_float(id));
+        dst.CA[d] = make_float4(r[4], r[5], r[6], r[7]);
+    }
+}
+
+template <int DIM>
+__device__ __forceinline__ void pack_record(const Particles& q, int i, float* r, int* id) {
+    float4 p = q.P[i], v = q.V[i], a = q.CA[i];
+    if (DIM == 3) {
+        float4 b = q.CB[i];
+        r[0] = p.x; r[1] = p.y; r[2] = p.z;
+        r[3] = v.x; r[4] = v.y; r[5] = v.z;
+        r[6] = a.x; r[7] = a.y; r[8] = a.z; r[9] = a.w;
+        r[10] = b.x; r[11] = b.y; r[12] = b.z; r[13] = b.w;
+        r[14] = q.CC[i];
+        r[15] = p.w;
+    } else {
+        r[0] = p.x; r[1] = p.y; r[2] = v.x; r[3] = v.y;
+        r[4] = a.x; r[5] = a.y; r[6] = a.z; r[7] = a.w;
+        r[8] = p.w;
+    }
+    *id = __float_as_int(v.w);
+}
+
+// iter_particle (3d:383-387): every particle stored in an a_rect block, compacted.
+template <int DIM>
+__global__ void k_pack_active(const __grid_constant__ Geo g, Particles q, int n,
+                              float* __restrict__ rec, int* __restrict__ ids,
+                              int* __restrict__ counter, int capacity) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = false;
+    if (i < n) {
+        float4 p = q.P[i];
+        if (!is_tombstone(p.x)) {
+            float pos[3] = {p.x, p.y, p.z};
+            int key[3];
+            take = classify<DIM>(g, pos, key) == CLS_ACTIVE;
+        }
+    }
+    unsigned m = __ballot_sync(0xffffffffu, take);
+    int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (take) {
+        int d = base + __popc(m & ((1u << lane) - 1));
+        if (d < capacity) {
+            constexpr int RF = 2 * DIM + DIM * DIM + 1;
+            int id;
+            pack_record<DIM>(q, i, rec + static_cast<int64_t>(d) * RF, &id);
+            if (ids) ids[d] = id;
+        }
+    }
+}
+
+// ids / cell / key / reference cell index of the sorted p_rect particles (parity taps).
+template <int DIM>
+__global__ void k_debug_keys(const __grid_constant__ Geo g, Particles q,
+                             const int* __restrict__ n_deposit, int* __restrict__ ids,
+                             int* __restrict__ cell, int* __restrict__ key,
+                             int* __restrict__ ref_index) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= *n_deposit) return;
+    float4 p = q.P[i];
+    float pos[3] = {p.x, p.y, p.z};
+    int k[3], rel[3] = {0, 0, 0};
+    classify<DIM>(g, pos, k);
+    for (int a = 0; a < DIM; ++a) {
+        int c = rust_as_i32(floorf(pos[a]));
+        if (cell) cell[i * DIM + a] = c;
+        if (key) key[i * DIM + a] = k[a];
+        rel[a] = c - g.org[a];
+    }
+    if (ids) ids[i] = __float_as_int(q.V[i].w);
+    if (ref_index) ref_index[i] = ref_cell_index<DIM>(g, rel);
+}
+
+// ---- the substep -----------------------------------------------------------------------
+
+struct DebugTaps {
+    int* ids = nullptr;
+    int* cell = nullptr;
+    int* key = nullptr;
+    float* density = nullptr;
+    float* pressure = nullptr;
+};
+
+template <int DIM>
+fluid_status sort_particles(fluid_sim* s) {
+    const int n = static_cast<int>(s->n);
+    const int64_t m = s->bucket_len;   // n_cells_pad + 2
+    CU_TRY(cudaMemsetAsync(s->count, 0, m * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->class_count, 0, 4 * sizeof(int), s->stream));
+    Particles& src = s->buf[s->cur];
+    Particles& dst = s->buf[s->cur ^ 1];
+    if (n > 0) {
+        k_classify_count<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(
+            s->geo, src.P, n, s->cell_idx, s->rank, s->count, s->class_count);
+        ++s->launches;
+    }
+    const unsigned nb = static_cast<unsigned>(s->n_scan_blocks);
+    k_scan_partial<<<nb, SCAN_THREADS, 0, s->stream>>>(s->count, static_cast<int>(m), s->block_sums);
+    k_scan_sums<<<1, 1024, 0, s->stream>>>(s->block_sums, static_cast<int>(nb));
+    k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->count, static_cast<int>(m), s->block_sums, s->start);
+    s->launches += 3;
+    if (n > 0) {
+        k_reorder<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->cell_idx, s->rank, s->start);
+        ++s->launches;
+        s->cur ^= 1;
+    }
+    CU_TRY(cudaGetLastError());
+    return FLUID_OK;
+}
+
+fluid_status profile_drain(fluid_sim* s) {
+    if (s->pool_used == 0) return FLUID_OK;
+    CU_TRY(cudaEventSynchronize(s->pool[(s->pool_used - 1) * N_EVENTS + N_EVENTS - 1]));
+    for (int k = 0; k < s->pool_used; ++k)
+        for (int i = 0; i < N_EVENTS - 1; ++i) {
+            float ms = 0.0f;
+            CU_TRY(cudaEventElapsedTime(&ms, s->pool[k * N_EVENTS + i], s->pool[k * N_EVENTS + i + 1]));
+            s->prof_sum[i] += ms * 1e-3;
+        }
+    s->prof_substeps += s->pool_used;
+    s->pool_used = 0;
+    return FLUID_OK;
+}
+
+template <int DIM>
+fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const DebugTaps* dbg) {
+    if (!s->rect_set || s->n == 0) return FLUID_OK;   // no blocks to walk (3d:149 over an empty rect)
+    const int n = static_cast<int>(s->n);
+    const int* n_dep = s->start + s->geo.n_cells_pad;
+    cudaEvent_t* ev = s->ev;
+    if (s->profiling) {
+        if (s->pool_used == PROFILE_POOL) ST_TRY(profile_drain(s));
+        ev = &s->pool[s->pool_used * N_EVENTS];
+        ++s->pool_used;
+        timed = true;
+    }
+    if (timed) CU_TRY(cudaEventRecord(ev[0], s->stream));
+    ST_TRY(sort_particles<DIM>(s));
+    Particles q = s->buf[s->cur];
+    if (dbg && (dbg->ids || dbg->cell || dbg->key)) {
+        k_debug_keys<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, q, n_dep, dbg->ids, dbg->cell,
+                                                                    dbg->key, nullptr);
+        ++s->launches;
+    }
+    if (timed) CU_TRY(cudaEventRecord(ev[1], s->stream));
+    // clear_grid (3d:136-146)
+    CU_TRY(cudaMemsetAsync(s->grid, 0, (s->grid_nodes + 2 * s->geo.guard) * sizeof(float4), s->stream));
+    if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
+    k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid);
+    if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
+    k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid,
+                                                                  dbg ? dbg->density : nullptr,
+                                                                  dbg ? dbg->pressure : nullptr);
+    if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
+    k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid, d_mouse);
+    if (timed) {
+        CU_TRY(cudaEventRecord(ev[5], s->stream));
+        s->last_ev = ev;
+        s->timers_recorded = true;
+    }
+    s->launches += 3;
+    CU_TRY(cudaGetLastError());
+    return FLUID_OK;
+}
+
+fluid_status substep(fluid_sim* s, const float* d_mouse, bool timed, const DebugTaps* dbg) {
+    return s->dim == 3 ? substep_impl<3>(s, d_mouse, timed, dbg) : substep_impl<2>(s, d_mouse, timed, dbg);
+}
+
+fluid_status upload_mouse(fluid_sim* s, const float* mouse_xy, const float** d_mouse) {
+    *d_mouse = nullptr;
+    if (!mouse_xy) return FLUID_OK;
+    CU_TRY(cudaMemcpyAsync(s->d_mouse, mouse_xy, 2 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    *d_mouse = s->d_mouse;
+    return FLUID_OK;
+}
+
+// Pull the class counters of the last sort; compact away tombstones (they sit at the tail).
+fluid_status refresh_counts(fluid_sim* s, int64_t counts[4]) {
+    counts[0] = counts[1] = counts[2] = 0;
+    counts[3] = s->dropped_total;
+    if (s->n == 0) return FLUID_OK;
+    if (!s->rect_set) {   // before set_rect every key is outside the (empty) rects
+        counts[2] = s->n;
+        return FLUID_OK;
+    }
+    ST_TRY(s->dim == 3 ? sort_particles<3>(s) : sort_particles<2>(s));
+    int h[4];
+    CU_TRY(cudaMemcpyAsync(h, s->class_count, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->dropped_total += h[3];
+    s->n -= h[3];   // sorted order: cells | limbo | dropped
+    counts[0] = h[0];
+    counts[1] = h[1];
+    counts[2] = h[2];
+    counts[3] = s->dropped_total;
+    return FLUID_OK;
+}
+
+}  // namespace
+
+// =========================================================================================
+extern "C" {
+
+int32_t fluid_abi_version(void) { return FLUID_B200_ABI_VERSION; }
+
+const char* fluid_last_error(void) { return g_last_error.c_str(); }
+
+const char* fluid_phase_label(int32_t phase) {
+    static const char* labels[FLUID_NUM_PHASES] = {"clear", "p2g 1", "p2g 2", "update", "g2p"};
+    return (phase >= 0 && phase < FLUID_NUM_PHASES) ? labels[phase] : "";
+}
+
+fluid_status fluid_config_default(int32_t dim, fluid_config* out) {
+    if (!out || (dim != 2 && dim != 3)) return fail(FLUID_ERR_INVALID_ARG, "fluid_config_default: dim must be 2 or 3");
+    std::memset(out, 0, sizeof(*out));
+    out->dim = dim;
+    out->dt = dim == 2 ? 0.032f : 0.066f;
+    out->iterations = static_cast<int32_t>(1.0 / 0.032);
+    out->grid_res = dim == 2 ? 32 : 16;
+    out->gravity[1] = 0.3f;
+    out->rest_density = dim == 2 ? 4.0f : 1.0f;
+    out->dynamic_viscosity = 0.1f;
+    out->eos_stiffness = 10.0f;
+    out->eos_power = 4.0f;
+    out->mouse_radius = 10.0f;
+    for (int a = 0; a < 3; ++a) {
+        out->clip_min[a] = 0.0f;
+        out->clip_max[a] = 64.0f;
+    }
+    out->boundary_damp_dist = 3.0f;
+    out->pressure_clamp = dim == 2 ? -0.0f : -0.1f;
+    return FLUID_OK;
+}
+
+fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** out) {
+    if (!cfg || !out) return fail(FLUID_ERR_INVALID_ARG, "fluid_create: null argument");
+    if (cfg->dim != 2 && cfg->dim != 3) return fail(FLUID_ERR_INVALID_ARG, "fluid_create: dim must be 2 or 3");
+    if (cfg->grid_res <= 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_create: grid_res must be positive");
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        (void)cudaGetLastError();
+        return fail(FLUID_ERR_NO_DEVICE, "fluid_create: no CUDA device (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= n_dev) return fail(FLUID_ERR_INVALID_ARG, "fluid_create: bad device index");
+    CU_TRY(cudaSetDevice(device));
+    fluid_sim* s = new (std::nothrow) fluid_sim;
+    if (!s) return fail(FLUID_ERR_OUT_OF_MEMORY, "fluid_create: host allocation failed");
+    s->cfg = *cfg;
+    s->dim = cfg->dim;
+    s->device = device;
+    cudaError_t ce = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->d_mouse, 2 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->class_count, 4 * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->d_counter, sizeof(int));
+    for (int i = 0; i < N_EVENTS && ce == cudaSuccess; ++i) ce = cudaEventCreate(&s->ev[i]);
+    if (ce != cudaSuccess) {
+        fluid_destroy(s);
+        return fail(FLUID_ERR_CUDA, std::string("fluid_create: ") + cudaGetErrorString(ce));
+    }
+    s->stream = s->own_stream;
+    *out = s;
+    return FLUID_OK;
+}
+
+fluid_status fluid_destroy(fluid_sim* s) {
+    if (!s) return FLUID_OK;
+    cudaSetDevice(s->device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
+    cudaFree(s->cell_idx);
+    cudaFree(s->rank);
+    cudaFree(s->count);
+    cudaFree(s->start);
+    cudaFree(s->block_sums);
+    cudaFree(s->class_count);
+    cudaFree(s->grid);
+    cudaFree(s->d_mouse);
+    cudaFree(s->d_stage);
+    cudaFree(s->d_stage_ids);
+    cudaFree(s->d_counter);
+    for (int i = 0; i < N_EVENTS; ++i)
+        if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (cudaEvent_t e : s->pool) cudaEventDestroy(e);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    (void)cudaGetLastError();
+    delete s;
+    return FLUID_OK;
+}
+
+fluid_status fluid_set_stream(fluid_sim* s, void* cuda_stream) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_stream: null handle");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
+    return FLUID_OK;
+}
+
+fluid_status fluid_synchronize(fluid_sim* s) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_synchronize: null handle");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return FLUID_OK;
+}
+
+fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
+    if (!s || !mn || !mx) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_rect: null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    const int D = s->dim;
+    Geo g{};
+    g.dim = D;
+    const float res = static_cast<float>(s->cfg.grid_res);
+    int64_t nodes = 1, tiles = 1;
+    const int tshape[3] = {D == 3 ? Tile<3>::X : Tile<2>::X, D == 3 ? Tile<3>::Y : Tile<2>::Y,
+                           D == 3 ? Tile<3>::Z : 1};
+    for (int a = 0; a < 3; ++a) {
+        if (a < D) {
+            int kmin = host_block_key(mn[a], res), kmax = host_block_key(mx[a], res);
+            if (kmax < kmin) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_rect: max < min");
+            g.a_lo[a] = kmin;
+            g.a_hi[a] = kmax + 1;
+            g.p_lo[a] = kmin - 1;
+            g.p_hi[a] = kmax + 2;
+            int64_t sz = static_cast<int64_t>(g.p_hi[a] - g.p_lo[a]) * s->cfg.grid_res;
+            int64_t org = static_cast<int64_t>(g.p_lo[a]) * s->cfg.grid_res;
+            if (sz > (1 << 20) || org < INT_MIN / 2 || org > INT_MAX / 2)
+                return fail(FLUID_ERR_INVALID_ARG, "fluid_set_rect: rect too large");
+            g.size[a] = static_cast<int>(sz);
+            g.org[a] = static_cast<int>(org);
+        } else {
+            g.size[a] = 1;
+            g.a_hi[a] = g.p_hi[a] = 1;
+        }
+        g.tdim[a] = (g.size[a] + tshape[a] - 1) / tshape[a];
+        nodes *= g.size[a];
+        tiles *= g.tdim[a];
+    }
+    // the reference indexes the grid with i32 (3d:170-172); keep the same limit
+    if (nodes > INT_MAX / 2 || tiles * 256 > INT_MAX / 2)
+        return fail(FLUID_ERR_INVALID_ARG, "fluid_set_rect: grid exceeds 2^30 nodes");
+    g.n_tiles = static_cast<int>(tiles);
+    g.n_cells_pad = static_cast<int>(tiles * 256);
+    g.guard = 1 + g.size[0] + (D == 3 ? g.size[0] * g.size[1] : 0);
+    g.slab_lo = s->slab_lo;
+    g.slab_hi = s->slab_hi;
+    g.res_f = res;
+    g.dt = s->cfg.dt;
+    g.rest_density = s->cfg.rest_density;
+    g.mu = s->cfg.dynamic_viscosity;
+    g.stiffness = s->cfg.eos_stiffness;
+    g.power = s->cfg.eos_power;
+    g.mouse_r2 = s->cfg.mouse_radius * s->cfg.mouse_radius;
+    g.pclamp = s->cfg.pressure_clamp;
+    for (int a = 0; a < 3; ++a) {
+        g.dtg[a] = s->cfg.dt * s->cfg.gravity[a];
+        g.clip_lo[a] = s->cfg.clip_min[a];
+        g.clip_hi[a] = s->cfg.clip_max[a];
+        g.wall_lo[a] = s->cfg.clip_min[a] + s->cfg.boundary_damp_dist;
+        g.wall_hi[a] = s->cfg.clip_max[a] - s->cfg.boundary_damp_dist;
+    }
+
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    cudaFree(s->grid);
+    cudaFree(s->count);
+    cudaFree(s->start);
+    cudaFree(s->block_sums);
+    s->grid = nullptr;
+    s->count = s->start = s->block_sums = nullptr;
+    s->rect_set = false;
+    const int64_t m = static_cast<int64_t>(g.n_cells_pad) + 2;
+    const int64_t nb = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
+    CU_TRY(cudaMalloc(&s->count, (m + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->start, (m + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->block_sums, nb * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(s->grid, 0, (nodes + 2 * g.guard) * sizeof(float4), s->stream));
+    CU_TRY(cudaMemsetAsync(s->start, 0, (m + 8) * sizeof(int), s->stream));
+    s->grid_nodes = nodes;
+    s->bucket_len = m;
+    s->n_scan_blocks = nb;
+    s->geo = g;
+    s->rect_set = true;
+    return FLUID_OK;
+}
+
+fluid_status fluid_get_rects(const fluid_sim* s, int32_t a_lo[3], int32_t a_hi[3], int32_t p_lo[3],
+                             int32_t p_hi[3], int32_t grid_origin[3], int32_t grid_size[3]) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_get_rects: null handle");
+    if (!s->rect_set) return fail(FLUID_ERR_STATE, "fluid_get_rects: set_rect has not been called");
+    for (int a = 0; a < 3; ++a) {
+        if (a_lo) a_lo[a] = s->geo.a_lo[a];
+        if (a_hi) a_hi[a] = s->geo.a_hi[a];
+        if (p_lo) p_lo[a] = s->geo.p_lo[a];
+        if (p_hi) p_hi[a] = s->geo.p_hi[a];
+        if (grid_origin) grid_origin[a] = s->geo.org[a];
+        if (grid_size) grid_size[a] = s->geo.size[a];
+    }
+    return FLUID_OK;
+}
+
+static fluid_status add_from_device(fluid_sim* s, const float* d_rec, const int* d_ids, int64_t n) {
+    ST_TRY(ensure_capacity(s, s->n + n));
+    const int base_id = s->next_id;
+    if (s->dim == 3)
+        k_unpack_records<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(d_rec, d_ids, base_id, static_cast<int>(n),
+                                                                      s->buf[s->cur], static_cast<int>(s->n));
+    else
+        k_unpack_records<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(d_rec, d_ids, base_id, static_cast<int>(n),
+                                                                      s->buf[s->cur], static_cast<int>(s->n));
+    ++s->launches;
+    CU_TRY(cudaGetLastError());
+    s->n += n;
+    s->next_id += static_cast<int32_t>(n);
+    return FLUID_OK;
+}
+
+fluid_status fluid_add_particles(fluid_sim* s, const float* records, const int32_t* ids, int64_t n) {
+    if (!s || n < 0 || (n > 0 && !records)) return fail(FLUID_ERR_INVALID_ARG, "fluid_add_particles: bad argument");
+    if (n == 0) return FLUID_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    const int64_t floats = n * rec_floats(s->dim);
+    ST_TRY(ensure_stage(s, floats, ids ? n : 0));
+    CU_TRY(cudaMemcpyAsync(s->d_stage, records, floats * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    if (ids) CU_TRY(cudaMemcpyAsync(s->d_stage_ids, ids, n * sizeof(int), cudaMemcpyHostToDevice, s->stream));
+    ST_TRY(add_from_device(s, s->d_stage, ids ? s->d_stage_ids : nullptr, n));
+    if (ids) {
+        int32_t mx = *std::max_element(ids, ids + n);
+        s->next_id = std::max(s->next_id, mx + 1);
+    }
+    return FLUID_OK;
+}
+
+fluid_status fluid_add_particles_device(fluid_sim* s, const float* d_records, const int32_t* d_ids, int64_t n) {
+    if (!s || n < 0 || (n > 0 && !d_records)) return fail(FLUID_ERR_INVALID_ARG, "fluid_add_particles_device: bad argument");
+    if (n == 0) return FLUID_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    return add_from_device(s, d_records, d_ids, n);
+}
+
+fluid_status fluid_clear_particles(fluid_sim* s) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_clear_particles: null handle");
+    s->n = 0;
+    s->next_id = 0;
+    s->dropped_total = 0;
+    return FLUID_OK;
+}
+
+fluid_status fluid_substeps(fluid_sim* s, int32_t n_substeps, const float* mouse_xy) {
+    if (!s || n_substeps < 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_substeps: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    const float* d_mouse = nullptr;
+    ST_TRY(upload_mouse(s, mouse_xy, &d_mouse));
+    for (int32_t i = 0; i < n_substeps; ++i)
+        ST_TRY(substep(s, d_mouse, /*timed=*/i == n_substeps - 1, nullptr));
+    return FLUID_OK;
+}
+
+fluid_status fluid_step(fluid_sim* s, const float* mouse_xy) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_step: null handle");
+    return fluid_substeps(s, s->cfg.iterations, mouse_xy);   // 3d:111
+}
+
+fluid_status fluid_particle_counts(fluid_sim* s, int64_t counts[4]) {
+    if (!s || !counts) return fail(FLUID_ERR_INVALID_ARG, "fluid_particle_counts: null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    return refresh_counts(s, counts);
+}
+
+fluid_status fluid_particle_count(fluid_sim* s, int64_t* n_active) {
+    if (!s || !n_active) return fail(FLUID_ERR_INVALID_ARG, "fluid_particle_count: null argument");
+    int64_t c[4];
+    ST_TRY(fluid_particle_counts(s, c));
+    *n_active = c[0];
+    return FLUID_OK;
+}
+
+fluid_status fluid_read_particles(fluid_sim* s, float* records, int32_t* ids, int64_t capacity, int64_t* n_written) {
+    if (!s || capacity < 0 || (capacity > 0 && !records)) return fail(FLUID_ERR_INVALID_ARG, "fluid_read_particles: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    if (n_written) *n_written = 0;
+    if (s->n == 0 || !s->rect_set) return FLUID_OK;
+    const int rf = rec_floats(s->dim);
+    const int64_t cap = std::min<int64_t>(capacity, s->n);
+    ST_TRY(ensure_stage(s, std::max<int64_t>(cap, 1) * rf, std::max<int64_t>(cap, 1)));
+    CU_TRY(cudaMemsetAsync(s->d_counter, 0, sizeof(int), s->stream));
+    const int n = static_cast<int>(s->n);
+    if (s->dim == 3)
+        k_pack_active<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n, s->d_stage,
+                                                                   s->d_stage_ids, s->d_counter, static_cast<int>(cap));
+    else
+        k_pack_active<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n, s->d_stage,
+                                                                   s->d_stage_ids, s->d_counter, static_cast<int>(cap));
+    ++s->launches;
+    CU_TRY(cudaGetLastError());
+    int h = 0;
+    CU_TRY(cudaMemcpyAsync(&h, s->d_counter, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    if (n_written) *n_written = h;
+    if (h > capacity) return fail(FLUID_ERR_TOO_SMALL, "fluid_read_particles: capacity smaller than the active particle count");
+    if (h > 0) {
+        CU_TRY(cudaMemcpyAsync(records, s->d_stage, static_cast<int64_t>(h) * rf * sizeof(float), cudaMemcpyDeviceToHost, s->stream));
+        if (ids) CU_TRY(cudaMemcpyAsync(ids, s->d_stage_ids, static_cast<int64_t>(h) * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU_TRY(cudaStreamSynchronize(s->stream));
+    }
+    return FLUID_OK;
+}
+
+fluid_status fluid_get_dt(const fluid_sim* s, float* dt) {
+    if (!s || !dt) return fail(FLUID_ERR_INVALID_ARG, "fluid_get_dt: null argument");
+    *dt = s->cfg.dt;
+    return FLUID_OK;
+}
+
+fluid_status fluid_get_phase_times(fluid_sim* s, double seconds[FLUID_NUM_PHASES], double* sort_seconds) {
+    if (!s || !seconds) return fail(FLUID_ERR_INVALID_ARG, "fluid_get_phase_times: null argument");
+    for (int i = 0; i < FLUID_NUM_PHASES; ++i) seconds[i] = 0.0;
+    if (sort_seconds) *sort_seconds = 0.0;
+    if (!s->timers_recorded) return FLUID_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    const cudaEvent_t* ev = s->last_ev;
+    CU_TRY(cudaEventSynchronize(ev[N_EVENTS - 1]));
+    float ms[N_EVENTS - 1];
+    for (int i = 0; i < N_EVENTS - 1; ++i) CU_TRY(cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]));
+    if (sort_seconds) *sort_seconds = ms[0] * 1e-3;
+    seconds[0] = ms[1] * 1e-3;   // clear
+    seconds[1] = ms[2] * 1e-3;   // p2g 1
+    seconds[2] = ms[3] * 1e-3;   // p2g 2
+    seconds[3] = 0.0;            // update: folded into g2p's node read
+    seconds[4] = ms[4] * 1e-3;   // g2p
+    return FLUID_OK;
+}
+
+fluid_status fluid_profile_enable(fluid_sim* s, int32_t on) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_profile_enable: null handle");
+    CU_TRY(cudaSetDevice(s->device));
+    if (on) {
+        if (s->pool.empty()) {
+            s->pool.resize(static_cast<size_t>(PROFILE_POOL) * N_EVENTS, nullptr);
+            for (cudaEvent_t& e : s->pool) CU_TRY(cudaEventCreate(&e));
+        }
+        CU_TRY(cudaStreamSynchronize(s->stream));
+        s->pool_used = 0;
+        for (double& v : s->prof_sum) v = 0.0;
+        s->prof_substeps = 0;
+        s->profiling = true;
+    } else {
+        ST_TRY(profile_drain(s));
+        s->profiling = false;
+    }
+    return FLUID_OK;
+}
+
+fluid_status fluid_profile_read(fluid_sim* s, double seconds[6], int64_t* n_substeps) {
+    if (!s || !seconds) return fail(FLUID_ERR_INVALID_ARG, "fluid_profile_read: null argument");
+    CU_TRY(cudaSetDevice(s->device));
+    ST_TRY(profile_drain(s));
+    seconds[0] = s->prof_sum[0];   // sort
+    seconds[1] = s->prof_sum[1];   // clear
+    seconds[2] = s->prof_sum[2];   // p2g 1
+    seconds[3] = s->prof_sum[3];   // p2g 2
+    seconds[4] = 0.0;              // update (folded into g2p)
+    seconds[5] = s->prof_sum[4];   // g2p
+    if (n_substeps) *n_substeps = s->prof_substeps;
+    return FLUID_OK;
+}
+
+fluid_status fluid_debug_substep(fluid_sim* s, const float* mouse_xy, int64_t capacity, int32_t* ids, int32_t* cell,
+                                 int32_t* key, float* density, float* pressure, int64_t* n_written) {
+    if (!s || capacity < 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_debug_substep: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    if (n_written) *n_written = 0;
+    if (!s->rect_set || s->n == 0) return FLUID_OK;
+    const int D = s->dim;
+    const int64_t n = s->n;
+    int *d_ids = nullptr, *d_cell = nullptr, *d_key = nullptr;
+    float *d_den = nullptr, *d_prs = nullptr;
+    auto cleanup = [&]() {
+        cudaFree(d_ids); cudaFree(d_cell); cudaFree(d_key); cudaFree(d_den); cudaFree(d_prs);
+    };
+    cudaError_t ce = cudaMalloc(&d_ids, n * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_cell, n * D * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_key, n * D * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_den, n * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_prs, n * sizeof(float));
+    if (ce != cudaSuccess) {
+        cleanup();
+        return fail(FLUID_ERR_OUT_OF_MEMORY, "fluid_debug_substep: scratch allocation failed");
+    }
+    DebugTaps taps;
+    taps.ids = d_ids; taps.cell = d_cell; taps.key = d_key; taps.density = d_den; taps.pressure = d_prs;
+    const float* d_mouse = nullptr;
+    fluid_status st = upload_mouse(s, mouse_xy, &d_mouse);
+    if (st == FLUID_OK) st = substep(s, d_mouse, true, &taps);
+    int h_dep = 0;
+    if (st == FLUID_OK) {
+        ce = cudaMemcpyAsync(&h_dep, s->start + s->geo.n_cells_pad, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->stream);
+        if (ce != cudaSuccess) st = fail(FLUID_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    if (st == FLUID_OK) {
+        if (n_written) *n_written = h_dep;
+        if (h_dep > capacity) st = fail(FLUID_ERR_TOO_SMALL, "fluid_debug_substep: capacity too small");
+    }
+    if (st == FLUID_OK && h_dep > 0) {
+        if (ids) cudaMemcpy(ids, d_ids, h_dep * sizeof(int), cudaMemcpyDeviceToHost);
+        if (cell) cudaMemcpy(cell, d_cell, static_cast<int64_t>(h_dep) * D * sizeof(int), cudaMemcpyDeviceToHost);
+        if (key) cudaMemcpy(key, d_key, static_cast<int64_t>(h_dep) * D * sizeof(int), cudaMemcpyDeviceToHost);
+        if (density) cudaMemcpy(density, d_den, h_dep * sizeof(float), cudaMemcpyDeviceToHost);
+        if (pressure) cudaMemcpy(pressure, d_prs, h_dep * sizeof(float), cudaMemcpyDeviceToHost);
+        ce = cudaGetLastError();
+        if (ce != cudaSuccess) st = fail(FLUID_ERR_CUDA, cudaGetErrorString(ce));
+    }
+    cleanup();
+    return st;
+}
+
+fluid_status fluid_debug_neighbour_table(fluid_sim* s, int64_t capacity, int32_t* ids, int32_t* cell_index,
+                                         int64_t* n_written) {
+    if (!s || capacity < 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_debug_neighbour_table: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    if (n_written) *n_written = 0;
+    if (!s->rect_set || s->n == 0) return FLUID_OK;
+    const int64_t n = s->n;
+    ST_TRY(s->dim == 3 ? sort_particles<3>(s) : sort_particles<2>(s));
+    int *d_ids = nullptr, *d_ref = nullptr;
+    cudaError_t ce = cudaMalloc(&d_ids, n * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&d_ref, n * sizeof(int));
+    if (ce != cudaSuccess) {
+        cudaFree(d_ids); cudaFree(d_ref);
+        return fail(FLUID_ERR_OUT_OF_MEMORY, "fluid_debug_neighbour_table: scratch allocation failed");
+    }
+    const int* n_dep = s->start + s->geo.n_cells_pad;
+    if (s->dim == 3)
+        k_debug_keys<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n_dep, d_ids, nullptr, nullptr, d_ref);
+    else
+        k_debug_keys<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n_dep, d_ids, nullptr, nullptr, d_ref);
+    ++s->launches;
+    int h_dep = 0;
+    fluid_status st = FLUID_OK;
+    ce = cudaMemcpyAsync(&h_dep, n_dep, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->stream);
+    if (ce != cudaSuccess) st = fail(FLUID_ERR_CUDA, cudaGetErrorString(ce));
+    if (st == FLUID_OK) {
+        if (n_written) *n_written = h_dep;
+        if (h_dep > capacity) st = fail(FLUID_ERR_TOO_SMALL, "fluid_debug_neighbour_table: capacity too small");
+    }
+    if (st == FLUID_OK && h_dep > 0) {
+        if (ids) cudaMemcpy(ids, d_ids, h_dep * sizeof(int), cudaMemcpyDeviceToHost);
+        if (cell_index) cudaMemcpy(cell_index, d_ref, h_dep * sizeof(int), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d_ids);
+    cudaFree(d_ref);
+    return st;
+}
+
+fluid_status fluid_read_grid(fluid_sim* s, float* nodes, int64_t capacity_nodes, int64_t* n_nodes) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_read_grid: null handle");
+    if (!s->rect_set) return fail(FLUID_ERR_STATE, "fluid_read_grid: set_rect has not been called");
+    CU_TRY(cudaSetDevice(s->device));
+    if (n_nodes) *n_nodes = s->grid_nodes;
+    if (!nodes) return FLUID_OK;
+    if (capacity_nodes < s->grid_nodes) return fail(FLUID_ERR_TOO_SMALL, "fluid_read_grid: capacity too small");
+    const int D = s->dim;
+    float* d_out = nullptr;
+    CU_TRY(cudaMalloc(&d_out, s->grid_nodes * (D + 1) * sizeof(float)));
+    const int n = static_cast<int>(s->grid_nodes);
+    if (D == 3) k_export_grid<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid, n, d_out);
+    else k_export_grid<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid, n, d_out);
+    ++s->launches;
+    cudaError_t ce = cudaMemcpyAsync(nodes, d_out, s->grid_nodes * (D + 1) * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->stream);
+    cudaFree(d_out);
+    if (ce != cudaSuccess) return fail(FLUID_ERR_CUDA, cudaGetErrorString(ce));
+    return FLUID_OK;
+}
+
+fluid_status fluid_launch_count(const fluid_sim* s, int64_t* launches) {
+    if (!s || !launches) return fail(FLUID_ERR_INVALID_ARG, "fluid_launch_count: null argument");
+    *launches = s->launches;
+    return FLUID_OK;
+}
+
+// ---- z-slab decomposition: not built yet (round-1 scope note in DESIGN.md) -----------------
+fluid_status fluid_slab_set(fluid_sim* s, int32_t, int32_t) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_set: null handle");
+    return fail(FLUID_ERR_STATE, "fluid_slab_set: slab decomposition is not implemented yet");
+}
+fluid_status fluid_slab_halo(fluid_sim*, int32_t, void**, void**, int64_t*) {
+    return fail(FLUID_ERR_STATE, "fluid_slab_halo: slab decomposition is not implemented yet");
+}
+fluid_status fluid_slab_phase(fluid_sim*, int32_t, const float*) {
+    return fail(FLUID_ERR_STATE, "fluid_slab_phase: slab decomposition is not implemented yet");
+}
+fluid_status fluid_slab_accumulate_halo(fluid_sim*, int32_t) {
+    return fail(FLUID_ERR_STATE, "fluid_slab_accumulate_halo: slab decomposition is not implemented yet");
+}
+fluid_status fluid_slab_migrants(fluid_sim*, int32_t, void**, int64_t*) {
+    return fail(FLUID_ERR_STATE, "fluid_slab_migrants: slab decomposition is not implemented yet");
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+/*
+ * fluid_b200.h — C ABI of the B200-native step engine (libfluid_b200.so).
+ *
+ * This is the drop-in boundary for the particle-state and step entry points of
+ * GossiperLoturot/fluid-rs (`struct Simulation`, src/3d_multi.rs:50-134,383-387 and
+ * src/2d_multi.rs:50-134,361-365).  The reference has no FFI of its own; the entry points
+ * below are what a `extern "C"` block in the Rust binaries would bind (INTEGRATION.md shows
+ * that block).  Plain pointers and sizes only — no torch / C++ types cross this boundary.
+ *
+ * Conventions
+ *   - every call returns a fluid_status; nothing unwinds across the boundary (the reference
+ *     panics via unwrap(), 3d:138,150,173,...; here invariant violations become codes);
+ *   - a handle is single-owner and not thread-safe (the reference takes &mut self everywhere);
+ *   - all device work of one handle is issued on one CUDA stream; calls are asynchronous
+ *     unless they return data to host memory;
+ *   - host particle records are packed f32, the field order of `struct Particle`
+ *     (3d:35-41 / 2d:35-41):   3D: pos[3] vel[3] C[9] mass  (16 floats, C column-major,
+ *     C[3*col+row] as glam Mat3), 2D: pos[2] vel[2] C[4] mass (9 floats).
+ */
+#ifndef FLUID_B200_H
+#define FLUID_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FLUID_B200_ABI_VERSION 1
+
+typedef enum fluid_status {
+    FLUID_OK = 0,
+    FLUID_ERR_INVALID_ARG = 1,   /* null pointer, bad dim, negative count ...            */
+    FLUID_ERR_CUDA = 2,          /* a CUDA runtime call failed; see fluid_last_error()   */
+    FLUID_ERR_NO_DEVICE = 3,     /* no CUDA device: there is NO CPU fallback             */
+    FLUID_ERR_OUT_OF_MEMORY = 4,
+    FLUID_ERR_STATE = 5,         /* call not valid in this state (e.g. slab not set)     */
+    FLUID_ERR_TOO_SMALL = 6      /* caller buffer smaller than the data to return        */
+} fluid_status;
+
+/* Mirrors `struct Config` (3d:3-15 / 2d:3-15).  Vectors are padded to 3 floats; 2D ignores
+ * the z lane.  `pressure_clamp` is the literal lower bound of the Tait pressure, which the
+ * reference hard-codes per binary (3d:218 = -0.1, 2d:212 = -0.0). */
+typedef struct fluid_config {
+    int32_t dim;                 /* 2 or 3                                                */
+    float   dt;                  /* 3d:20 0.066 | 2d:20 0.032                             */
+    int32_t iterations;          /* 3d:21 (1.0/0.032) as i32 = 31                         */
+    int32_t grid_res;            /* 3d:22 16    | 2d:22 32   cells per block edge         */
+    float   gravity[3];          /* 3d:23 (0,0.3,0)                                       */
+    float   rest_density;        /* 3d:24 1.0   | 2d:24 4.0                               */
+    float   dynamic_viscosity;   /* 3d:25 0.1                                             */
+    float   eos_stiffness;       /* 3d:26 10.0                                            */
+    float   eos_power;           /* 3d:27 4.0                                             */
+    float   mouse_radius;        /* 3d:28 10.0                                            */
+    float   clip_min[3];         /* 3d:29 boundary_clip.0                                 */
+    float   clip_max[3];         /* 3d:29 boundary_clip.1                                 */
+    float   boundary_damp_dist;  /* 3d:30 3.0                                             */
+    float   pressure_clamp;      /* 3d:218 -0.1 | 2d:212 -0.0                             */
+} fluid_config;
+
+typedef struct fluid_sim fluid_sim;   /* opaque; owns all device memory */
+
+/* Labels of the five phase timers, in the order of `debug_elapseds` (3d:112-132). */
+#define FLUID_NUM_PHASES 5
+/* "clear", "p2g 1", "p2g 2", "update", "g2p" */
+
+/* ---- library ---------------------------------------------------------------------- */
+int32_t      fluid_abi_version(void);
+/* Message of the last failing call on this thread ("" if none). */
+const char*  fluid_last_error(void);
+/* `Config::default()` of the 2D / 3D binary (3d:17-33 / 2d:17-33). */
+fluid_status fluid_config_default(int32_t dim, fluid_config* out);
+
+/* ---- lifecycle: Simulation::new (3d:64-77) ------------------------------------------ */
+fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** out);
+fluid_status fluid_destroy(fluid_sim* sim);
+/* Issue all later work of this handle on `cuda_stream` (a cudaStream_t / CUstream; NULL =
+ * the handle's own stream).  Lets a host framework time or order the work with its own
+ * events. */
+fluid_status fluid_set_stream(fluid_sim* sim, void* cuda_stream);
+fluid_status fluid_synchronize(fluid_sim* sim);
+
+/* ---- Simulation::set_rect (3d:79-102) ----------------------------------------------- */
+/* a_rect = [key(min), key(max)+1), p_rect = a_rect grown by one block; (re)allocates the
+ * dense node grid over p_rect.  May be called before or after particles are added; does not
+ * remove particles.  min/max hold `dim` floats. */
+fluid_status fluid_set_rect(fluid_sim* sim, const float* min, const float* max);
+/* Rect read-back: a_rect/p_rect as block keys (lo[dim], hi[dim]), grid origin cell and
+ * grid size in cells (3d:94). */
+fluid_status fluid_get_rects(const fluid_sim* sim, int32_t a_lo[3], int32_t a_hi[3],
+                             int32_t p_lo[3], int32_t p_hi[3],
+                             int32_t grid_origin[3], int32_t grid_size[3]);
+
+/* ---- Simulation::add_particle (3d:104-108), bulk ------------------------------------- */
+/* Append n packed host records.  `ids` may be NULL (ids continue from the running count).
+ * The reference pushes one particle per call; a bulk array is the same operation n times. */
+fluid_status fluid_add_particles(fluid_sim* sim, const float* records, const int32_t* ids,
+                                 int64_t n);
+/* Same, records already resident in device memory (same packed layout). */
+fluid_status fluid_add_particles_device(fluid_sim* sim, const float* d_records,
+                                        const int32_t* d_ids, int64_t n);
+/* Remove all particles (no reference equivalent; needed to reuse a handle). */
+fluid_status fluid_clear_particles(fluid_sim* sim);
+
+/* ---- Simulation::step (3d:110-134) --------------------------------------------------- */
+/* Runs config.iterations substeps of clear -> p2g 1 -> p2g 2 -> update -> g2p.
+ * mouse_xy: NULL for `None`, else two floats (world x,y) for `Some(Vec2)` (3d:305-310). */
+fluid_status fluid_step(fluid_sim* sim, const float* mouse_xy);
+/* Same phases, an explicit number of substeps (bench / parity harness). */
+fluid_status fluid_substeps(fluid_sim* sim, int32_t n_substeps, const float* mouse_xy);
+
+/* ---- Simulation::iter_particle (3d:383-387) ------------------------------------------ */
+/* Number of particles `iter_particle` would yield (those stored in a_rect blocks). */
+fluid_status fluid_particle_count(fluid_sim* sim, int64_t* n_active);
+/* Counts by class: [0] in a_rect blocks (advanced), [1] in the p_rect halo ring (deposit to
+ * the grid but frozen, 3d:149 vs 3d:263), [2] outside p_rect (kept, ignored), [3] dropped so
+ * far by migration out of p_rect (3d:356-366). */
+fluid_status fluid_particle_counts(fluid_sim* sim, int64_t counts[4]);
+/* Copy the a_rect particles to host: records (packed, capacity*floats_per_record) and ids
+ * (may be NULL).  Order is unspecified, as in the reference (block order x shuffled Vec
+ * order); use ids to match.  *n_written receives the count. */
+fluid_status fluid_read_particles(fluid_sim* sim, float* records, int32_t* ids,
+                                  int64_t capacity, int64_t* n_written);
+
+/* ---- fields main/draw read: sim.config.dt (3d:541), sim.debug_elapseds (3d:502) ------- */
+fluid_status fluid_get_dt(const fluid_sim* sim, float* dt);
+/* Seconds spent in the five phases of the LAST substep of the last step call (the reference
+ * clears the list every substep, 3d:112).  Blocks until that substep has finished.
+ * Neighbour-search work (keys, sort, reorder) is reported separately in *sort_seconds
+ * (may be NULL); it has no reference counterpart (the hash-of-Vecs is maintained in g2p). */
+fluid_status fluid_get_phase_times(fluid_sim* sim, double seconds[FLUID_NUM_PHASES],
+                                   double* sort_seconds);
+const char*  fluid_phase_label(int32_t phase);
+/* Profile mode: CUDA events around every phase of EVERY substep, summed until read.  on=1
+ * (re)starts with zeroed sums, on=0 stops.  seconds[0..5] = sort, clear, p2g 1, p2g 2, update,
+ * g2p.  The kernels launched are the same with or without it. */
+fluid_status fluid_profile_enable(fluid_sim* sim, int32_t on);
+fluid_status fluid_profile_read(fluid_sim* sim, double seconds[6], int64_t* n_substeps);
+
+/* ---- parity / debug (no reference equivalent; test harness only) ---------------------- */
+/* Run ONE substep and return, per p_rect particle in the engine's sorted order:
+ * id, cell (floor(pos), 3d:153), block key (3d:398-401), density and pressure (locals at
+ * 3d:198,217).  Any pointer may be NULL.  cell/key hold dim ints per particle. */
+fluid_status fluid_debug_substep(fluid_sim* sim, const float* mouse_xy, int64_t capacity,
+                                 int32_t* ids, int32_t* cell, int32_t* key,
+                                 float* density, float* pressure, int64_t* n_written);
+/* Neighbour tables of the current state, built from the current positions: per p_rect
+ * particle (sorted order) its id and linear cell index in the reference's layout
+ * (x + y*sx + z*sx*sy over the p_rect grid, 3d:169-172).  Sorted order is non-decreasing in
+ * the engine's tiled cell order; `cell_index` lets a checker rebuild cellStart/cellEnd. */
+fluid_status fluid_debug_neighbour_table(fluid_sim* sim, int64_t capacity, int32_t* ids,
+                                         int32_t* cell_index, int64_t* n_written);
+/* Node grid after the last substep, reference layout: vel_or_momentum[dim] then mass, per
+ * node, x fastest (3d:169-172).  `stage`: 0 = as left by the last substep (velocities after
+ * update where mass>0). capacity in nodes. */
+fluid_status fluid_read_grid(fluid_sim* sim, float* nodes, int64_t capacity_nodes,
+                             int64_t* n_nodes);
+/* Number of kernels this handle has launched so far (bench `gpu_launches`). */
+fluid_status fluid_launch_count(const fluid_sim* sim, int64_t* launches);
+
+/* ---- multi-GPU: z-slab decomposition (no reference equivalent) --- */
+/* Restrict this handle to the slab of node planes [z_lo, z_hi) (cells, world coords; for 2D
+ * the slab axis is y).  Particles whose cell is outside the slab are exported by
+ * fluid_slab_collect_migrants.  The caller (one process per GPU) moves halo planes and
+ * migrants between ranks (NCCL / peer copies) using the device pointers returned here. */
+fluid_status fluid_slab_set(fluid_sim* sim, int32_t lo, int32_t hi);
+/* Device pointer + node count of the `which` halo plane pair: 0 = low side, 1 = high side.
+ * Each is two contiguous node planes of float4 {momentum.xyz, mass}: the plane just outside
+ * the slab followed/preceded by the outermost owned plane. */
+fluid_status fluid_slab_halo(fluid_sim* sim, int32_t which, void** d_send, void** d_recv,
+                             int64_t* n_float4);
+/* Split substep for slab runs: phase A = sort + clear + p2g 1 (then exchange+add halos),
+ * phase B = p2g 2 (then exchange+add halos), phase C = update + g2p + migrant collection. */
+fluid_status fluid_slab_phase(fluid_sim* sim, int32_t phase, const float* mouse_xy);
+/* Add the received halo planes (d_recv buffers) into the grid. */
+fluid_status fluid_slab_accumulate_halo(fluid_sim* sim, int32_t which);
+/* Migrants leaving through side `which` after phase C: device pointer to packed records
+ * (17 words: 16 floats + id) and their count (host value, synchronises the stream). */
+fluid_status fluid_slab_migrants(fluid_sim* sim, int32_t which, void** d_records,
+                                 int64_t* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FLUID_B200_H */

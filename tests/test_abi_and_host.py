@@ -1,0 +1,129 @@
+"""CPU-side checks of the boundary and the host logic: the C-ABI library loads and exports every
+symbol include/fluid_b200.h declares, the ctypes structs match the header, the engine refuses
+to run without a GPU (no CPU fallback), and the product never touches oracle/."""
+import ctypes as C
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def header_functions():
+    text = (ROOT / "include" / "fluid_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(fluid_[a-z0-9_]+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_header_declares_the_reference_entry_points():
+    names = header_functions()
+    for must in ("fluid_create", "fluid_set_rect", "fluid_add_particles", "fluid_step",
+                 "fluid_read_particles", "fluid_get_dt", "fluid_get_phase_times"):
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    L = pkg.lib()
+    for name in header_functions():
+        assert hasattr(L, name), f"{name} declared in include/fluid_b200.h but not exported"
+
+
+def test_binding_covers_header(pkg):
+    assert sorted(pkg.SIGNATURES) == header_functions()
+
+
+def test_library_is_sm100a_and_has_our_kernels(pkg):
+    out = subprocess.run(["cuobjdump", "-lelf", str(pkg.LIB_PATH)], capture_output=True, text=True)
+    assert "sm_100a" in out.stdout
+    syms = subprocess.run(["cuobjdump", "-sass", str(pkg.LIB_PATH)], capture_output=True, text=True).stdout
+    for k in ("k_classify_count", "k_reorder", "k_scan_final"):
+        assert k in syms
+
+
+def test_config_struct_matches_header(pkg):
+    # layout as the C compiler sees include/fluid_b200.h, field order of `struct Config` (3d:3-15)
+    import tempfile
+    src = '#include <stdio.h>\n#include <stddef.h>\n#include "fluid_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu\\n",' \
+          'sizeof(fluid_config), offsetof(fluid_config, gravity), offsetof(fluid_config, clip_min),' \
+          'offsetof(fluid_config, boundary_damp_dist), offsetof(fluid_config, pressure_clamp));return 0;}'
+    with tempfile.TemporaryDirectory() as td:
+        (Path(td) / "a.c").write_text(src)
+        subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", f"{td}/a", f"{td}/a.c"], check=True)
+        got = [int(x) for x in subprocess.run([f"{td}/a"], capture_output=True, text=True).stdout.split()]
+    F = pkg.FluidConfig
+    assert got == [C.sizeof(F), F.gravity.offset, F.clip_min.offset, F.boundary_damp_dist.offset,
+                   F.pressure_clamp.offset]
+    c3, c2 = pkg.default_config(3), pkg.default_config(2)
+    assert (c3.dim, c3.grid_res, c3.iterations) == (3, 16, 31)
+    assert (c2.dim, c2.grid_res, c2.iterations) == (2, 32, 31)
+    assert c3.dt == np.float32(0.066) and c2.dt == np.float32(0.032)
+    assert c3.rest_density == 1.0 and c2.rest_density == 4.0
+    assert c3.pressure_clamp == np.float32(-0.1) and c2.pressure_clamp == 0.0
+    assert list(c3.gravity) == [0.0, np.float32(0.3), 0.0]
+    assert list(c3.clip_max) == [64.0, 64.0, 64.0] and c3.boundary_damp_dist == 3.0
+
+
+def test_python_default_config_matches_c(pkg, scenes):
+    for dim in (2, 3):
+        d = scenes.default_config(dim)
+        c = pkg.config_from_dict(d)
+        ref = pkg.default_config(dim)
+        assert bytes(c) == bytes(ref)
+
+
+def test_abi_version_and_labels(pkg):
+    L = pkg.lib()
+    assert L.fluid_abi_version() == 1
+    assert [L.fluid_phase_label(i).decode() for i in range(5)] == ["clear", "p2g 1", "p2g 2", "update", "g2p"]
+
+
+def test_argument_errors_are_status_codes_not_crashes(pkg):
+    L = pkg.lib()
+    assert L.fluid_create(None, 0, None) == 1            # FLUID_ERR_INVALID_ARG
+    assert b"null" in L.fluid_last_error()
+    bad = pkg.default_config(3)
+    bad.dim = 4
+    h = C.c_void_p()
+    assert L.fluid_create(C.byref(bad), 0, C.byref(h)) == 1
+    assert L.fluid_step(None, None) == 1
+    assert L.fluid_destroy(None) == 0
+
+
+def test_no_cpu_fallback_without_a_device(pkg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(pkg.FluidError) as e:
+        pkg.Simulation.new(pkg.default_config(3))
+    assert e.value.status == 3                           # FLUID_ERR_NO_DEVICE
+
+
+def test_product_never_references_the_oracle():
+    for p in list((ROOT / "fluid-rs_b200").rglob("*")) + list((ROOT / "include").rglob("*")):
+        if p.is_file() and p.suffix in (".py", ".cu", ".cuh", ".h", ".hpp", ".cpp"):
+            text = p.read_text()
+            for needle in ("liboracle", "from oracle", "import oracle", "oracle.py", "orc_", "oracle.cpp"):
+                assert needle not in text, (p, needle)
+
+
+def test_scene_generator_is_counter_based(scenes):
+    sc = scenes.dam_break_1m()
+    a = sc.records(0, 1000)
+    b = sc.records(500, 100)
+    np.testing.assert_array_equal(a[500:600], b)         # any index range regenerates exactly
+    assert sc.n == 1 << 20 and list(sc.rect_max) == [384.0, 96.0, 134.0]
+    assert sc.cfg["gravity"][1] == pytest.approx(4.8 / 64)
+    pos = a[:, :3]
+    assert (pos >= sc.fill_lo).all() and (pos <= sc.fill_hi).all()
+    assert scenes.dam_break_16m().n == 1 << 24 and scenes.dam_break_128m().n == 1 << 27
+    assert scenes.dam_break_for_gpus(8).n == 1 << 27 and scenes.dam_break_for_gpus(2).n == 1 << 25
+
+
+def test_splitmix_known_values(scenes):
+    # splitmix64 reference outputs for state 0: first output 0xE220A8397B1DCDAF
+    z = scenes.splitmix64(np.array([0], dtype=np.uint64))
+    assert int(z[0]) == 0xE220A8397B1DCDAF

@@ -1,0 +1,366 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the same
+seeded inputs.  Bars (BASELINE.json north_star):
+  * cell assignment, block keys and per-cell neighbour sets: BIT-EXACT;
+  * density, pressure, velocity, position, affine matrix after one substep: 1e-5, stated as
+    |gpu - ref| <= 1e-5 * max(|ref|, scale) with scale = rest_density (density), eos_stiffness
+    (pressure; the clamp value is 0 in 2D so a pure relative bound is undefined, and
+    (rho/rho0)^4 - 1 cancels near rho0), inf-norm of the field (velocity, C), box size (pos);
+  * long runs: aggregate invariants (count, mass, mean density error, kinetic energy,
+    free-surface height), because summation order differs and trajectories are chaotic.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+
+
+def build_pair(pkg, orc, cfg, records, rect_min, rect_max, ids=None):
+    sim = pkg.Simulation.new(cfg, device=0)
+    sim.add_particles(records, ids)
+    sim.set_rect(rect_min, rect_max)
+    ref = orc.OracleSim(cfg)
+    ref.add_particles(records, ids)
+    ref.set_rect(rect_min, rect_max)
+    return sim, ref
+
+
+def oracle_substep_with_taps(ref):
+    for ph in range(5):
+        ref.phase(ph)
+        if ph == 2:
+            taps = ref.read(which=1, debug=True)
+            grid_mass = ref.read_grid()[:, -1].copy()
+    return taps, grid_mass
+
+
+def scaled_err(a, b, scale):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), scale)))
+
+
+def randomised(scene, seed=5, vel=0.3, aff=0.05):
+    d = scene.dim
+    rec = scene.records()
+    rng = np.random.default_rng(seed)
+    rec[:, d:2 * d] = rng.normal(0, vel, (scene.n, d)).astype(np.float32)
+    rec[:, 2 * d:2 * d + d * d] = rng.normal(0, aff, (scene.n, d * d)).astype(np.float32)
+    rec[:, -1] = rng.uniform(0.5, 1.5, scene.n).astype(np.float32)
+    return rec
+
+
+def check_one_substep(pkg, orc, scene, rec, mouse=None):
+    d = scene.dim
+    sim, ref = build_pair(pkg, orc, scene.cfg, rec, scene.rect_min, scene.rect_max)
+    g = sim.debug_substep(mouse)
+    for ph in range(5):
+        ref.phase(ph, mouse)
+        if ph == 2:
+            taps = ref.read(which=1, debug=True)
+    go, ro = np.argsort(g["ids"]), np.argsort(taps["ids"])
+    assert np.array_equal(g["ids"][go], taps["ids"][ro])
+    # integer outputs: bit-exact
+    np.testing.assert_array_equal(g["cell"][go], taps["cell"][ro])
+    np.testing.assert_array_equal(g["key"][go], taps["key"][ro])
+    # per-particle density / pressure
+    assert scaled_err(g["density"][go], taps["density"][ro], scene.cfg["rest_density"]) < TOL
+    assert scaled_err(g["pressure"][go], taps["pressure"][ro], scene.cfg["eos_stiffness"]) < TOL
+    # state after the substep
+    g_rec, g_ids = sim.read_particles(sort_by_id=True)
+    r_rec, r_ids = ref.read()
+    o = np.argsort(r_ids)
+    r_rec, r_ids = r_rec[o], r_ids[o]
+    assert np.array_equal(g_ids, r_ids)
+    vs = max(float(np.abs(r_rec[:, d:2 * d]).max()), 1e-3)
+    cs = max(float(np.abs(r_rec[:, 2 * d:2 * d + d * d]).max()), 1e-3)
+    assert scaled_err(g_rec[:, d:2 * d], r_rec[:, d:2 * d], vs) < TOL                      # velocity
+    assert scaled_err(g_rec[:, 2 * d:2 * d + d * d], r_rec[:, 2 * d:2 * d + d * d], cs) < TOL  # affine C
+    assert scaled_err(g_rec[:, :d], r_rec[:, :d], float(max(scene.rect_max))) < TOL          # position
+    np.testing.assert_array_equal(g_rec[:, -1], r_rec[:, -1])                              # mass untouched
+    # node grid (velocities after update_grid, masses)
+    gg, rg = sim.read_grid(), ref.read_grid()
+    assert gg.shape == rg.shape
+    ms = max(float(rg[:, -1].max()), 1e-3)
+    assert scaled_err(gg[:, -1], rg[:, -1], ms) < TOL
+    live = rg[:, -1] > 1e-4 * ms      # node velocity = mom/mass is ill-conditioned where mass ~ 0
+    gs = max(float(np.abs(rg[live, :d]).max()), 1e-3)
+    assert scaled_err(gg[live, :d], rg[live, :d], gs) < 5 * TOL
+    sim.close()
+    ref.close()
+
+
+# ---- BASELINE configs 1 and 2 (reference default scenes) ------------------------------------------
+
+def test_config1_2d_default_one_substep(pkg, orc, scenes):
+    sc = scenes.default_2d()
+    check_one_substep(pkg, orc, sc, sc.records())
+
+
+def test_config2_3d_default_one_substep(pkg, orc, scenes):
+    sc = scenes.default_3d()
+    check_one_substep(pkg, orc, sc, sc.records())
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_randomised_state_one_substep(pkg, orc, scenes, dim):
+    sc = scenes.default_2d() if dim == 2 else scenes.default_3d()
+    check_one_substep(pkg, orc, sc, randomised(sc))
+
+
+def test_mouse_push_one_substep(pkg, orc, scenes):
+    sc = scenes.default_3d()
+    check_one_substep(pkg, orc, sc, randomised(sc), mouse=[24.0, 24.0])
+
+
+def test_dam_break_small_one_substep(pkg, orc, scenes):
+    sc = scenes.dam_break_3d(48, 32, 40)      # 61,440 particles, same construction as configs 3-5
+    check_one_substep(pkg, orc, sc, sc.records())
+
+
+def test_non_power_of_two_grid_res(pkg, orc, scenes):
+    sc = scenes.default_3d(3000)
+    sc.cfg["grid_res"] = 10
+    check_one_substep(pkg, orc, sc, randomised(sc))
+
+
+# ---- golden fixtures (oracle self-goldens, committed) ----------------------------------------------
+
+@pytest.mark.parametrize("name,dim", [("oracle_3d_default_256_s31", 3), ("oracle_2d_default_256_s31", 2)])
+def test_against_committed_golden(pkg, scenes, name, dim):
+    from pathlib import Path
+    g = np.load(Path(__file__).parent / "golden" / f"{name}.npz")
+    sc = scenes.default_3d(256) if dim == 3 else scenes.default_2d(256)
+    sim = pkg.Simulation.new(sc.cfg)
+    sim.add_particles(g["records0"])
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    t = sim.debug_substep()
+    o = np.argsort(t["ids"])
+    np.testing.assert_array_equal(t["cell"][o], g["cell0"])
+    np.testing.assert_array_equal(t["key"][o], g["key0"])
+    assert scaled_err(t["density"][o], g["density1"], sc.cfg["rest_density"]) < TOL
+    assert scaled_err(t["pressure"][o], g["pressure1"], sc.cfg["eos_stiffness"]) < TOL
+    sim.substeps(sc.cfg["iterations"] - 1)
+    rec, ids = sim.read_particles(sort_by_id=True)
+    # 31 substeps: rounding differences grow, so a looser, stated bound: 2e-3 cells
+    assert np.abs(rec[:, :dim] - g["records"][:, :dim]).max() < 2e-3
+    sim.close()
+
+
+# ---- neighbour search -------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_neighbour_sets_bit_exact(pkg, orc, scenes, dim):
+    """cellStart/cellEnd + sorted ids: each cell holds exactly the ids the oracle puts there."""
+    sc = scenes.default_2d(4096) if dim == 2 else scenes.dam_break_3d(40, 24, 24)
+    rec = sc.records()
+    sim, ref = build_pair(pkg, orc, sc.cfg, rec, sc.rect_min, sc.rect_max)
+    for _ in range(3):                       # let particles cross cells and blocks first
+        ids, cidx = sim.neighbour_table()
+        r = ref.read(which=1, debug=True)
+        rr = ref.rects()
+        rel = r["cell"] - rr["origin"]
+        ref_idx = rel[:, 0] + rel[:, 1] * rr["size"][0]
+        if dim == 3:
+            ref_idx = ref_idx + rel[:, 2] * rr["size"][0] * rr["size"][1]
+        # the engine's own positions decide its cells; compare on identical inputs:
+        g_rec, g_ids = sim.read_particles(sort_by_id=True)
+        _, cell_of_gpu_pos = orc.key_from_pos(g_rec[:, :dim], sc.cfg["grid_res"])
+        rel_g = cell_of_gpu_pos - rr["origin"]
+        want = rel_g[:, 0] + rel_g[:, 1] * rr["size"][0]
+        if dim == 3:
+            want = want + rel_g[:, 2] * rr["size"][0] * rr["size"][1]
+        o = np.argsort(ids)
+        assert np.array_equal(ids[o], g_ids)
+        np.testing.assert_array_equal(cidx[o], want)
+        # particles of one cell are contiguous in the sorted order (cellStart/cellEnd exist)
+        change = np.flatnonzero(np.diff(cidx) != 0)
+        runs = np.split(cidx, change + 1)
+        assert len(set(int(x[0]) for x in runs)) == len(runs)
+        sim.substeps(7)
+        ref.substeps(7)
+    sim.close()
+    ref.close()
+
+
+def test_first_substep_neighbour_sets_match_oracle_exactly(pkg, orc, scenes):
+    sc = scenes.default_3d()
+    rec = sc.records()
+    sim, ref = build_pair(pkg, orc, sc.cfg, rec, sc.rect_min, sc.rect_max)
+    ids, cidx = sim.neighbour_table()
+    r = ref.read(which=1, debug=True)
+    rr = ref.rects()
+    rel = r["cell"] - rr["origin"]
+    ref_idx = rel[:, 0] + rel[:, 1] * rr["size"][0] + rel[:, 2] * rr["size"][0] * rr["size"][1]
+    g = {}
+    for i, c in zip(ids.tolist(), cidx.tolist()):
+        g.setdefault(c, set()).add(i)
+    w = {}
+    for i, c in zip(r["ids"].tolist(), ref_idx.tolist()):
+        w.setdefault(c, set()).add(i)
+    assert g == w
+
+
+# ---- edge cases --------------------------------------------------------------------------------------
+
+def test_empty_and_unset(pkg, scenes):
+    sim = pkg.Simulation.new(scenes.default_config(3))
+    sim.step()                                        # no rect, no particles: nothing to walk
+    assert sim.particle_count() == 0
+    sim.set_rect([0, 0, 0], [64, 64, 64])
+    sim.step()
+    rec, ids = sim.read_particles()
+    assert rec.shape[0] == 0
+    sim.add_particle([20.5, 20.5, 20.5])
+    sim.substeps(2)
+    assert sim.particle_count() == 1
+    sim.close()
+
+
+def test_single_particle_closed_form(pkg, scenes):
+    for dim, sc in ((2, scenes.default_2d()), (3, scenes.default_3d())):
+        sim = pkg.Simulation.new(sc.cfg)
+        sim.add_particle([20.5] * dim)
+        sim.set_rect(sc.rect_min, sc.rect_max)
+        t = sim.debug_substep()
+        assert abs(float(t["density"][0]) - 0.59375 ** dim) < 1e-6
+        assert np.float32(t["pressure"][0]) == np.float32(sc.cfg["pressure_clamp"])
+        g = sim.read_grid()
+        assert abs(float(g[:, -1].sum()) - 1.0) < 1e-6
+        sim.close()
+
+
+def test_halo_frozen_outside_and_dropped_particles(pkg, orc, scenes):
+    sc = scenes.default_3d()
+    cfg = dict(sc.cfg)
+    cfg["clip_min"] = [-200.0] * 3
+    cfg["clip_max"] = [200.0] * 3
+    cfg["gravity"] = [0.0, 0.0, 0.0]
+    rec = np.zeros((5, 16), dtype=np.float32)
+    rec[0, :3] = [-3.5, 20.5, 20.5]       # halo block: deposits, frozen
+    rec[1, :3] = [20.5, 20.5, 20.5]       # active
+    rec[2, :3] = [150.0, 20.5, 20.5]      # outside p_rect: ignored, kept
+    rec[3, :3] = [78.0, 20.5, 20.5]       # active, jumps past the halo ring -> dropped
+    rec[3, 3] = 300.0
+    rec[4, :3] = [79.9, 30.5, 30.5]       # active, walks into the halo ring -> frozen there
+    rec[4, 3] = 4.0
+    rec[:, -1] = 1.0
+    sim, ref = build_pair(pkg, orc, cfg, rec, [0, 0, 0], [64, 64, 64])
+    assert sim.particle_counts() == dict(active=3, frozen=1, outside=1, dropped=0)
+    sim.substeps(1)
+    ref.substeps(1)
+    c = sim.particle_counts()
+    assert (c["active"], c["frozen"], c["outside"], c["dropped"]) == (ref.count(0), ref.count(1) - ref.count(0), 1, 1)
+    sim.substeps(30)
+    ref.substeps(30)
+    c = sim.particle_counts()
+    assert c == dict(active=1, frozen=2, outside=1, dropped=1)
+    assert ref.count(0) == 1 and ref.count(1) == 3 and ref.count(2) == 1
+    g_rec, g_ids = sim.read_particles(sort_by_id=True)
+    assert g_ids.tolist() == [1]
+    sim.close()
+    ref.close()
+
+
+def test_add_after_set_rect_and_second_set_rect(pkg, orc, scenes):
+    sc = scenes.default_3d(1000)
+    rec = sc.records()
+    sim = pkg.Simulation.new(sc.cfg)
+    ref = orc.OracleSim(sc.cfg)
+    for s in (sim, ref):
+        s.set_rect(sc.rect_min, sc.rect_max)
+        s.add_particles(rec[:400])
+        s.substeps(2)
+        s.add_particles(rec[400:])
+        s.substeps(2)
+        s.set_rect([0, 0, 0], [40, 64, 64])           # shrink the active rect; particles stay
+        s.substeps(2)
+    g_rec, g_ids = sim.read_particles(sort_by_id=True)
+    r_rec, r_ids = ref.read()
+    o = np.argsort(r_ids)
+    assert np.array_equal(g_ids, r_ids[o])
+    assert np.abs(g_rec[:, :3] - r_rec[o][:, :3]).max() < 1e-4
+    sim.close()
+    ref.close()
+
+
+def test_ragged_cell_occupancy(pkg, orc, scenes):
+    # 300 particles in one cell, neighbours empty: long per-cell lists, duplicates in the sort
+    sc = scenes.default_3d()
+    rng = np.random.default_rng(2)
+    rec = np.zeros((300, 16), dtype=np.float32)
+    rec[:, :3] = (30.0 + rng.uniform(0, 1, (300, 3))).astype(np.float32)
+    rec[:, -1] = 1.0
+    check_one_substep(pkg, orc, sc, rec)
+
+
+# ---- long-run invariants ----------------------------------------------------------------------------
+
+def invariants(rec, dim, density):
+    m = rec[:, -1].astype(np.float64)
+    v = rec[:, dim:2 * dim].astype(np.float64)
+    return dict(count=rec.shape[0], mass=m.sum(), ke=0.5 * (m * (v * v).sum(axis=1)).sum(),
+                surface=float(rec[:, 1].min()),       # +y is down (3d:23): free surface = min y
+                y_mean=float(rec[:, 1].mean()))
+
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_1000_substep_invariants(pkg, orc, scenes, dim):
+    sc = scenes.default_2d(2048) if dim == 2 else scenes.default_3d(4096)
+    rec = sc.records()
+    sim, ref = build_pair(pkg, orc, sc.cfg, rec, sc.rect_min, sc.rect_max)
+    sim.substeps(999)
+    ref.substeps(999)
+    gt = sim.debug_substep()
+    rt, _ = oracle_substep_with_taps(ref)
+    g_rec, _ = sim.read_particles()
+    r_rec, _ = ref.read()
+    gi, ri = invariants(g_rec, dim, gt["density"]), invariants(r_rec, dim, rt["density"])
+    assert gi["count"] == ri["count"] == sc.n
+    assert gi["mass"] == ri["mass"]
+    rho0 = sc.cfg["rest_density"]
+    g_derr = float(np.mean(np.abs(gt["density"] - rho0)) / rho0)
+    r_derr = float(np.mean(np.abs(rt["density"] - rho0)) / rho0)
+    # stated tolerances for chaotic 1000-substep trajectories:
+    assert abs(g_derr - r_derr) < 0.02                     # mean density error: 2 % of rho0
+    assert abs(gi["y_mean"] - ri["y_mean"]) < 0.25         # centre of mass height: 0.25 cell
+    assert abs(gi["surface"] - ri["surface"]) < 1.5        # free-surface height: 1.5 cells
+    ke_scale = max(ri["ke"], 1e-3 * sc.n)
+    assert abs(gi["ke"] - ri["ke"]) / ke_scale < 0.25      # kinetic energy: 25 % (settling sloshes)
+    pos = g_rec[:, :dim]
+    assert (pos >= 0).all() and (pos <= 64).all()
+    sim.close()
+    ref.close()
+
+
+# ---- BASELINE full sizes: size-independent properties -------------------------------------------------
+
+@pytest.mark.parametrize("which", ["1M", "16M"])
+def test_full_size_conservation(pkg, scenes, which):
+    """Configs 3 and 4 at full size: node masses sum to the particle mass, node momentum sums to
+    the particle momentum (sum of weights = 1, sum w (x_i - x_p) = 0), count is constant, every
+    particle stays in the clip box."""
+    sc = scenes.dam_break_1m() if which == "1M" else scenes.dam_break_16m()
+    sim = pkg.Simulation.new(sc.cfg)
+    chunk = 1 << 21
+    for s in range(0, sc.n, chunk):
+        sim.add_particles(sc.records(s, min(chunk, sc.n - s)))
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    sim.substeps(3)
+    assert sim.particle_counts() == dict(active=sc.n, frozen=0, outside=0, dropped=0)
+    g = sim.read_grid()
+    mass = g[:, 3].astype(np.float64)
+    assert abs(mass.sum() - sc.n) / sc.n < 1e-6
+    rec, ids = sim.read_particles()
+    assert rec.shape[0] == sc.n
+    assert np.array_equal(np.sort(ids), np.arange(sc.n, dtype=np.int32))
+    # grid momentum after update = sum m_i (v_i) ; particle momentum after g2p = sum_p m v_p:
+    # g2p's gather conserves momentum (sum_p w_ip = ... ) only approximately per node, so compare
+    # total momentum before the walls act: gravity impulse per substep = m * dt * g
+    pv = rec[:, 3:6].astype(np.float64).sum(axis=0)
+    gy = 3 * sc.cfg["dt"] * sc.cfg["gravity"][1] * sc.n
+    assert abs(pv[1] - gy) / gy < 0.05
+    lo, hi = np.float32(sc.cfg["clip_min"]), np.float32(sc.cfg["clip_max"])
+    assert (rec[:, :3] >= lo).all() and (rec[:, :3] <= hi).all()
+    sim.close()
