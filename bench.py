@@ -210,7 +210,10 @@ def run_ours(args):
         hnp[s:s + c] = sc.records(s, c)
     back = torch.empty((sc.n, rf), dtype=torch.float32, pin_memory=True)
 
-    stream = torch.cuda.current_stream()
+    # a non-default stream: the engine and the timing events share it (NULL would mean "the
+    # handle's own stream" to fluid_set_stream)
+    stream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(stream)
     sim = pkg.Simulation.new(sc.cfg, device=local_rank)
     sim.set_stream(stream.cuda_stream)
     sim.set_rect(sc.rect_min, sc.rect_max)

@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <climits>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -17,6 +18,7 @@
 
 #include "common.cuh"
 #include "phases_generic.cuh"
+#include "phases_tiled.cuh"
 #include "sort.cuh"
 
 using namespace fluid;
@@ -83,6 +85,7 @@ struct fluid_sim {
     int cur = 0;
     int* cell_idx = nullptr;
     int* rank = nullptr;
+    int* perm = nullptr;     // cell-sorted slot -> (rank, cell)-sorted slot inside each tile (3D)
 
     int* count = nullptr;    // n_cells_pad + 2 buckets
     int* start = nullptr;    // n_cells_pad + 3 (exclusive scan + total)
@@ -91,8 +94,10 @@ struct fluid_sim {
     int64_t n_scan_blocks = 0;
     int* class_count = nullptr;   // 4 ints (device)
 
-    float4* grid = nullptr;
+    float4* grid = nullptr;      // {momentum.xyz, mass} per node, reference layout + guards
+    float* gmass = nullptr;      // node masses alone (p2g 1 output, read by p2g 2), same layout
     int64_t grid_nodes = 0;      // reference node count (without guards)
+    bool tiled = true;           // 3D: tiled sm_100a kernels; FLUID_B200_GENERIC=1 forces the generic ones
     float* d_mouse = nullptr;
 
     float* d_stage = nullptr;    // staging for host<->device record copies
@@ -156,12 +161,14 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->cell_idx);
     cudaFree(s->rank);
-    s->cell_idx = s->rank = nullptr;
+    cudaFree(s->perm);
+    s->cell_idx = s->rank = s->perm = nullptr;
     s->buf[0] = nb[0];
     s->buf[1] = nb[1];
     s->cur = 0;
     CU_TRY(cudaMalloc(&s->cell_idx, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->rank, cap * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->perm, cap * sizeof(int)));
     s->cap = cap;
     return FLUID_OK;
 }
@@ -309,8 +316,17 @@ fluid_status sort_particles(fluid_sim* s) {
     k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->count, static_cast<int>(m), s->block_sums, s->start);
     s->launches += 3;
     if (n > 0) {
-        k_reorder<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->cell_idx, s->rank, s->start);
-        ++s->launches;
+        if (DIM == 3) {
+            // order inside each tile: (rank in cell, cell) — see phases_tiled.cuh
+            const int64_t tile_threads = static_cast<int64_t>(s->geo.n_tiles) * 32;
+            k_tile_perm<<<blocks_for(tile_threads, 128), 128, 0, s->stream>>>(s->geo, s->count, s->start, s->perm);
+            k_reorder_perm<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->cell_idx, s->rank, s->start,
+                                                                          s->perm, s->geo.n_cells_pad);
+            s->launches += 2;
+        } else {
+            k_reorder<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->cell_idx, s->rank, s->start);
+            ++s->launches;
+        }
         s->cur ^= 1;
     }
     CU_TRY(cudaGetLastError());
@@ -353,15 +369,29 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     }
     if (timed) CU_TRY(cudaEventRecord(ev[1], s->stream));
     // clear_grid (3d:136-146)
-    CU_TRY(cudaMemsetAsync(s->grid, 0, (s->grid_nodes + 2 * s->geo.guard) * sizeof(float4), s->stream));
-    if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-    k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid);
-    if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
-    k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid,
-                                                                  dbg ? dbg->density : nullptr,
-                                                                  dbg ? dbg->pressure : nullptr);
-    if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
-    k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid, d_mouse);
+    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+    if (DIM == 3 && s->tiled) {
+        CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
+        const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);
+        if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
+        k_mass_tiled<<<tb, T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->start, s->gmass);
+        if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
+        k_p2g_tiled<<<tb, T3::THREADS, sizeof(P2GSmem), s->stream>>>(s->geo, q, s->start, s->gmass, s->grid,
+                                                                    dbg ? dbg->density : nullptr,
+                                                                    dbg ? dbg->pressure : nullptr);
+        if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
+        k_g2p_tiled<<<tb, T3::THREADS, 0, s->stream>>>(s->geo, q, s->start, s->grid, d_mouse);
+    } else {
+        if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
+        k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid);
+        if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
+        k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid,
+                                                                      dbg ? dbg->density : nullptr,
+                                                                      dbg ? dbg->pressure : nullptr);
+        if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
+        k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid, d_mouse);
+    }
     if (timed) {
         CU_TRY(cudaEventRecord(ev[5], s->stream));
         s->last_ev = ev;
@@ -469,6 +499,9 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
         return fail(FLUID_ERR_CUDA, std::string("fluid_create: ") + cudaGetErrorString(ce));
     }
     s->stream = s->own_stream;
+    const char* force_generic = std::getenv("FLUID_B200_GENERIC");
+    s->tiled = !(force_generic && force_generic[0] == '1');
+    cudaFuncSetAttribute(k_p2g_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
     *out = s;
     return FLUID_OK;
 }
@@ -480,6 +513,8 @@ fluid_status fluid_destroy(fluid_sim* s) {
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->cell_idx);
     cudaFree(s->rank);
+    cudaFree(s->perm);
+    cudaFree(s->gmass);
     cudaFree(s->count);
     cudaFree(s->start);
     cudaFree(s->block_sums);
@@ -571,15 +606,18 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
 
     CU_TRY(cudaStreamSynchronize(s->stream));
     cudaFree(s->grid);
+    cudaFree(s->gmass);
     cudaFree(s->count);
     cudaFree(s->start);
     cudaFree(s->block_sums);
     s->grid = nullptr;
+    s->gmass = nullptr;
     s->count = s->start = s->block_sums = nullptr;
     s->rect_set = false;
     const int64_t m = static_cast<int64_t>(g.n_cells_pad) + 2;
     const int64_t nb = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
+    if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
     CU_TRY(cudaMalloc(&s->count, (m + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->start, (m + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->block_sums, nb * sizeof(int)));

@@ -1,0 +1,428 @@
+// phases_tiled.cuh — the 3D hot path: warp-private shared-memory node tiles, sm_100a.
+//
+// One warp owns one tile of 8x8x4 cells (Tile<3>) and the 10x10x6 nodes its particles can touch
+// (3^3 stencil reach, 3d:157-158).  Particles arrive sorted by (tile, rank-in-cell, cell), so the
+// 32 particles a warp handles in one iteration sit in 32 DISTINCT cells: at stencil offset o lane
+// l updates node cell_l + o, all different, and a plain LDS / FFMA / STS read-modify-write is
+// race free inside the warp — shared-memory float atomics are a CAS loop on sm_100a
+// (ATOMS.CAST.SPIN) and are not used.  A __match_any_sync over the cell ids splits an iteration
+// into passes if two lanes ever share a cell, so correctness never depends on the sort order.
+// Tiles are flushed to the dense grid with vector reductions (red.global.add.v4.f32,
+// SASS REDG.E.ADD.F32x4).
+//
+// Phase mapping to the reference (3d:110-134):
+//   k_mass_tiled  "p2g 1"  node mass   m_i  = sum_p w_ip m_p                      (3d:164,175)
+//   k_p2g_tiled   "p2g 2"  density, Tait pressure, stress (3d:198-225) and ONE scatter of
+//                          w_ip * (m v + (m C + T) (x_i - x_p)) = the momentum of p2g_1
+//                          (3d:163,176) plus the force term of p2g_2 (3d:242); the w lane of
+//                          the float4 node carries w_ip m_p again so g2p reads one record
+//   k_g2p_tiled   "update" + "g2p": v_i = mom/m + dt g while loading the tile (3d:253-256),
+//                          gather, C = 4B, advect, mouse, clamp, soft wall (3d:267-343)
+#pragma once
+
+#include "common.cuh"
+#include "phases_generic.cuh"
+#include "sort.cuh"
+
+namespace fluid {
+
+struct T3 {
+    static constexpr int X = Tile<3>::X, Y = Tile<3>::Y, Z = Tile<3>::Z;
+    static constexpr int NX = X + 2, NY = Y + 2, NZ = Z + 2;
+    static constexpr int NODES = NX * NY * NZ;       // 600
+    static constexpr int WARPS = 4;                  // tiles per CTA (no CTA-level sync is used)
+    static constexpr int THREADS = WARPS * 32;
+};
+
+struct TileCtx {
+    int c0[3];     // first cell of the tile, relative to the grid origin
+    int base;      // first particle slot
+    int count;     // particles in the tile
+};
+
+__device__ __forceinline__ bool tile_setup(const Geo& g, const int* __restrict__ start, int t,
+                                           TileCtx& tc) {
+    if (t >= g.n_tiles) return false;
+    tc.base = start[t * Tile<3>::CELLS];
+    tc.count = start[(t + 1) * Tile<3>::CELLS] - tc.base;
+    if (tc.count <= 0) return false;
+    int tx = t % g.tdim[0];
+    int r = t / g.tdim[0];
+    int ty = r % g.tdim[1];
+    int tz = r / g.tdim[1];
+    tc.c0[0] = tx * T3::X;
+    tc.c0[1] = ty * T3::Y;
+    tc.c0[2] = tz * T3::Z;
+    return true;
+}
+
+// Global node index of local footprint node k, or -1 outside the p_rect grid.
+__device__ __forceinline__ int footprint_to_global(const Geo& g, const TileCtx& tc, int k) {
+    int lx = k % T3::NX;
+    int r = k / T3::NX;
+    int ly = r % T3::NY;
+    int lz = r / T3::NY;
+    int x = tc.c0[0] - 1 + lx, y = tc.c0[1] - 1 + ly, z = tc.c0[2] - 1 + lz;
+    if (x < 0 || y < 0 || z < 0 || x >= g.size[0] || y >= g.size[1] || z >= g.size[2]) return -1;
+    return g.guard + x + (y + z * g.size[1]) * g.size[0];
+}
+
+// Per-particle stencil in tile coordinates.
+struct TStencil {
+    float wx[3], wy[3], wz[3];   // zeroed outside the p_rect grid (3d:166-168)
+    float cx, cy, cz;            // pos - (cell + 0.5)
+    int node0;                   // footprint index of stencil offset (0,0,0)
+    int cellkey;                 // cell index inside the tile (conflict detection)
+};
+
+__device__ __forceinline__ void axis_weights(float c, float* w) {
+    float m = 0.5f - c, p = 0.5f + c;
+    w[0] = 0.5f * m * m;
+    w[1] = 0.75f - c * c;
+    w[2] = 0.5f * p * p;
+}
+
+__device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, float px, float py,
+                                             float pz, TStencil& s) {
+    float fx = floorf(px), fy = floorf(py), fz = floorf(pz);
+    s.cx = px - (fx + 0.5f);
+    s.cy = py - (fy + 0.5f);
+    s.cz = pz - (fz + 0.5f);
+    axis_weights(s.cx, s.wx);
+    axis_weights(s.cy, s.wy);
+    axis_weights(s.cz, s.wz);
+    int rx = rust_as_i32(fx) - g.org[0], ry = rust_as_i32(fy) - g.org[1], rz = rust_as_i32(fz) - g.org[2];
+#pragma unroll
+    for (int o = 0; o < 3; ++o) {
+        int nx = rx - 1 + o, ny = ry - 1 + o, nz = rz - 1 + o;
+        if (nx < 0 || nx >= g.size[0]) s.wx[o] = 0.0f;
+        if (ny < 0 || ny >= g.size[1]) s.wy[o] = 0.0f;
+        if (nz < 0 || nz >= g.size[2]) s.wz[o] = 0.0f;
+    }
+    // the sort put this particle into this tile from the same floor(pos); the clamp only guards
+    // shared memory against non-finite positions
+    int lx = min(max(rx - tc.c0[0], 0), T3::X - 1);
+    int ly = min(max(ry - tc.c0[1], 0), T3::Y - 1);
+    int lz = min(max(rz - tc.c0[2], 0), T3::Z - 1);
+    s.node0 = lx + T3::NX * (ly + T3::NY * lz);
+    s.cellkey = lx + T3::X * (ly + T3::Y * lz);
+}
+
+// Pass structure of one 32-particle iteration: lanes that share a cell take turns.
+__device__ __forceinline__ void conflict_passes(bool active, int cellkey, int lane, int& my_pass,
+                                                int& n_pass) {
+    unsigned peers = __match_any_sync(0xffffffffu, active ? cellkey : (-1 - lane));
+    my_pass = __popc(peers & ((1u << lane) - 1u));
+    n_pass = __reduce_max_sync(0xffffffffu, my_pass) + 1;
+}
+
+// ---- p2g 1: node masses ---------------------------------------------------------------------
+
+__global__ void __launch_bounds__(T3::THREADS)
+k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
+             const int* __restrict__ start, float* __restrict__ gmass) {
+    __shared__ float sm[T3::WARPS * T3::NODES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TileCtx tc;
+    if (!tile_setup(g, start, blockIdx.x * T3::WARPS + warp, tc)) return;
+    float* tile = sm + warp * T3::NODES;
+    for (int k = lane; k < T3::NODES; k += 32) tile[k] = 0.0f;
+    __syncwarp();
+
+    for (int it = 0; it < tc.count; it += 32) {
+        const bool active = it + lane < tc.count;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) p = __ldg(&P[tc.base + it + lane]);
+        TStencil s;
+        tile_stencil(g, tc, p.x, p.y, p.z, s);
+        float wzm[3] = {s.wz[0] * p.w, s.wz[1] * p.w, s.wz[2] * p.w};
+        int my_pass, n_pass;
+        conflict_passes(active, s.cellkey, lane, my_pass, n_pass);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const bool go = active && my_pass == pass;
+            asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
+#pragma unroll
+            for (int oz = 0; oz < 3; ++oz)
+#pragma unroll
+                for (int oy = 0; oy < 3; ++oy) {
+                    const float wyz = s.wy[oy] * wzm[oz];
+#pragma unroll
+                    for (int ox = 0; ox < 3; ++ox) {
+                        const int idx = s.node0 + ox + T3::NX * (oy + T3::NY * oz);
+                        if (go) tile[idx] += s.wx[ox] * wyz;
+                        __syncwarp();
+                    }
+                }
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < T3::NODES; k += 32) {
+        float v = tile[k];
+        if (v != 0.0f) {
+            int gi = footprint_to_global(g, tc, k);
+            if (gi >= 0) atomicAdd(&gmass[gi], v);
+        }
+    }
+}
+
+// ---- p2g 2: density, pressure, stress; fused momentum + force scatter ---------------------------
+
+struct P2GSmem {
+    float4 acc[T3::WARPS][T3::NODES];   // {momentum + force, mass} accumulators
+    float mass[T3::WARPS][T3::NODES];   // complete node masses (from k_mass_tiled)
+};
+
+__global__ void __launch_bounds__(T3::THREADS, 4)
+k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ start,
+            const float* __restrict__ gmass, float4* __restrict__ grid,
+            float* __restrict__ dbg_density, float* __restrict__ dbg_pressure) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TileCtx tc;
+    if (!tile_setup(g, start, blockIdx.x * T3::WARPS + warp, tc)) return;
+    float4* acc = sm.acc[warp];
+    float* ms = sm.mass[warp];
+    for (int k = lane; k < T3::NODES; k += 32) {
+        acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        int gi = footprint_to_global(g, tc, k);
+        ms[k] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
+    }
+    __syncwarp();
+
+    for (int it = 0; it < tc.count; it += 32) {
+        const bool active = it + lane < tc.count;
+        const int i = tc.base + it + lane;
+        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, ca = p, cb = p;
+        float cc = 0.0f;
+        if (active) {
+            p = __ldg(&q.P[i]);
+            v = __ldg(&q.V[i]);
+            ca = __ldg(&q.CA[i]);
+            cb = __ldg(&q.CB[i]);
+            cc = __ldg(&q.CC[i]);
+        }
+        TStencil s;
+        tile_stencil(g, tc, p.x, p.y, p.z, s);
+
+        // density = sum_i m_i w_ip (3d:198-215)
+        float density = 0.0f;
+#pragma unroll
+        for (int oz = 0; oz < 3; ++oz)
+#pragma unroll
+            for (int oy = 0; oy < 3; ++oy) {
+                const float wyz = s.wy[oy] * s.wz[oz];
+#pragma unroll
+                for (int ox = 0; ox < 3; ++ox)
+                    density += ms[s.node0 + ox + T3::NX * (oy + T3::NY * oz)] * (s.wx[ox] * wyz);
+            }
+        const float m = p.w;
+        float volume = 0.0f, pressure = 0.0f;
+        if (active) {
+            volume = __fdiv_rn(m, density);
+            pressure = tait_pressure(g, density);
+            if (dbg_density) dbg_density[i] = density;
+            if (dbg_pressure) dbg_pressure[i] = pressure;
+        }
+        // M = m C + T,  T = -4 V (-p I + mu (C + C^T)) dt   (3d:222-225), column-major
+        const float C[9] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, cc};
+        const float s1 = -4.0f * volume * g.dt;
+        float M[9];
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                float stress = g.mu * (C[3 * c + r] + C[3 * r + c]);
+                if (c == r) stress -= pressure;
+                M[3 * c + r] = m * C[3 * c + r] + s1 * stress;
+            }
+        // value at offset o: w * (b + ox*M0 + oy*M1 + oz*M2), b = m v + M * (-1 - c)
+        const float dx0 = -1.0f - s.cx, dy0 = -1.0f - s.cy, dz0 = -1.0f - s.cz;
+        float b[3];
+        b[0] = m * v.x + M[0] * dx0 + M[3] * dy0 + M[6] * dz0;
+        b[1] = m * v.y + M[1] * dx0 + M[4] * dy0 + M[7] * dz0;
+        b[2] = m * v.z + M[2] * dx0 + M[5] * dy0 + M[8] * dz0;
+
+        int my_pass, n_pass;
+        conflict_passes(active, s.cellkey, lane, my_pass, n_pass);
+        for (int pass = 0; pass < n_pass; ++pass) {
+            const bool go = active && my_pass == pass;
+            // n_pass is 1 except when two lanes share a cell: keep the 108 per-node values out of
+            // registers across passes (the compiler would hoist them as loop invariants)
+            asm volatile("" : "+f"(b[0]), "+f"(b[1]), "+f"(b[2]));
+            asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
+#pragma unroll
+            for (int oz = 0; oz < 3; ++oz) {
+                const float bz0 = b[0] + oz * M[6], bz1 = b[1] + oz * M[7], bz2 = b[2] + oz * M[8];
+#pragma unroll
+                for (int oy = 0; oy < 3; ++oy) {
+                    const float wyz = s.wy[oy] * s.wz[oz];
+                    const float r0 = bz0 + oy * M[3], r1 = bz1 + oy * M[4], r2 = bz2 + oy * M[5];
+#pragma unroll
+                    for (int ox = 0; ox < 3; ++ox) {
+                        const float w = s.wx[ox] * wyz;
+                        const int idx = s.node0 + ox + T3::NX * (oy + T3::NY * oz);
+                        if (go) {
+                            float4 a = acc[idx];
+                            a.x += w * (r0 + ox * M[0]);
+                            a.y += w * (r1 + ox * M[1]);
+                            a.z += w * (r2 + ox * M[2]);
+                            a.w += w * m;
+                            acc[idx] = a;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    for (int k = lane; k < T3::NODES; k += 32) {
+        float4 a = acc[k];
+        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) {
+            int gi = footprint_to_global(g, tc, k);
+            if (gi >= 0) atomicAdd(&grid[gi], a);
+        }
+    }
+}
+
+// ---- update + g2p -----------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(T3::THREADS)
+k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ start,
+            const float4* __restrict__ grid, const float* __restrict__ mouse) {
+    __shared__ float4 sm[T3::WARPS * T3::NODES];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    TileCtx tc;
+    if (!tile_setup(g, start, blockIdx.x * T3::WARPS + warp, tc)) return;
+    float4* vt = sm + warp * T3::NODES;
+    for (int k = lane; k < T3::NODES; k += 32) {
+        int gi = footprint_to_global(g, tc, k);
+        float4 nd = gi >= 0 ? __ldg(&grid[gi]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (nd.w > 0.0f) {   // update_grid (3d:253-256)
+            nd.x = __fdiv_rn(nd.x, nd.w) + g.dtg[0];
+            nd.y = __fdiv_rn(nd.y, nd.w) + g.dtg[1];
+            nd.z = __fdiv_rn(nd.z, nd.w) + g.dtg[2];
+        }
+        vt[k] = nd;
+    }
+    __syncwarp();
+
+    for (int it = 0; it < tc.count; it += 32) {
+        if (it + lane >= tc.count) continue;
+        const int i = tc.base + it + lane;
+        const float4 p = q.P[i];
+        float pos[3] = {p.x, p.y, p.z};
+        int key[3];
+        if (classify<3>(g, pos, key) != CLS_ACTIVE) continue;   // g2p walks a_rect blocks only
+        TStencil s;
+        tile_stencil(g, tc, p.x, p.y, p.z, s);
+        // S = sum w v ; Dk = sum w v (o_k - 1) ; B col k = Dk - S c_k
+        float S[3] = {0.f, 0.f, 0.f}, Dx[3] = {0.f, 0.f, 0.f}, Dy[3] = {0.f, 0.f, 0.f}, Dz[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int oz = 0; oz < 3; ++oz) {
+            float Pz[3] = {0.f, 0.f, 0.f}, Pdx[3] = {0.f, 0.f, 0.f}, Pdy[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+            for (int oy = 0; oy < 3; ++oy) {
+                const float4* row = vt + s.node0 + T3::NX * (oy + T3::NY * oz);
+                const float4 n0 = row[0], n1 = row[1], n2 = row[2];
+                float a0[3] = {n0.x * s.wx[0], n0.y * s.wx[0], n0.z * s.wx[0]};
+                float a2[3] = {n2.x * s.wx[2], n2.y * s.wx[2], n2.z * s.wx[2]};
+                float rs[3] = {a0[0] + n1.x * s.wx[1] + a2[0], a0[1] + n1.y * s.wx[1] + a2[1],
+                               a0[2] + n1.z * s.wx[1] + a2[2]};
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float rsw = rs[r] * s.wy[oy];
+                    Pz[r] += rsw;
+                    Pdx[r] += (a2[r] - a0[r]) * s.wy[oy];
+                    if (oy == 0) Pdy[r] -= rsw;
+                    if (oy == 2) Pdy[r] += rsw;
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const float pz = Pz[r] * s.wz[oz];
+                S[r] += pz;
+                Dx[r] += Pdx[r] * s.wz[oz];
+                Dy[r] += Pdy[r] * s.wz[oz];
+                if (oz == 0) Dz[r] -= pz;
+                if (oz == 2) Dz[r] += pz;
+            }
+        }
+        float vel[3] = {S[0], S[1], S[2]};
+        float B[9];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            B[r] = Dx[r] - S[r] * s.cx;
+            B[3 + r] = Dy[r] - S[r] * s.cy;
+            B[6 + r] = Dz[r] - S[r] * s.cz;
+        }
+        integrate_particle<3>(g, pos, vel, mouse);
+        if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
+        const float idw = q.V[i].w;
+        q.P[i] = make_float4(pos[0], pos[1], pos[2], p.w);
+        q.V[i] = make_float4(vel[0], vel[1], vel[2], idw);
+        q.CA[i] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);
+        q.CB[i] = make_float4(4.0f * B[4], 4.0f * B[5], 4.0f * B[6], 4.0f * B[7]);
+        q.CC[i] = 4.0f * B[8];
+    }
+}
+
+// ---- sort order inside a tile: (rank in cell, cell) ---------------------------------------------
+// One warp per tile turns the cell-sorted slot (cellStart[cell] + rank) into the slot of the
+// (rank, cell) order, so that consecutive particles of a tile lie in distinct cells.
+
+__global__ void __launch_bounds__(128)
+k_tile_perm(const __grid_constant__ Geo g, const int* __restrict__ count,
+            const int* __restrict__ start, int* __restrict__ perm) {
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= g.n_tiles) return;
+    const int c_first = t * Tile<3>::CELLS;
+    const int base = start[c_first];
+    const int n_t = start[c_first + Tile<3>::CELLS] - base;
+    if (n_t <= 0) return;
+    int cnt[8], st[8];
+    {
+        const int4* cp = reinterpret_cast<const int4*>(count + c_first + lane * 8);
+        const int4* sp = reinterpret_cast<const int4*>(start + c_first + lane * 8);
+        int4 a = cp[0], b = cp[1], c = sp[0], d = sp[1];
+        cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
+        cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
+        st[0] = c.x; st[1] = c.y; st[2] = c.z; st[3] = c.w;
+        st[4] = d.x; st[5] = d.y; st[6] = d.z; st[7] = d.w;
+    }
+    int rank_base = base;
+    for (int r = 0;; ++r) {
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine += cnt[j] > r;
+        int inc = warp_inclusive_scan(mine);
+        int total = __shfl_sync(0xffffffffu, inc, 31);
+        if (total == 0) break;
+        int dst = rank_base + inc - mine;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (cnt[j] > r) perm[st[j] + r] = dst++;
+        rank_base += total;
+    }
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_reorder_perm(Particles src, Particles dst, int n, const int* __restrict__ cell_idx,
+               const int* __restrict__ rank, const int* __restrict__ start,
+               const int* __restrict__ perm, int n_cells_pad) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int c = cell_idx[i];
+    int d = start[c] + rank[i];
+    if (c < n_cells_pad) d = perm[d];     // the two tail buckets (ignored / dropped) keep their slot
+    dst.P[d] = src.P[i];
+    dst.V[d] = src.V[i];
+    dst.CA[d] = src.CA[i];
+    dst.CB[d] = src.CB[i];
+    dst.CC[d] = src.CC[i];
+}
+
+}  // namespace fluid
