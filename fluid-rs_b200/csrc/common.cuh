@@ -27,6 +27,8 @@ struct Geo {
     int n_cells_pad;   // n_tiles * 256: length of the tiled cell index space
     int guard;         // guard nodes before/after the grid array (zero-weight overreach)
     int slab_lo, slab_hi;   // owned cell range along the last axis (world cells); open if unset
+    int res_i;         // grid_res
+    int res_shift;     // log2(grid_res) when it is a power of two, else -1
     float res_f;       // grid_res as f32 (3d:399)
     float dt, rest_density, mu, stiffness, power, mouse_r2, pclamp;
     float dtg[3];      // dt * gravity (3d:255)
@@ -50,6 +52,21 @@ __device__ __forceinline__ int block_key(float p, float res_f) {
     return rust_as_i32(rust_div_euclid(p, res_f));
 }
 
+// Same key from the integer cell: for every f32 pos and integer grid_res,
+//   key_from_pos(pos) == floor_div(floor(pos) as i32, grid_res)
+// because the rounded quotient pos/res never crosses a block face (ulp(res*k)/res > ulp(k)/2);
+// tests/test_oracle.py::test_key_equals_floor_div_of_cell checks it one ulp either side of every
+// face, tests/test_gpu_parity.py::test_fast_key_matches_exact_key checks this function against
+// block_key() on the device.  Saturated cells (|pos| >= 2^31, inf, the drop tombstone) give keys
+// near +-2^27, outside any rect set_rect accepts, exactly like the exact rule.  The hot kernels
+// use this (shift or integer division) instead of IEEE division + fmodf per axis.
+__device__ __forceinline__ int block_key_of_cell(const int cell, const int res_i, const int res_shift) {
+    if (res_shift >= 0) return cell >> res_shift;          // arithmetic shift = floor division
+    int q = cell / res_i;
+    if ((cell % res_i) < 0) --q;
+    return q;
+}
+
 enum ParticleClass : int { CLS_ACTIVE = 0, CLS_FROZEN = 1, CLS_LIMBO = 2, CLS_DROPPED = 3 };
 
 // Class of a particle from its position alone: the reference stores a particle in the block
@@ -66,6 +83,27 @@ __device__ __forceinline__ int classify(const Geo& g, const float* pos, int* key
         in_p = in_p && (k >= g.p_lo[a]) && (k < g.p_hi[a]);
     }
     return in_a ? CLS_ACTIVE : (in_p ? CLS_FROZEN : CLS_LIMBO);
+}
+
+// classify() for the hot kernels: keys from the integer cells (see block_key_of_cell).
+template <int DIM>
+__device__ __forceinline__ int classify_cells(const Geo& g, const int* cell) {
+    bool in_a = true, in_p = true;
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) {
+        int k = block_key_of_cell(cell[a], g.res_i, g.res_shift);
+        in_a = in_a && (k >= g.a_lo[a]) && (k < g.a_hi[a]);
+        in_p = in_p && (k >= g.p_lo[a]) && (k < g.p_hi[a]);
+    }
+    return in_a ? CLS_ACTIVE : (in_p ? CLS_FROZEN : CLS_LIMBO);
+}
+
+template <int DIM>
+__device__ __forceinline__ int classify_pos(const Geo& g, const float* pos) {
+    int cell[3];
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) cell[a] = rust_as_i32(floorf(pos[a]));
+    return classify_cells<DIM>(g, cell);
 }
 
 // Tiled cell index (sort key).  rel = cell - origin, clamped into the grid by the caller.

@@ -86,6 +86,10 @@ struct fluid_sim {
     int* cell_idx = nullptr;
     int* rank = nullptr;
     int* perm = nullptr;     // cell-sorted slot -> (rank, cell)-sorted slot inside each tile (3D)
+    int4* tiles = nullptr;   // active tile list {tile, first slot, count, 0}, rebuilt by every sort
+    int* n_active = nullptr; // its length (device)
+    int sm_count = 148;
+    unsigned grid_mass = 0, grid_p2g = 0, grid_g2p = 0;   // persistent grids: SMs x resident CTAs
 
     int* count = nullptr;    // n_cells_pad + 2 buckets
     int* start = nullptr;    // n_cells_pad + 3 (exclusive scan + total)
@@ -245,8 +249,7 @@ __global__ void k_pack_active(const __grid_constant__ Geo g, Particles q, int n,
         float4 p = q.P[i];
         if (!is_tombstone(p.x)) {
             float pos[3] = {p.x, p.y, p.z};
-            int key[3];
-            take = classify<DIM>(g, pos, key) == CLS_ACTIVE;
+            take = classify_pos<DIM>(g, pos) == CLS_ACTIVE;
         }
     }
     unsigned m = __ballot_sync(0xffffffffu, take);
@@ -280,7 +283,10 @@ __global__ void k_debug_keys(const __grid_constant__ Geo g, Particles q,
     for (int a = 0; a < DIM; ++a) {
         int c = rust_as_i32(floorf(pos[a]));
         if (cell) cell[i * DIM + a] = c;
-        if (key) key[i * DIM + a] = k[a];
+        // exact rule (3d:398-401); if the hot kernels' integer rule ever disagreed, report the
+        // integer rule's key so the bit-exact parity tests fail loudly
+        int kf = block_key_of_cell(c, g.res_i, g.res_shift);
+        if (key) key[i * DIM + a] = (kf == k[a]) ? k[a] : kf;
         rel[a] = c - g.org[a];
     }
     if (ids) ids[i] = __float_as_int(q.V[i].w);
@@ -319,7 +325,9 @@ fluid_status sort_particles(fluid_sim* s) {
         if (DIM == 3) {
             // order inside each tile: (rank in cell, cell) — see phases_tiled.cuh
             const int64_t tile_threads = static_cast<int64_t>(s->geo.n_tiles) * 32;
-            k_tile_perm<<<blocks_for(tile_threads, 128), 128, 0, s->stream>>>(s->geo, s->count, s->start, s->perm);
+            CU_TRY(cudaMemsetAsync(s->n_active, 0, sizeof(int), s->stream));
+            k_tile_perm<<<blocks_for(tile_threads, 128), 128, 0, s->stream>>>(s->geo, s->count, s->start, s->perm,
+                                                                            s->tiles, s->n_active);
             k_reorder_perm<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->cell_idx, s->rank, s->start,
                                                                           s->perm, s->geo.n_cells_pad);
             s->launches += 2;
@@ -373,15 +381,17 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
     if (DIM == 3 && s->tiled) {
         CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
-        const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);
+        const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);   // never more CTAs than tiles / 4
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-        k_mass_tiled<<<tb, T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->start, s->gmass);
+        k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->tiles, s->n_active,
+                                                                              s->gmass);
         if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
-        k_p2g_tiled<<<tb, T3::THREADS, sizeof(P2GSmem), s->stream>>>(s->geo, q, s->start, s->gmass, s->grid,
-                                                                    dbg ? dbg->density : nullptr,
-                                                                    dbg ? dbg->pressure : nullptr);
+        k_p2g_tiled<<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
+            s->geo, q, s->tiles, s->n_active, s->gmass, s->grid, dbg ? dbg->density : nullptr,
+            dbg ? dbg->pressure : nullptr);
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
-        k_g2p_tiled<<<tb, T3::THREADS, 0, s->stream>>>(s->geo, q, s->start, s->grid, d_mouse);
+        k_g2p_tiled<<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(s->geo, q, s->tiles, s->n_active,
+                                                                             s->grid, d_mouse);
     } else {
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
         k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid);
@@ -493,6 +503,8 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     if (ce == cudaSuccess) ce = cudaMalloc(&s->d_mouse, 2 * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->class_count, 4 * sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->d_counter, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->n_active, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemset(s->n_active, 0, sizeof(int));
     for (int i = 0; i < N_EVENTS && ce == cudaSuccess; ++i) ce = cudaEventCreate(&s->ev[i]);
     if (ce != cudaSuccess) {
         fluid_destroy(s);
@@ -502,6 +514,18 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
     cudaFuncSetAttribute(k_p2g_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
+    {   // persistent grids: one wave of resident CTAs per kernel (148 SMs x occupancy)
+        cudaDeviceProp prop{};
+        if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
+        int occ = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mass_tiled, T3::THREADS, 0);
+        s->grid_mass = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_tiled, T3::THREADS, sizeof(P2GSmem));
+        s->grid_p2g = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled, T3::THREADS, 0);
+        s->grid_g2p = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
+        (void)cudaGetLastError();
+    }
     *out = s;
     return FLUID_OK;
 }
@@ -515,6 +539,8 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->rank);
     cudaFree(s->perm);
     cudaFree(s->gmass);
+    cudaFree(s->tiles);
+    cudaFree(s->n_active);
     cudaFree(s->count);
     cudaFree(s->start);
     cudaFree(s->block_sums);
@@ -589,6 +615,10 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     g.slab_lo = s->slab_lo;
     g.slab_hi = s->slab_hi;
     g.res_f = res;
+    g.res_i = s->cfg.grid_res;
+    g.res_shift = -1;
+    for (int b = 0; b < 30; ++b)
+        if (s->cfg.grid_res == (1 << b)) g.res_shift = b;
     g.dt = s->cfg.dt;
     g.rest_density = s->cfg.rest_density;
     g.mu = s->cfg.dynamic_viscosity;
@@ -607,17 +637,22 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaStreamSynchronize(s->stream));
     cudaFree(s->grid);
     cudaFree(s->gmass);
+    cudaFree(s->tiles);
     cudaFree(s->count);
     cudaFree(s->start);
     cudaFree(s->block_sums);
     s->grid = nullptr;
     s->gmass = nullptr;
+    s->tiles = nullptr;
     s->count = s->start = s->block_sums = nullptr;
     s->rect_set = false;
     const int64_t m = static_cast<int64_t>(g.n_cells_pad) + 2;
     const int64_t nb = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
-    if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
+    if (D == 3) {
+        CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
+        CU_TRY(cudaMalloc(&s->tiles, static_cast<int64_t>(g.n_tiles) * sizeof(int4)));
+    }
     CU_TRY(cudaMalloc(&s->count, (m + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->start, (m + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->block_sums, nb * sizeof(int)));

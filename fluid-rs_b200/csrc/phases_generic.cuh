@@ -176,13 +176,7 @@ __device__ __forceinline__ void integrate_particle(const Geo& g, float* pos, flo
 // If the advanced particle's key left p_rect the reference drops it (3d:356-366): tombstone.
 template <int DIM>
 __device__ __forceinline__ bool left_p_rect(const Geo& g, const float* pos) {
-    bool out = false;
-#pragma unroll
-    for (int a = 0; a < DIM; ++a) {
-        int k = block_key(pos[a], g.res_f);
-        out = out || k < g.p_lo[a] || k >= g.p_hi[a];
-    }
-    return out;
+    return classify_pos<DIM>(g, pos) == CLS_LIMBO;
 }
 
 // update_grid + g2p (3d:249-381)
@@ -194,8 +188,7 @@ k_g2p_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict_
     if (i >= *n_deposit) return;
     float4 p = q.P[i];
     float pos[3] = {p.x, p.y, p.z};
-    int key[3];
-    if (classify<DIM>(g, pos, key) != CLS_ACTIVE) return;   // g2p walks a_rect blocks only
+    if (classify_pos<DIM>(g, pos) != CLS_ACTIVE) return;   // g2p walks a_rect blocks only
     Stencil<DIM> s;
     make_stencil<DIM>(g, pos, s);
     constexpr int NZ = DIM == 3 ? 3 : 1;

@@ -40,12 +40,12 @@ struct TileCtx {
     int count;     // particles in the tile
 };
 
-__device__ __forceinline__ bool tile_setup(const Geo& g, const int* __restrict__ start, int t,
-                                           TileCtx& tc) {
-    if (t >= g.n_tiles) return false;
-    tc.base = start[t * Tile<3>::CELLS];
-    tc.count = start[(t + 1) * Tile<3>::CELLS] - tc.base;
-    if (tc.count <= 0) return false;
+// Active tiles (those holding particles), listed by k_tile_perm: {tile id, first slot, count, 0}.
+// The tile kernels run persistent warps that stride over this list, so empty tiles cost nothing.
+__device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileCtx& tc) {
+    const int t = e.x;
+    tc.base = e.y;
+    tc.count = e.z;
     int tx = t % g.tdim[0];
     int r = t / g.tdim[0];
     int ty = r % g.tdim[1];
@@ -53,7 +53,6 @@ __device__ __forceinline__ bool tile_setup(const Geo& g, const int* __restrict__
     tc.c0[0] = tx * T3::X;
     tc.c0[1] = ty * T3::Y;
     tc.c0[2] = tz * T3::Z;
-    return true;
 }
 
 // Global node index of local footprint node k, or -1 outside the p_rect grid.
@@ -63,16 +62,19 @@ __device__ __forceinline__ int footprint_to_global(const Geo& g, const TileCtx& 
     int ly = r % T3::NY;
     int lz = r / T3::NY;
     int x = tc.c0[0] - 1 + lx, y = tc.c0[1] - 1 + ly, z = tc.c0[2] - 1 + lz;
-    if (x < 0 || y < 0 || z < 0 || x >= g.size[0] || y >= g.size[1] || z >= g.size[2]) return -1;
+    if (k >= T3::NODES || x < 0 || y < 0 || z < 0 || x >= g.size[0] || y >= g.size[1] || z >= g.size[2])
+        return -1;
     return g.guard + x + (y + z * g.size[1]) * g.size[0];
 }
+
+constexpr int FOOT_ITERS = (T3::NODES + 31) / 32;   // 19 footprint nodes per lane
 
 // Per-particle stencil in tile coordinates.
 struct TStencil {
     float wx[3], wy[3], wz[3];   // zeroed outside the p_rect grid (3d:166-168)
     float cx, cy, cz;            // pos - (cell + 0.5)
     int node0;                   // footprint index of stencil offset (0,0,0)
-    int cellkey;                 // cell index inside the tile (conflict detection)
+    int column;                  // (x, y) column inside the tile (conflict detection)
 };
 
 __device__ __forceinline__ void axis_weights(float c, float* w) {
@@ -105,13 +107,16 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
     int ly = min(max(ry - tc.c0[1], 0), T3::Y - 1);
     int lz = min(max(rz - tc.c0[2], 0), T3::Z - 1);
     s.node0 = lx + T3::NX * (ly + T3::NY * lz);
-    s.cellkey = lx + T3::X * (ly + T3::Y * lz);
+    s.column = lx + T3::X * ly;
 }
 
-// Pass structure of one 32-particle iteration: lanes that share a cell take turns.
-__device__ __forceinline__ void conflict_passes(bool active, int cellkey, int lane, int& my_pass,
-                                                int& n_pass) {
-    unsigned peers = __match_any_sync(0xffffffffu, active ? cellkey : (-1 - lane));
+// Pass structure of one 32-particle window.  Lanes of one pass sit in DISTINCT (x,y) COLUMNS of
+// the tile: for a fixed (ox,oy) the three nodes oz = 0,1,2 of every lane are then private to that
+// lane, so the three read-modify-writes need no ordering among themselves (three independent
+// LDS/FFMA/STS chains in flight) and one __syncwarp per (ox,oy) suffices: 9 per pass, not 27.
+__device__ __forceinline__ void column_passes(bool active, int column, int lane, int& my_pass,
+                                              int& n_pass) {
+    unsigned peers = __match_any_sync(0xffffffffu, active ? column : (-1 - lane));
     my_pass = __popc(peers & ((1u << lane) - 1u));
     n_pass = __reduce_max_sync(0xffffffffu, my_pass) + 1;
 }
@@ -120,48 +125,62 @@ __device__ __forceinline__ void conflict_passes(bool active, int cellkey, int la
 
 __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
-             const int* __restrict__ start, float* __restrict__ gmass) {
+             const int4* __restrict__ tiles, const int* __restrict__ n_active,
+             float* __restrict__ gmass) {
     __shared__ float sm[T3::WARPS * T3::NODES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    TileCtx tc;
-    if (!tile_setup(g, start, blockIdx.x * T3::WARPS + warp, tc)) return;
     float* tile = sm + warp * T3::NODES;
-    for (int k = lane; k < T3::NODES; k += 32) tile[k] = 0.0f;
-    __syncwarp();
-
-    for (int it = 0; it < tc.count; it += 32) {
-        const bool active = it + lane < tc.count;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) p = __ldg(&P[tc.base + it + lane]);
-        TStencil s;
-        tile_stencil(g, tc, p.x, p.y, p.z, s);
-        float wzm[3] = {s.wz[0] * p.w, s.wz[1] * p.w, s.wz[2] * p.w};
-        int my_pass, n_pass;
-        conflict_passes(active, s.cellkey, lane, my_pass, n_pass);
-        for (int pass = 0; pass < n_pass; ++pass) {
-            const bool go = active && my_pass == pass;
-            asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
+    const int n_act = *n_active;
+    const int n_warps = gridDim.x * T3::WARPS;
+    for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
+        TileCtx tc;
+        tile_from_list(g, __ldg(&tiles[a]), tc);
+        for (int k = lane; k < T3::NODES; k += 32) tile[k] = 0.0f;
+        __syncwarp();
+        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < tc.count) p_next = __ldg(&P[tc.base + lane]);
+        for (int it = 0; it < tc.count; it += 32) {
+            const bool active = it + lane < tc.count;
+            const float4 p = p_next;
+            if (it + 32 + lane < tc.count) p_next = __ldg(&P[tc.base + it + 32 + lane]);   // prefetch
+            TStencil s;
+            tile_stencil(g, tc, p.x, p.y, p.z, s);
+            const float wzm[3] = {s.wz[0] * p.w, s.wz[1] * p.w, s.wz[2] * p.w};
+            int my_pass, n_pass;
+            column_passes(active, s.column, lane, my_pass, n_pass);
+            for (int pass = 0; pass < n_pass; ++pass) {
+                const bool go = active && my_pass == pass;
+                asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
 #pragma unroll
-            for (int oz = 0; oz < 3; ++oz)
-#pragma unroll
-                for (int oy = 0; oy < 3; ++oy) {
-                    const float wyz = s.wy[oy] * wzm[oz];
+                for (int oy = 0; oy < 3; ++oy)
 #pragma unroll
                     for (int ox = 0; ox < 3; ++ox) {
-                        const int idx = s.node0 + ox + T3::NX * (oy + T3::NY * oz);
-                        if (go) tile[idx] += s.wx[ox] * wyz;
+                        const float wxy = s.wx[ox] * s.wy[oy];
+                        float* nd = tile + s.node0 + ox + T3::NX * oy;
+                        if (go) {
+                            float a0 = nd[0], a1 = nd[T3::NX * T3::NY], a2 = nd[2 * T3::NX * T3::NY];
+                            a0 += wxy * wzm[0];
+                            a1 += wxy * wzm[1];
+                            a2 += wxy * wzm[2];
+                            nd[0] = a0;
+                            nd[T3::NX * T3::NY] = a1;
+                            nd[2 * T3::NX * T3::NY] = a2;
+                        }
                         __syncwarp();
                     }
-                }
+            }
         }
-    }
-    __syncwarp();
-    for (int k = lane; k < T3::NODES; k += 32) {
-        float v = tile[k];
-        if (v != 0.0f) {
-            int gi = footprint_to_global(g, tc, k);
-            if (gi >= 0) atomicAdd(&gmass[gi], v);
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < FOOT_ITERS; ++j) {
+            const int k = lane + 32 * j;
+            const float v = k < T3::NODES ? tile[k] : 0.0f;
+            if (v != 0.0f) {
+                int gi = footprint_to_global(g, tc, k);
+                if (gi >= 0) atomicAdd(&gmass[gi], v);
+            }
         }
+        __syncwarp();
     }
 }
 
@@ -172,199 +191,258 @@ struct P2GSmem {
     float mass[T3::WARPS][T3::NODES];   // complete node masses (from k_mass_tiled)
 };
 
+struct PRec {   // one particle's streams
+    float4 p, v, ca, cb;
+    float cc;
+};
+
+__device__ __forceinline__ void load_prec(const Particles& q, int i, bool ok, PRec& r) {
+    r.p = r.v = r.ca = r.cb = make_float4(0.f, 0.f, 0.f, 0.f);
+    r.cc = 0.0f;
+    if (ok) {
+        r.p = __ldg(&q.P[i]);
+        r.v = __ldg(&q.V[i]);
+        r.ca = __ldg(&q.CA[i]);
+        r.cb = __ldg(&q.CB[i]);
+        r.cc = __ldg(&q.CC[i]);
+    }
+}
+
 __global__ void __launch_bounds__(T3::THREADS, 4)
-k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ start,
-            const float* __restrict__ gmass, float4* __restrict__ grid,
-            float* __restrict__ dbg_density, float* __restrict__ dbg_pressure) {
+k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__ tiles,
+            const int* __restrict__ n_active, const float* __restrict__ gmass,
+            float4* __restrict__ grid, float* __restrict__ dbg_density,
+            float* __restrict__ dbg_pressure) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    TileCtx tc;
-    if (!tile_setup(g, start, blockIdx.x * T3::WARPS + warp, tc)) return;
     float4* acc = sm.acc[warp];
     float* ms = sm.mass[warp];
-    for (int k = lane; k < T3::NODES; k += 32) {
-        acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-        int gi = footprint_to_global(g, tc, k);
-        ms[k] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
-    }
-    __syncwarp();
-
-    for (int it = 0; it < tc.count; it += 32) {
-        const bool active = it + lane < tc.count;
-        const int i = tc.base + it + lane;
-        float4 p = make_float4(0.f, 0.f, 0.f, 0.f), v = p, ca = p, cb = p;
-        float cc = 0.0f;
-        if (active) {
-            p = __ldg(&q.P[i]);
-            v = __ldg(&q.V[i]);
-            ca = __ldg(&q.CA[i]);
-            cb = __ldg(&q.CB[i]);
-            cc = __ldg(&q.CC[i]);
-        }
-        TStencil s;
-        tile_stencil(g, tc, p.x, p.y, p.z, s);
-
-        // density = sum_i m_i w_ip (3d:198-215)
-        float density = 0.0f;
+    const int n_act = *n_active;
+    const int n_warps = gridDim.x * T3::WARPS;
+    constexpr int PLANE = T3::NX * T3::NY;
+    for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
+        TileCtx tc;
+        tile_from_list(g, __ldg(&tiles[a]), tc);
+        PRec nxt;
+        load_prec(q, tc.base + lane, lane < tc.count, nxt);
+        {   // node masses of the footprint: all loads in flight before the first store
+            float mv[FOOT_ITERS];
 #pragma unroll
-        for (int oz = 0; oz < 3; ++oz)
-#pragma unroll
-            for (int oy = 0; oy < 3; ++oy) {
-                const float wyz = s.wy[oy] * s.wz[oz];
-#pragma unroll
-                for (int ox = 0; ox < 3; ++ox)
-                    density += ms[s.node0 + ox + T3::NX * (oy + T3::NY * oz)] * (s.wx[ox] * wyz);
+            for (int j = 0; j < FOOT_ITERS; ++j) {
+                int gi = footprint_to_global(g, tc, lane + 32 * j);
+                mv[j] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
             }
-        const float m = p.w;
-        float volume = 0.0f, pressure = 0.0f;
-        if (active) {
-            volume = __fdiv_rn(m, density);
-            pressure = tait_pressure(g, density);
-            if (dbg_density) dbg_density[i] = density;
-            if (dbg_pressure) dbg_pressure[i] = pressure;
-        }
-        // M = m C + T,  T = -4 V (-p I + mu (C + C^T)) dt   (3d:222-225), column-major
-        const float C[9] = {ca.x, ca.y, ca.z, ca.w, cb.x, cb.y, cb.z, cb.w, cc};
-        const float s1 = -4.0f * volume * g.dt;
-        float M[9];
 #pragma unroll
-        for (int c = 0; c < 3; ++c)
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                float stress = g.mu * (C[3 * c + r] + C[3 * r + c]);
-                if (c == r) stress -= pressure;
-                M[3 * c + r] = m * C[3 * c + r] + s1 * stress;
+            for (int j = 0; j < FOOT_ITERS; ++j) {
+                const int k = lane + 32 * j;
+                if (k < T3::NODES) {
+                    ms[k] = mv[j];
+                    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
             }
-        // value at offset o: w * (b + ox*M0 + oy*M1 + oz*M2), b = m v + M * (-1 - c)
-        const float dx0 = -1.0f - s.cx, dy0 = -1.0f - s.cy, dz0 = -1.0f - s.cz;
-        float b[3];
-        b[0] = m * v.x + M[0] * dx0 + M[3] * dy0 + M[6] * dz0;
-        b[1] = m * v.y + M[1] * dx0 + M[4] * dy0 + M[7] * dz0;
-        b[2] = m * v.z + M[2] * dx0 + M[5] * dy0 + M[8] * dz0;
+        }
+        __syncwarp();
 
-        int my_pass, n_pass;
-        conflict_passes(active, s.cellkey, lane, my_pass, n_pass);
-        for (int pass = 0; pass < n_pass; ++pass) {
-            const bool go = active && my_pass == pass;
-            // n_pass is 1 except when two lanes share a cell: keep the 108 per-node values out of
-            // registers across passes (the compiler would hoist them as loop invariants)
-            asm volatile("" : "+f"(b[0]), "+f"(b[1]), "+f"(b[2]));
-            asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
+        for (int it = 0; it < tc.count; it += 32) {
+            const bool active = it + lane < tc.count;
+            const int i = tc.base + it + lane;
+            const PRec cur = nxt;
+            load_prec(q, i + 32, it + 32 + lane < tc.count, nxt);   // prefetch the next window
+            TStencil s;
+            tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
+
+            // density = sum_i m_i w_ip (3d:198-215)
+            float density = 0.0f;
 #pragma unroll
-            for (int oz = 0; oz < 3; ++oz) {
-                const float bz0 = b[0] + oz * M[6], bz1 = b[1] + oz * M[7], bz2 = b[2] + oz * M[8];
+            for (int oz = 0; oz < 3; ++oz)
 #pragma unroll
                 for (int oy = 0; oy < 3; ++oy) {
                     const float wyz = s.wy[oy] * s.wz[oz];
-                    const float r0 = bz0 + oy * M[3], r1 = bz1 + oy * M[4], r2 = bz2 + oy * M[5];
+#pragma unroll
+                    for (int ox = 0; ox < 3; ++ox)
+                        density += ms[s.node0 + ox + T3::NX * oy + PLANE * oz] * (s.wx[ox] * wyz);
+                }
+            const float m = cur.p.w;
+            float volume = 0.0f, pressure = 0.0f;
+            if (active) {
+                volume = __fdiv_rn(m, density);
+                pressure = tait_pressure(g, density);
+                if (dbg_density) dbg_density[i] = density;
+                if (dbg_pressure) dbg_pressure[i] = pressure;
+            }
+            // M = m C + T,  T = -4 V (-p I + mu (C + C^T)) dt   (3d:222-225), column-major
+            const float C[9] = {cur.ca.x, cur.ca.y, cur.ca.z, cur.ca.w, cur.cb.x, cur.cb.y, cur.cb.z, cur.cb.w, cur.cc};
+            const float s1 = -4.0f * volume * g.dt;
+            float M[9];
+#pragma unroll
+            for (int c = 0; c < 3; ++c)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    float stress = g.mu * (C[3 * c + r] + C[3 * r + c]);
+                    if (c == r) stress -= pressure;
+                    M[3 * c + r] = m * C[3 * c + r] + s1 * stress;
+                }
+            // value at offset o: w * (b + ox*M0 + oy*M1 + oz*M2), b = m v + M * (-1 - c)
+            const float dx0 = -1.0f - s.cx, dy0 = -1.0f - s.cy, dz0 = -1.0f - s.cz;
+            float b[3];
+            b[0] = m * cur.v.x + M[0] * dx0 + M[3] * dy0 + M[6] * dz0;
+            b[1] = m * cur.v.y + M[1] * dx0 + M[4] * dy0 + M[7] * dz0;
+            b[2] = m * cur.v.z + M[2] * dx0 + M[5] * dy0 + M[8] * dz0;
+            const float wzm[3] = {s.wz[0] * m, s.wz[1] * m, s.wz[2] * m};
+
+            int my_pass, n_pass;
+            column_passes(active, s.column, lane, my_pass, n_pass);
+            for (int pass = 0; pass < n_pass; ++pass) {
+                const bool go = active && my_pass == pass;
+                // n_pass is 1 unless two lanes share a column: keep the per-node values out of
+                // registers across passes (the compiler would hoist them as loop invariants)
+                asm volatile("" : "+f"(b[0]), "+f"(b[1]), "+f"(b[2]));
+                asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
+#pragma unroll
+                for (int oy = 0; oy < 3; ++oy) {
+                    const float r0 = b[0] + oy * M[3], r1 = b[1] + oy * M[4], r2 = b[2] + oy * M[5];
 #pragma unroll
                     for (int ox = 0; ox < 3; ++ox) {
-                        const float w = s.wx[ox] * wyz;
-                        const int idx = s.node0 + ox + T3::NX * (oy + T3::NY * oz);
+                        const float wxy = s.wx[ox] * s.wy[oy];
+                        const float c0 = r0 + ox * M[0], c1 = r1 + ox * M[1], c2 = r2 + ox * M[2];
+                        float4* nd = acc + s.node0 + ox + T3::NX * oy;
                         if (go) {
-                            float4 a = acc[idx];
-                            a.x += w * (r0 + ox * M[0]);
-                            a.y += w * (r1 + ox * M[1]);
-                            a.z += w * (r2 + ox * M[2]);
-                            a.w += w * m;
-                            acc[idx] = a;
+                            // three nodes along z: private to this lane within the pass
+                            float4 a0 = nd[0], a1 = nd[PLANE], a2 = nd[2 * PLANE];
+                            const float w0 = wxy * s.wz[0], w1 = wxy * s.wz[1], w2 = wxy * s.wz[2];
+                            a0.x += w0 * c0;              a0.y += w0 * c1;              a0.z += w0 * c2;
+                            a1.x += w1 * (c0 + M[6]);     a1.y += w1 * (c1 + M[7]);     a1.z += w1 * (c2 + M[8]);
+                            a2.x += w2 * (c0 + 2.f * M[6]); a2.y += w2 * (c1 + 2.f * M[7]); a2.z += w2 * (c2 + 2.f * M[8]);
+                            a0.w += wxy * wzm[0];
+                            a1.w += wxy * wzm[1];
+                            a2.w += wxy * wzm[2];
+                            nd[0] = a0;
+                            nd[PLANE] = a1;
+                            nd[2 * PLANE] = a2;
                         }
                         __syncwarp();
                     }
                 }
             }
         }
-    }
-    __syncwarp();
-    for (int k = lane; k < T3::NODES; k += 32) {
-        float4 a = acc[k];
-        if (a.w != 0.0f || a.x != 0.0f || a.y != 0.0f || a.z != 0.0f) {
-            int gi = footprint_to_global(g, tc, k);
-            if (gi >= 0) atomicAdd(&grid[gi], a);
+        __syncwarp();
+#pragma unroll 4
+        for (int j = 0; j < FOOT_ITERS; ++j) {
+            const int k = lane + 32 * j;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (k < T3::NODES) v = acc[k];
+            if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
+                int gi = footprint_to_global(g, tc, k);
+                if (gi >= 0) atomicAdd(&grid[gi], v);
+            }
         }
+        __syncwarp();
     }
 }
 
 // ---- update + g2p -----------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(T3::THREADS)
-k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ start,
-            const float4* __restrict__ grid, const float* __restrict__ mouse) {
+k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__ tiles,
+            const int* __restrict__ n_active, const float4* __restrict__ grid,
+            const float* __restrict__ mouse) {
     __shared__ float4 sm[T3::WARPS * T3::NODES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    TileCtx tc;
-    if (!tile_setup(g, start, blockIdx.x * T3::WARPS + warp, tc)) return;
     float4* vt = sm + warp * T3::NODES;
-    for (int k = lane; k < T3::NODES; k += 32) {
-        int gi = footprint_to_global(g, tc, k);
-        float4 nd = gi >= 0 ? __ldg(&grid[gi]) : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (nd.w > 0.0f) {   // update_grid (3d:253-256)
-            nd.x = __fdiv_rn(nd.x, nd.w) + g.dtg[0];
-            nd.y = __fdiv_rn(nd.y, nd.w) + g.dtg[1];
-            nd.z = __fdiv_rn(nd.z, nd.w) + g.dtg[2];
+    const int n_act = *n_active;
+    const int n_warps = gridDim.x * T3::WARPS;
+    constexpr int PLANE = T3::NX * T3::NY;
+    for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
+        TileCtx tc;
+        tile_from_list(g, __ldg(&tiles[a]), tc);
+        float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane < tc.count) p_next = q.P[tc.base + lane];
+        // node velocities of the footprint, in two batches of independent loads
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            constexpr int HB = (FOOT_ITERS + 1) / 2;
+            float4 nv[HB];
+#pragma unroll
+            for (int j = 0; j < HB; ++j) {
+                const int k = lane + 32 * (half * HB + j);
+                int gi = (half * HB + j) < FOOT_ITERS ? footprint_to_global(g, tc, k) : -1;
+                nv[j] = gi >= 0 ? __ldg(&grid[gi]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int j = 0; j < HB; ++j) {
+                const int k = lane + 32 * (half * HB + j);
+                float4 nd = nv[j];
+                if (nd.w > 0.0f) {   // update_grid (3d:253-256); one IEEE reciprocal, three multiplies
+                    const float inv = __frcp_rn(nd.w);
+                    nd.x = nd.x * inv + g.dtg[0];
+                    nd.y = nd.y * inv + g.dtg[1];
+                    nd.z = nd.z * inv + g.dtg[2];
+                }
+                if (k < T3::NODES) vt[k] = nd;
+            }
         }
-        vt[k] = nd;
-    }
-    __syncwarp();
+        __syncwarp();
 
-    for (int it = 0; it < tc.count; it += 32) {
-        if (it + lane >= tc.count) continue;
-        const int i = tc.base + it + lane;
-        const float4 p = q.P[i];
-        float pos[3] = {p.x, p.y, p.z};
-        int key[3];
-        if (classify<3>(g, pos, key) != CLS_ACTIVE) continue;   // g2p walks a_rect blocks only
-        TStencil s;
-        tile_stencil(g, tc, p.x, p.y, p.z, s);
-        // S = sum w v ; Dk = sum w v (o_k - 1) ; B col k = Dk - S c_k
-        float S[3] = {0.f, 0.f, 0.f}, Dx[3] = {0.f, 0.f, 0.f}, Dy[3] = {0.f, 0.f, 0.f}, Dz[3] = {0.f, 0.f, 0.f};
+        for (int it = 0; it < tc.count; it += 32) {
+            const bool active = it + lane < tc.count;
+            const int i = tc.base + it + lane;
+            const float4 p = p_next;
+            if (it + 32 + lane < tc.count) p_next = q.P[i + 32];   // prefetch the next window
+            float pos[3] = {p.x, p.y, p.z};
+            if (!active || classify_pos<3>(g, pos) != CLS_ACTIVE) continue;   // g2p walks a_rect blocks only
+            TStencil s;
+            tile_stencil(g, tc, p.x, p.y, p.z, s);
+            // S = sum w v ; Dk = sum w v (o_k - 1) ; B col k = Dk - S c_k
+            float S[3] = {0.f, 0.f, 0.f}, Dx[3] = {0.f, 0.f, 0.f}, Dy[3] = {0.f, 0.f, 0.f}, Dz[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int oz = 0; oz < 3; ++oz) {
-            float Pz[3] = {0.f, 0.f, 0.f}, Pdx[3] = {0.f, 0.f, 0.f}, Pdy[3] = {0.f, 0.f, 0.f};
+            for (int oz = 0; oz < 3; ++oz) {
+                float Pz[3] = {0.f, 0.f, 0.f}, Pdx[3] = {0.f, 0.f, 0.f}, Pdy[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int oy = 0; oy < 3; ++oy) {
-                const float4* row = vt + s.node0 + T3::NX * (oy + T3::NY * oz);
-                const float4 n0 = row[0], n1 = row[1], n2 = row[2];
-                float a0[3] = {n0.x * s.wx[0], n0.y * s.wx[0], n0.z * s.wx[0]};
-                float a2[3] = {n2.x * s.wx[2], n2.y * s.wx[2], n2.z * s.wx[2]};
-                float rs[3] = {a0[0] + n1.x * s.wx[1] + a2[0], a0[1] + n1.y * s.wx[1] + a2[1],
-                               a0[2] + n1.z * s.wx[1] + a2[2]};
+                for (int oy = 0; oy < 3; ++oy) {
+                    const float4* row = vt + s.node0 + T3::NX * oy + PLANE * oz;
+                    const float4 n0 = row[0], n1 = row[1], n2 = row[2];
+                    float a0[3] = {n0.x * s.wx[0], n0.y * s.wx[0], n0.z * s.wx[0]};
+                    float a2[3] = {n2.x * s.wx[2], n2.y * s.wx[2], n2.z * s.wx[2]};
+                    float rs[3] = {a0[0] + n1.x * s.wx[1] + a2[0], a0[1] + n1.y * s.wx[1] + a2[1],
+                                   a0[2] + n1.z * s.wx[1] + a2[2]};
+#pragma unroll
+                    for (int r = 0; r < 3; ++r) {
+                        const float rsw = rs[r] * s.wy[oy];
+                        Pz[r] += rsw;
+                        Pdx[r] += (a2[r] - a0[r]) * s.wy[oy];
+                        if (oy == 0) Pdy[r] -= rsw;
+                        if (oy == 2) Pdy[r] += rsw;
+                    }
+                }
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const float rsw = rs[r] * s.wy[oy];
-                    Pz[r] += rsw;
-                    Pdx[r] += (a2[r] - a0[r]) * s.wy[oy];
-                    if (oy == 0) Pdy[r] -= rsw;
-                    if (oy == 2) Pdy[r] += rsw;
+                    const float pz = Pz[r] * s.wz[oz];
+                    S[r] += pz;
+                    Dx[r] += Pdx[r] * s.wz[oz];
+                    Dy[r] += Pdy[r] * s.wz[oz];
+                    if (oz == 0) Dz[r] -= pz;
+                    if (oz == 2) Dz[r] += pz;
                 }
             }
+            float vel[3] = {S[0], S[1], S[2]};
+            float B[9];
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
-                const float pz = Pz[r] * s.wz[oz];
-                S[r] += pz;
-                Dx[r] += Pdx[r] * s.wz[oz];
-                Dy[r] += Pdy[r] * s.wz[oz];
-                if (oz == 0) Dz[r] -= pz;
-                if (oz == 2) Dz[r] += pz;
+                B[r] = Dx[r] - S[r] * s.cx;
+                B[3 + r] = Dy[r] - S[r] * s.cy;
+                B[6 + r] = Dz[r] - S[r] * s.cz;
             }
+            integrate_particle<3>(g, pos, vel, mouse);
+            if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
+            const float idw = q.V[i].w;
+            q.P[i] = make_float4(pos[0], pos[1], pos[2], p.w);
+            q.V[i] = make_float4(vel[0], vel[1], vel[2], idw);
+            q.CA[i] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);
+            q.CB[i] = make_float4(4.0f * B[4], 4.0f * B[5], 4.0f * B[6], 4.0f * B[7]);
+            q.CC[i] = 4.0f * B[8];
         }
-        float vel[3] = {S[0], S[1], S[2]};
-        float B[9];
-#pragma unroll
-        for (int r = 0; r < 3; ++r) {
-            B[r] = Dx[r] - S[r] * s.cx;
-            B[3 + r] = Dy[r] - S[r] * s.cy;
-            B[6 + r] = Dz[r] - S[r] * s.cz;
-        }
-        integrate_particle<3>(g, pos, vel, mouse);
-        if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
-        const float idw = q.V[i].w;
-        q.P[i] = make_float4(pos[0], pos[1], pos[2], p.w);
-        q.V[i] = make_float4(vel[0], vel[1], vel[2], idw);
-        q.CA[i] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);
-        q.CB[i] = make_float4(4.0f * B[4], 4.0f * B[5], 4.0f * B[6], 4.0f * B[7]);
-        q.CC[i] = 4.0f * B[8];
+        __syncwarp();
     }
 }
 
@@ -374,7 +452,8 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
 
 __global__ void __launch_bounds__(128)
 k_tile_perm(const __grid_constant__ Geo g, const int* __restrict__ count,
-            const int* __restrict__ start, int* __restrict__ perm) {
+            const int* __restrict__ start, int* __restrict__ perm,
+            int4* __restrict__ tiles, int* __restrict__ n_active) {
     const int lane = threadIdx.x & 31;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= g.n_tiles) return;
@@ -382,6 +461,7 @@ k_tile_perm(const __grid_constant__ Geo g, const int* __restrict__ count,
     const int base = start[c_first];
     const int n_t = start[c_first + Tile<3>::CELLS] - base;
     if (n_t <= 0) return;
+    if (lane == 0) tiles[atomicAdd(n_active, 1)] = make_int4(t, base, n_t, 0);
     int cnt[8], st[8];
     {
         const int4* cp = reinterpret_cast<const int4*>(count + c_first + lane * 8);

@@ -38,24 +38,22 @@ k_classify_count(const __grid_constant__ Geo g, const float4* __restrict__ P, in
     if (i < n) {
         float4 p = P[i];
         float pos[3] = {p.x, p.y, p.z};
-        int key[3];
         int bucket;
         if (is_tombstone(p.x)) {
             cls = CLS_DROPPED;
             bucket = g.n_cells_pad + 1;
         } else {
-            cls = classify<DIM>(g, pos, key);
+            int cell[3] = {0, 0, 0};
+#pragma unroll
+            for (int a = 0; a < DIM; ++a) cell[a] = rust_as_i32(floorf(pos[a]));
+            cls = classify_cells<DIM>(g, cell);
             if (cls == CLS_LIMBO) {
                 bucket = g.n_cells_pad;
             } else {
                 int rel[3] = {0, 0, 0};
 #pragma unroll
-                for (int a = 0; a < DIM; ++a) {
-                    int c = rust_as_i32(floorf(pos[a])) - g.org[a];
-                    // key and floor(pos) can disagree by one cell at a block face when grid_res
-                    // is not a power of two (rounded division); the bucket is only a sort key.
-                    rel[a] = min(max(c, 0), g.size[a] - 1);
-                }
+                for (int a = 0; a < DIM; ++a)   // in p_rect => inside the grid; clamp guards smem only
+                    rel[a] = min(max(cell[a] - g.org[a], 0), g.size[a] - 1);
                 bucket = tiled_cell_index<DIM>(g, rel);
             }
         }
