@@ -83,17 +83,23 @@ struct fluid_sim {
     int64_t cap = 0;
     Particles buf[2]{};
     int cur = 0;
-    int* cell_idx = nullptr;
-    int* rank = nullptr;
-    int* perm = nullptr;     // cell-sorted slot -> (rank, cell)-sorted slot inside each tile (3D)
+    // neighbour search (sort.cuh)
+    int* gcell = nullptr;    // per particle: bucket (tile * 256 + cell in tile)
+    int* rank = nullptr;     // per particle: rank inside its bucket
+    int* perm = nullptr;     // cell-sorted slot -> slot in the tile order
+    int* imm_list = nullptr; // particles that changed tile in the last g2p
     int4* tiles = nullptr;   // active tile list {tile, first slot, count, 0}, rebuilt by every sort
-    int* n_active = nullptr; // its length (device)
+    int* scal = nullptr;     // device scalars: [0] active tiles, [1] immigrants
+    int* cell_off = nullptr; // per bucket: first cell-sorted slot (cellStart)
+    int* tile_total = nullptr;
+    int* tile_base = nullptr;    // exclusive scan of tile_total; [n_tiles] = number of p_rect particles
+    bool sorted_valid = false;   // arrays are in tile order for the current positions
+    bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
+    int tile_order = ORDER_RANK_CELL;
     int sm_count = 148;
     unsigned grid_mass = 0, grid_p2g = 0, grid_g2p = 0;   // persistent grids: SMs x resident CTAs
 
-    int* count = nullptr;    // n_cells_pad + 2 buckets
-    int* start = nullptr;    // n_cells_pad + 3 (exclusive scan + total)
-    int64_t bucket_len = 0;
+    int* count = nullptr;    // per bucket, (n_tiles + 2) * 256; all zero outside a sort
     int* block_sums = nullptr;
     int64_t n_scan_blocks = 0;
     int* class_count = nullptr;   // 4 ints (device)
@@ -163,16 +169,19 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     }
     CU_TRY(cudaStreamSynchronize(s->stream));
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
-    cudaFree(s->cell_idx);
+    cudaFree(s->gcell);
     cudaFree(s->rank);
     cudaFree(s->perm);
-    s->cell_idx = s->rank = s->perm = nullptr;
+    cudaFree(s->imm_list);
+    s->gcell = s->rank = s->perm = s->imm_list = nullptr;
+    s->sorted_valid = s->counts_pending = false;
     s->buf[0] = nb[0];
     s->buf[1] = nb[1];
     s->cur = 0;
-    CU_TRY(cudaMalloc(&s->cell_idx, cap * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->gcell, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->rank, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->perm, cap * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->imm_list, cap * sizeof(int)));
     s->cap = cap;
     return FLUID_OK;
 }
@@ -303,41 +312,80 @@ struct DebugTaps {
     float* pressure = nullptr;
 };
 
+SortTables sort_tables(fluid_sim* s) {
+    SortTables t;
+    t.gcell = s->gcell;
+    t.rank = s->rank;
+    t.count = s->count;
+    t.tile_total = s->tile_total;
+    t.imm_list = s->imm_list;
+    t.scal = s->scal;
+    return t;
+}
+
+// scan over the tile totals, per-tile order, reorder (count[], tile_total[], gcell[], rank[] are filled)
 template <int DIM>
-fluid_status sort_particles(fluid_sim* s) {
+fluid_status sort_finish(fluid_sim* s) {
     const int n = static_cast<int>(s->n);
-    const int64_t m = s->bucket_len;   // n_cells_pad + 2
-    CU_TRY(cudaMemsetAsync(s->count, 0, m * sizeof(int), s->stream));
-    CU_TRY(cudaMemsetAsync(s->class_count, 0, 4 * sizeof(int), s->stream));
-    Particles& src = s->buf[s->cur];
-    Particles& dst = s->buf[s->cur ^ 1];
-    if (n > 0) {
-        k_classify_count<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(
-            s->geo, src.P, n, s->cell_idx, s->rank, s->count, s->class_count);
-        ++s->launches;
-    }
+    const int m = s->geo.n_tiles + 2;
     const unsigned nb = static_cast<unsigned>(s->n_scan_blocks);
-    k_scan_partial<<<nb, SCAN_THREADS, 0, s->stream>>>(s->count, static_cast<int>(m), s->block_sums);
+    k_scan_partial<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums);
     k_scan_sums<<<1, 1024, 0, s->stream>>>(s->block_sums, static_cast<int>(nb));
-    k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->count, static_cast<int>(m), s->block_sums, s->start);
-    s->launches += 3;
+    k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base);
+    CU_TRY(cudaMemsetAsync(s->scal, 0, 2 * sizeof(int), s->stream));
+    const unsigned pb = blocks_for(static_cast<int64_t>(m) * 32, 128);
+    const int order = DIM == 3 ? s->tile_order : ORDER_CELL;
+    if (order == ORDER_RANK_BANK)
+        k_tile_perm<ORDER_RANK_BANK><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
+    else if (order == ORDER_RANK_CELL)
+        k_tile_perm<ORDER_RANK_CELL><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
+    else
+        k_tile_perm<ORDER_CELL><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
+    s->launches += 4;
     if (n > 0) {
-        if (DIM == 3) {
-            // order inside each tile: (rank in cell, cell) — see phases_tiled.cuh
-            const int64_t tile_threads = static_cast<int64_t>(s->geo.n_tiles) * 32;
-            CU_TRY(cudaMemsetAsync(s->n_active, 0, sizeof(int), s->stream));
-            k_tile_perm<<<blocks_for(tile_threads, 128), 128, 0, s->stream>>>(s->geo, s->count, s->start, s->perm,
-                                                                            s->tiles, s->n_active);
-            k_reorder_perm<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->cell_idx, s->rank, s->start,
-                                                                          s->perm, s->geo.n_cells_pad);
-            s->launches += 2;
-        } else {
-            k_reorder<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->cell_idx, s->rank, s->start);
-            ++s->launches;
-        }
+        Particles& src = s->buf[s->cur];
+        Particles& dst = s->buf[s->cur ^ 1];
+        k_reorder_perm<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->gcell, s->rank, s->cell_off, s->perm);
+        ++s->launches;
         s->cur ^= 1;
     }
     CU_TRY(cudaGetLastError());
+    s->sorted_valid = true;
+    s->counts_pending = false;
+    return FLUID_OK;
+}
+
+// cold start: every particle classified and counted with global atomics
+template <int DIM>
+fluid_status sort_cold(fluid_sim* s) {
+    const int n = static_cast<int>(s->n);
+    const int64_t buckets = static_cast<int64_t>(s->geo.n_tiles + 2) * TILE_CELLS;
+    CU_TRY(cudaMemsetAsync(s->count, 0, buckets * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->tile_total, 0, (s->geo.n_tiles + 2) * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->class_count, 0, 4 * sizeof(int), s->stream));
+    if (n > 0) {
+        k_classify_all<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur].P, n, sort_tables(s),
+                                                                      s->class_count);
+        ++s->launches;
+    }
+    return sort_finish<DIM>(s);
+}
+
+// steady state: g2p already counted the particles that stayed in their tile
+template <int DIM>
+fluid_status sort_steady(fluid_sim* s) {
+    const int n = static_cast<int>(s->n);
+    k_immigrants<<<s->sm_count * 4, 256, 0, s->stream>>>(sort_tables(s));
+    k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, s->buf[s->cur].P, s->tile_base + s->geo.n_tiles, n,
+                                                   sort_tables(s));
+    s->launches += 2;
+    return sort_finish<DIM>(s);
+}
+
+template <int DIM>
+fluid_status ensure_sorted(fluid_sim* s) {
+    if (!s->sorted_valid) return sort_cold<DIM>(s);
+    if (s->counts_pending) return sort_steady<DIM>(s);
     return FLUID_OK;
 }
 
@@ -359,7 +407,7 @@ template <int DIM>
 fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const DebugTaps* dbg) {
     if (!s->rect_set || s->n == 0) return FLUID_OK;   // no blocks to walk (3d:149 over an empty rect)
     const int n = static_cast<int>(s->n);
-    const int* n_dep = s->start + s->geo.n_cells_pad;
+    const int* n_dep = s->tile_base + s->geo.n_tiles;
     cudaEvent_t* ev = s->ev;
     if (s->profiling) {
         if (s->pool_used == PROFILE_POOL) ST_TRY(profile_drain(s));
@@ -368,7 +416,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
         timed = true;
     }
     if (timed) CU_TRY(cudaEventRecord(ev[0], s->stream));
-    ST_TRY(sort_particles<DIM>(s));
+    ST_TRY(ensure_sorted<DIM>(s));
     Particles q = s->buf[s->cur];
     if (dbg && (dbg->ids || dbg->cell || dbg->key)) {
         k_debug_keys<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, q, n_dep, dbg->ids, dbg->cell,
@@ -383,15 +431,17 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
         CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
         const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);   // never more CTAs than tiles / 4
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-        k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->tiles, s->n_active,
-                                                                              s->gmass);
+        const int* n_act = s->scal + SCAL_N_ACTIVE;
+        k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->tiles, n_act, s->gmass);
         if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         k_p2g_tiled<<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
-            s->geo, q, s->tiles, s->n_active, s->gmass, s->grid, dbg ? dbg->density : nullptr,
+            s->geo, q, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
             dbg ? dbg->pressure : nullptr);
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
-        k_g2p_tiled<<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(s->geo, q, s->tiles, s->n_active,
-                                                                             s->grid, d_mouse);
+        // g2p also counts the particles for the next substep's neighbour search
+        k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(s->geo, q, s->tiles, n_act, s->grid,
+                                                                                   d_mouse, sort_tables(s));
+        s->counts_pending = true;
     } else {
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
         k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid);
@@ -401,6 +451,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                                                                       dbg ? dbg->pressure : nullptr);
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
         k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid, d_mouse);
+        s->sorted_valid = false;   // positions moved; the generic path re-sorts from scratch
     }
     if (timed) {
         CU_TRY(cudaEventRecord(ev[5], s->stream));
@@ -433,7 +484,7 @@ fluid_status refresh_counts(fluid_sim* s, int64_t counts[4]) {
         counts[2] = s->n;
         return FLUID_OK;
     }
-    ST_TRY(s->dim == 3 ? sort_particles<3>(s) : sort_particles<2>(s));
+    ST_TRY(s->dim == 3 ? sort_cold<3>(s) : sort_cold<2>(s));
     int h[4];
     CU_TRY(cudaMemcpyAsync(h, s->class_count, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
@@ -503,8 +554,8 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     if (ce == cudaSuccess) ce = cudaMalloc(&s->d_mouse, 2 * sizeof(float));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->class_count, 4 * sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->d_counter, sizeof(int));
-    if (ce == cudaSuccess) ce = cudaMalloc(&s->n_active, sizeof(int));
-    if (ce == cudaSuccess) ce = cudaMemset(s->n_active, 0, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->scal, 8 * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemset(s->scal, 0, 8 * sizeof(int));
     for (int i = 0; i < N_EVENTS && ce == cudaSuccess; ++i) ce = cudaEventCreate(&s->ev[i]);
     if (ce != cudaSuccess) {
         fluid_destroy(s);
@@ -513,6 +564,9 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     s->stream = s->own_stream;
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
+    const char* order = std::getenv("FLUID_B200_ORDER");   // 1 = (rank, cell), 2 = (rank, bank class, cell)
+    if (order && order[0] == '2') s->tile_order = ORDER_RANK_BANK;
+    if (order && order[0] == '1') s->tile_order = ORDER_RANK_CELL;
     cudaFuncSetAttribute(k_p2g_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
     {   // persistent grids: one wave of resident CTAs per kernel (148 SMs x occupancy)
         cudaDeviceProp prop{};
@@ -522,7 +576,7 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
         s->grid_mass = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_tiled, T3::THREADS, sizeof(P2GSmem));
         s->grid_p2g = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled, T3::THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled<true>, T3::THREADS, 0);
         s->grid_g2p = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
         (void)cudaGetLastError();
     }
@@ -535,14 +589,17 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
-    cudaFree(s->cell_idx);
+    cudaFree(s->gcell);
     cudaFree(s->rank);
     cudaFree(s->perm);
+    cudaFree(s->imm_list);
     cudaFree(s->gmass);
     cudaFree(s->tiles);
-    cudaFree(s->n_active);
+    cudaFree(s->scal);
     cudaFree(s->count);
-    cudaFree(s->start);
+    cudaFree(s->cell_off);
+    cudaFree(s->tile_total);
+    cudaFree(s->tile_base);
     cudaFree(s->block_sums);
     cudaFree(s->class_count);
     cudaFree(s->grid);
@@ -639,27 +696,32 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     cudaFree(s->gmass);
     cudaFree(s->tiles);
     cudaFree(s->count);
-    cudaFree(s->start);
+    cudaFree(s->cell_off);
+    cudaFree(s->tile_total);
+    cudaFree(s->tile_base);
     cudaFree(s->block_sums);
     s->grid = nullptr;
     s->gmass = nullptr;
     s->tiles = nullptr;
-    s->count = s->start = s->block_sums = nullptr;
+    s->count = s->cell_off = s->tile_total = s->tile_base = s->block_sums = nullptr;
     s->rect_set = false;
-    const int64_t m = static_cast<int64_t>(g.n_cells_pad) + 2;
-    const int64_t nb = (m + SCAN_CHUNK - 1) / SCAN_CHUNK;
+    s->sorted_valid = s->counts_pending = false;
+    const int64_t n_pt = static_cast<int64_t>(g.n_tiles) + 2;            // tiles + the two pseudo tiles
+    const int64_t m = n_pt * TILE_CELLS;                                  // buckets
+    const int64_t nb = (n_pt + SCAN_CHUNK - 1) / SCAN_CHUNK;
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
-    if (D == 3) {
-        CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
-        CU_TRY(cudaMalloc(&s->tiles, static_cast<int64_t>(g.n_tiles) * sizeof(int4)));
-    }
+    if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + 2) * sizeof(int4)));
     CU_TRY(cudaMalloc(&s->count, (m + 8) * sizeof(int)));
-    CU_TRY(cudaMalloc(&s->start, (m + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->cell_off, (m + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->tile_total, (n_pt + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->tile_base, (n_pt + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->block_sums, nb * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(s->count, 0, (m + 8) * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->tile_total, 0, (n_pt + 8) * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->tile_base, 0, (n_pt + 8) * sizeof(int), s->stream));
     CU_TRY(cudaMemsetAsync(s->grid, 0, (nodes + 2 * g.guard) * sizeof(float4), s->stream));
-    CU_TRY(cudaMemsetAsync(s->start, 0, (m + 8) * sizeof(int), s->stream));
     s->grid_nodes = nodes;
-    s->bucket_len = m;
     s->n_scan_blocks = nb;
     s->geo = g;
     s->rect_set = true;
@@ -694,6 +756,7 @@ static fluid_status add_from_device(fluid_sim* s, const float* d_rec, const int*
     CU_TRY(cudaGetLastError());
     s->n += n;
     s->next_id += static_cast<int32_t>(n);
+    s->sorted_valid = s->counts_pending = false;
     return FLUID_OK;
 }
 
@@ -725,6 +788,7 @@ fluid_status fluid_clear_particles(fluid_sim* s) {
     s->n = 0;
     s->next_id = 0;
     s->dropped_total = 0;
+    s->sorted_valid = s->counts_pending = false;
     return FLUID_OK;
 }
 
@@ -876,7 +940,7 @@ fluid_status fluid_debug_substep(fluid_sim* s, const float* mouse_xy, int64_t ca
     if (st == FLUID_OK) st = substep(s, d_mouse, true, &taps);
     int h_dep = 0;
     if (st == FLUID_OK) {
-        ce = cudaMemcpyAsync(&h_dep, s->start + s->geo.n_cells_pad, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+        ce = cudaMemcpyAsync(&h_dep, s->tile_base + s->geo.n_tiles, sizeof(int), cudaMemcpyDeviceToHost, s->stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->stream);
         if (ce != cudaSuccess) st = fail(FLUID_ERR_CUDA, cudaGetErrorString(ce));
     }
@@ -904,7 +968,7 @@ fluid_status fluid_debug_neighbour_table(fluid_sim* s, int64_t capacity, int32_t
     if (n_written) *n_written = 0;
     if (!s->rect_set || s->n == 0) return FLUID_OK;
     const int64_t n = s->n;
-    ST_TRY(s->dim == 3 ? sort_particles<3>(s) : sort_particles<2>(s));
+    ST_TRY(s->dim == 3 ? sort_cold<3>(s) : sort_cold<2>(s));
     int *d_ids = nullptr, *d_ref = nullptr;
     cudaError_t ce = cudaMalloc(&d_ids, n * sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&d_ref, n * sizeof(int));
@@ -912,7 +976,7 @@ fluid_status fluid_debug_neighbour_table(fluid_sim* s, int64_t capacity, int32_t
         cudaFree(d_ids); cudaFree(d_ref);
         return fail(FLUID_ERR_OUT_OF_MEMORY, "fluid_debug_neighbour_table: scratch allocation failed");
     }
-    const int* n_dep = s->start + s->geo.n_cells_pad;
+    const int* n_dep = s->tile_base + s->geo.n_tiles;
     if (s->dim == 3)
         k_debug_keys<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n_dep, d_ids, nullptr, nullptr, d_ref);
     else

@@ -36,6 +36,7 @@ struct T3 {
 
 struct TileCtx {
     int c0[3];     // first cell of the tile, relative to the grid origin
+    int tile;      // tile id
     int base;      // first particle slot
     int count;     // particles in the tile
 };
@@ -44,6 +45,7 @@ struct TileCtx {
 // The tile kernels run persistent warps that stride over this list, so empty tiles cost nothing.
 __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileCtx& tc) {
     const int t = e.x;
+    tc.tile = t;
     tc.base = e.y;
     tc.count = e.z;
     int tx = t % g.tdim[0];
@@ -343,13 +345,19 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
 
 // ---- update + g2p -----------------------------------------------------------------------------
 
+// COUNT: also start the next substep's neighbour search (sort.cuh): every particle of the tile
+// gets its new bucket; the ones that stay in this tile are ranked with shared-memory integer
+// atomics (native ATOMS.ADD), the few that change tile or are dropped go to the immigrant list.
+template <bool COUNT>
 __global__ void __launch_bounds__(T3::THREADS)
 k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__ tiles,
             const int* __restrict__ n_active, const float4* __restrict__ grid,
-            const float* __restrict__ mouse) {
+            const float* __restrict__ mouse, SortTables st) {
     __shared__ float4 sm[T3::WARPS * T3::NODES];
+    __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* vt = sm + warp * T3::NODES;
+    int* scnt = scnt_all + warp * TILE_CELLS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
     constexpr int PLANE = T3::NX * T3::NY;
@@ -358,6 +366,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
         tile_from_list(g, __ldg(&tiles[a]), tc);
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < tc.count) p_next = q.P[tc.base + lane];
+        if (COUNT) {
+#pragma unroll
+            for (int j = 0; j < TILE_CELLS / 32; ++j) scnt[lane + 32 * j] = 0;
+        }
         // node velocities of the footprint, in two batches of independent loads
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -390,119 +402,92 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
             const float4 p = p_next;
             if (it + 32 + lane < tc.count) p_next = q.P[i + 32];   // prefetch the next window
             float pos[3] = {p.x, p.y, p.z};
-            if (!active || classify_pos<3>(g, pos) != CLS_ACTIVE) continue;   // g2p walks a_rect blocks only
-            TStencil s;
-            tile_stencil(g, tc, p.x, p.y, p.z, s);
-            // S = sum w v ; Dk = sum w v (o_k - 1) ; B col k = Dk - S c_k
-            float S[3] = {0.f, 0.f, 0.f}, Dx[3] = {0.f, 0.f, 0.f}, Dy[3] = {0.f, 0.f, 0.f}, Dz[3] = {0.f, 0.f, 0.f};
+            const bool advance = active && classify_pos<3>(g, pos) == CLS_ACTIVE;   // g2p walks a_rect blocks only
+            if (advance) {
+                TStencil s;
+                tile_stencil(g, tc, p.x, p.y, p.z, s);
+                // S = sum w v ; Dk = sum w v (o_k - 1) ; B col k = Dk - S c_k
+                float S[3] = {0.f, 0.f, 0.f}, Dx[3] = {0.f, 0.f, 0.f}, Dy[3] = {0.f, 0.f, 0.f}, Dz[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-            for (int oz = 0; oz < 3; ++oz) {
-                float Pz[3] = {0.f, 0.f, 0.f}, Pdx[3] = {0.f, 0.f, 0.f}, Pdy[3] = {0.f, 0.f, 0.f};
+                for (int oz = 0; oz < 3; ++oz) {
+                    float Pz[3] = {0.f, 0.f, 0.f}, Pdx[3] = {0.f, 0.f, 0.f}, Pdy[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-                for (int oy = 0; oy < 3; ++oy) {
-                    const float4* row = vt + s.node0 + T3::NX * oy + PLANE * oz;
-                    const float4 n0 = row[0], n1 = row[1], n2 = row[2];
-                    float a0[3] = {n0.x * s.wx[0], n0.y * s.wx[0], n0.z * s.wx[0]};
-                    float a2[3] = {n2.x * s.wx[2], n2.y * s.wx[2], n2.z * s.wx[2]};
-                    float rs[3] = {a0[0] + n1.x * s.wx[1] + a2[0], a0[1] + n1.y * s.wx[1] + a2[1],
-                                   a0[2] + n1.z * s.wx[1] + a2[2]};
+                    for (int oy = 0; oy < 3; ++oy) {
+                        const float4* row = vt + s.node0 + T3::NX * oy + PLANE * oz;
+                        const float4 n0 = row[0], n1 = row[1], n2 = row[2];
+                        float a0[3] = {n0.x * s.wx[0], n0.y * s.wx[0], n0.z * s.wx[0]};
+                        float a2[3] = {n2.x * s.wx[2], n2.y * s.wx[2], n2.z * s.wx[2]};
+                        float rs[3] = {a0[0] + n1.x * s.wx[1] + a2[0], a0[1] + n1.y * s.wx[1] + a2[1],
+                                       a0[2] + n1.z * s.wx[1] + a2[2]};
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            const float rsw = rs[r] * s.wy[oy];
+                            Pz[r] += rsw;
+                            Pdx[r] += (a2[r] - a0[r]) * s.wy[oy];
+                            if (oy == 0) Pdy[r] -= rsw;
+                            if (oy == 2) Pdy[r] += rsw;
+                        }
+                    }
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        const float rsw = rs[r] * s.wy[oy];
-                        Pz[r] += rsw;
-                        Pdx[r] += (a2[r] - a0[r]) * s.wy[oy];
-                        if (oy == 0) Pdy[r] -= rsw;
-                        if (oy == 2) Pdy[r] += rsw;
+                        const float pz = Pz[r] * s.wz[oz];
+                        S[r] += pz;
+                        Dx[r] += Pdx[r] * s.wz[oz];
+                        Dy[r] += Pdy[r] * s.wz[oz];
+                        if (oz == 0) Dz[r] -= pz;
+                        if (oz == 2) Dz[r] += pz;
                     }
                 }
+                float vel[3] = {S[0], S[1], S[2]};
+                float B[9];
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
-                    const float pz = Pz[r] * s.wz[oz];
-                    S[r] += pz;
-                    Dx[r] += Pdx[r] * s.wz[oz];
-                    Dy[r] += Pdy[r] * s.wz[oz];
-                    if (oz == 0) Dz[r] -= pz;
-                    if (oz == 2) Dz[r] += pz;
+                    B[r] = Dx[r] - S[r] * s.cx;
+                    B[3 + r] = Dy[r] - S[r] * s.cy;
+                    B[6 + r] = Dz[r] - S[r] * s.cz;
+                }
+                integrate_particle<3>(g, pos, vel, mouse);
+                if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
+                const float idw = q.V[i].w;
+                q.P[i] = make_float4(pos[0], pos[1], pos[2], p.w);
+                q.V[i] = make_float4(vel[0], vel[1], vel[2], idw);
+                q.CA[i] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);
+                q.CB[i] = make_float4(4.0f * B[4], 4.0f * B[5], 4.0f * B[6], 4.0f * B[7]);
+                q.CC[i] = 4.0f * B[8];
+            }
+            if (COUNT) {
+                // bucket of the (possibly moved) particle; frozen halo particles keep theirs
+                int cls = -1, bucket = 0;
+                if (active) bucket = bucket_of<3>(g, make_float4(pos[0], pos[1], pos[2], 0.f), cls);
+                const bool stays = active && (bucket >> 8) == tc.tile;
+                const bool leaves = active && !stays;
+                if (active) st.gcell[i] = bucket;
+                if (stays) st.rank[i] = atomicAdd(&scnt[bucket & (TILE_CELLS - 1)], 1);
+                const unsigned lm = __ballot_sync(0xffffffffu, leaves);
+                if (lm) {
+                    int slot = 0;
+                    if (lane == 0) slot = atomicAdd(&st.scal[SCAL_N_IMM], __popc(lm));
+                    slot = __shfl_sync(0xffffffffu, slot, 0);
+                    if (leaves) st.imm_list[slot + __popc(lm & ((1u << lane) - 1u))] = i;
                 }
             }
-            float vel[3] = {S[0], S[1], S[2]};
-            float B[9];
+        }
+        __syncwarp();
+        if (COUNT) {
+            // residents per cell -> count[], their total -> tile_total[] (plain stores: this warp owns
+            // the tile; immigrants are added by k_immigrants afterwards)
+            int total = 0;
 #pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                B[r] = Dx[r] - S[r] * s.cx;
-                B[3 + r] = Dy[r] - S[r] * s.cy;
-                B[6 + r] = Dz[r] - S[r] * s.cz;
+            for (int j = 0; j < TILE_CELLS / 32; ++j) {
+                const int c = scnt[lane + 32 * j];
+                st.count[tc.tile * TILE_CELLS + lane + 32 * j] = c;
+                total += c;
             }
-            integrate_particle<3>(g, pos, vel, mouse);
-            if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
-            const float idw = q.V[i].w;
-            q.P[i] = make_float4(pos[0], pos[1], pos[2], p.w);
-            q.V[i] = make_float4(vel[0], vel[1], vel[2], idw);
-            q.CA[i] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);
-            q.CB[i] = make_float4(4.0f * B[4], 4.0f * B[5], 4.0f * B[6], 4.0f * B[7]);
-            q.CC[i] = 4.0f * B[8];
+            total = __reduce_add_sync(0xffffffffu, total);
+            if (lane == 0) st.tile_total[tc.tile] = total;
         }
         __syncwarp();
     }
-}
-
-// ---- sort order inside a tile: (rank in cell, cell) ---------------------------------------------
-// One warp per tile turns the cell-sorted slot (cellStart[cell] + rank) into the slot of the
-// (rank, cell) order, so that consecutive particles of a tile lie in distinct cells.
-
-__global__ void __launch_bounds__(128)
-k_tile_perm(const __grid_constant__ Geo g, const int* __restrict__ count,
-            const int* __restrict__ start, int* __restrict__ perm,
-            int4* __restrict__ tiles, int* __restrict__ n_active) {
-    const int lane = threadIdx.x & 31;
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= g.n_tiles) return;
-    const int c_first = t * Tile<3>::CELLS;
-    const int base = start[c_first];
-    const int n_t = start[c_first + Tile<3>::CELLS] - base;
-    if (n_t <= 0) return;
-    if (lane == 0) tiles[atomicAdd(n_active, 1)] = make_int4(t, base, n_t, 0);
-    int cnt[8], st[8];
-    {
-        const int4* cp = reinterpret_cast<const int4*>(count + c_first + lane * 8);
-        const int4* sp = reinterpret_cast<const int4*>(start + c_first + lane * 8);
-        int4 a = cp[0], b = cp[1], c = sp[0], d = sp[1];
-        cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
-        cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
-        st[0] = c.x; st[1] = c.y; st[2] = c.z; st[3] = c.w;
-        st[4] = d.x; st[5] = d.y; st[6] = d.z; st[7] = d.w;
-    }
-    int rank_base = base;
-    for (int r = 0;; ++r) {
-        int mine = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) mine += cnt[j] > r;
-        int inc = warp_inclusive_scan(mine);
-        int total = __shfl_sync(0xffffffffu, inc, 31);
-        if (total == 0) break;
-        int dst = rank_base + inc - mine;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (cnt[j] > r) perm[st[j] + r] = dst++;
-        rank_base += total;
-    }
-}
-
-template <int DIM>
-__global__ void __launch_bounds__(256)
-k_reorder_perm(Particles src, Particles dst, int n, const int* __restrict__ cell_idx,
-               const int* __restrict__ rank, const int* __restrict__ start,
-               const int* __restrict__ perm, int n_cells_pad) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    int c = cell_idx[i];
-    int d = start[c] + rank[i];
-    if (c < n_cells_pad) d = perm[d];     // the two tail buckets (ignored / dropped) keep their slot
-    dst.P[d] = src.P[i];
-    dst.V[d] = src.V[i];
-    dst.CA[d] = src.CA[i];
-    dst.CB[d] = src.CB[i];
-    dst.CC[d] = src.CC[i];
 }
 
 }  // namespace fluid

@@ -1,13 +1,24 @@
-// sort.cuh — uniform-grid neighbour search: cell keys, counting sort, reorder, cellStart table.
+// sort.cuh — uniform-grid neighbour search: cell keys, counting sort, reorder, cellStart tables.
 //
 // GPU stand-in for the reference's `particles_mul: AHashMap<block key, Vec<Particle>>` and its
-// per-block migration mailboxes (3d:52,56,104-108,345-380).  Every substep:
-//   1. k_classify_count: block key (div_euclid, 3d:398-401) -> class; cell = floor(pos)
-//      (3d:153) -> tiled cell index; rank = atomicAdd(count[cell], 1)
-//   2. exclusive scan of count -> cellStart (hand-written 3-kernel scan, no CUB)
-//   3. k_reorder: dst = cellStart[cell] + rank; all SoA streams move to the other buffer
-// Buckets n_cells_pad and n_cells_pad+1 collect the particles the reference ignores (key
-// outside p_rect) and the ones it dropped in migration (3d:356-366).
+// per-block migration mailboxes `swap_mul` (3d:52,56,104-108,345-380).
+//
+// Buckets.  The grid is cut into tiles of 256 cells (8x8x4 in 3D, 16x16 in 2D); bucket id =
+// tile * 256 + cell-in-tile.  Two pseudo tiles follow the real ones: tile n_tiles collects the
+// particles the reference ignores (block key outside p_rect), tile n_tiles + 1 the ones it dropped
+// in migration (3d:356-366).
+//
+// Every substep the particles are brought into the order (tile, rank in cell, cell):
+//   counts   count[bucket], tile_total[tile] and per particle (bucket, rank)
+//            - steady state (3D tiled path): g2p counts the particles that stay in their tile in
+//              SHARED memory (native integer atomics) and lists the few that change tile;
+//              k_immigrants / k_tail give those their rank with global atomics;
+//            - cold start (after add_particles / set_rect, and the generic path): k_classify_all
+//              does it for every particle with global atomics;
+//   scan     exclusive scan over the TILE totals only (hand-written three-kernel scan, no CUB);
+//   perm     one warp per tile: cell offsets inside the tile (cellStart), the slot of every
+//            (cell, rank) in the chosen order, the active-tile list; resets count[] for reuse;
+//   reorder  all SoA streams move to the other buffer.
 #pragma once
 
 #include "common.cuh"
@@ -22,54 +33,113 @@ struct Particles {
     float*  CC;   // C[8]      (3D only)
 };
 
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;   // 2048 counts per block
+// Everything the counting kernels write.
+struct SortTables {
+    int* gcell;        // per particle: bucket
+    int* rank;         // per particle: rank inside its bucket
+    int* count;        // per bucket (n_cells_pad + 512)
+    int* tile_total;   // per tile (+2 pseudo tiles)
+    int* imm_list;     // particles that changed tile in g2p
+    int* scal;         // [0] n_active tiles, [1] n_imm
+};
+
+constexpr int TILE_CELLS = 256;
+constexpr int SCAL_N_ACTIVE = 0, SCAL_N_IMM = 1;
 
 __device__ __forceinline__ bool is_tombstone(float x) { return isinf(x) && x > 0.0f; }
 
+__device__ __forceinline__ int limbo_bucket(const Geo& g) { return g.n_cells_pad; }
+__device__ __forceinline__ int dropped_bucket(const Geo& g) { return g.n_cells_pad + TILE_CELLS; }
+
+// Bucket and class of a position (exact integer rules, common.cuh).
+template <int DIM>
+__device__ __forceinline__ int bucket_of(const Geo& g, const float4 p, int& cls) {
+    if (is_tombstone(p.x)) {
+        cls = CLS_DROPPED;
+        return dropped_bucket(g);
+    }
+    const float pos[3] = {p.x, p.y, p.z};
+    int cell[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < DIM; ++a) cell[a] = rust_as_i32(floorf(pos[a]));
+    cls = classify_cells<DIM>(g, cell);
+    if (cls == CLS_LIMBO) return limbo_bucket(g);
+    int rel[3] = {0, 0, 0};
+#pragma unroll
+    for (int a = 0; a < DIM; ++a)   // key in p_rect => cell inside the grid; the clamp guards memory only
+        rel[a] = min(max(cell[a] - g.org[a], 0), g.size[a] - 1);
+    return tiled_cell_index<DIM>(g, rel);
+}
+
+// One global-atomic count: rank inside the bucket, tile total aggregated per warp.
+__device__ __forceinline__ void count_global(const SortTables& t, int i, int bucket, bool valid) {
+    const int lane = threadIdx.x & 31;
+    const int tile = valid ? (bucket >> 8) : (-1 - lane);
+    if (valid) {
+        t.gcell[i] = bucket;
+        t.rank[i] = atomicAdd(&t.count[bucket], 1);
+    }
+    const unsigned peers = __match_any_sync(0xffffffffu, tile);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&t.tile_total[tile], __popc(peers));
+}
+
+// Cold start: every particle through global atomics.
 template <int DIM>
 __global__ void __launch_bounds__(256)
-k_classify_count(const __grid_constant__ Geo g, const float4* __restrict__ P, int n,
-                 int* __restrict__ cell_idx, int* __restrict__ rank, int* __restrict__ count,
-                 int* __restrict__ class_count) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int cls = -1;
-    if (i < n) {
-        float4 p = P[i];
-        float pos[3] = {p.x, p.y, p.z};
-        int bucket;
-        if (is_tombstone(p.x)) {
-            cls = CLS_DROPPED;
-            bucket = g.n_cells_pad + 1;
-        } else {
-            int cell[3] = {0, 0, 0};
-#pragma unroll
-            for (int a = 0; a < DIM; ++a) cell[a] = rust_as_i32(floorf(pos[a]));
-            cls = classify_cells<DIM>(g, cell);
-            if (cls == CLS_LIMBO) {
-                bucket = g.n_cells_pad;
-            } else {
-                int rel[3] = {0, 0, 0};
-#pragma unroll
-                for (int a = 0; a < DIM; ++a)   // in p_rect => inside the grid; clamp guards smem only
-                    rel[a] = min(max(cell[a] - g.org[a], 0), g.size[a] - 1);
-                bucket = tiled_cell_index<DIM>(g, rel);
-            }
-        }
-        cell_idx[i] = bucket;
-        rank[i] = atomicAdd(&count[bucket], 1);
-    }
-    // class counters: one atomic per warp and class
-    unsigned full = 0xffffffffu;
+k_classify_all(const __grid_constant__ Geo g, const float4* __restrict__ P, int n, SortTables t,
+               int* __restrict__ class_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int cls = -1, bucket = 0;
+    if (i < n) bucket = bucket_of<DIM>(g, P[i], cls);
+    count_global(t, i, bucket, i < n);
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
-        unsigned m = __ballot_sync(full, cls == c);
+        unsigned m = __ballot_sync(0xffffffffu, cls == c);
         if ((threadIdx.x & 31) == 0 && m) atomicAdd(&class_count[c], __popc(m));
     }
 }
 
-// ---- exclusive scan over the count array -----------------------------------------------
+// Steady state: the particles g2p listed because they left their tile (or were dropped).
+__global__ void __launch_bounds__(256)
+k_immigrants(SortTables t) {
+    const int n_imm = t.scal[SCAL_N_IMM];
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (n_imm + stride - 1) / stride;   // every lane takes part in the warp votes
+    for (int r = 0; r < rounds; ++r) {
+        const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = j < n_imm;
+        int i = 0, bucket = 0;
+        if (valid) {
+            i = t.imm_list[j];
+            bucket = t.gcell[i];
+        }
+        count_global(t, i, bucket, valid);
+    }
+}
+
+// Steady state: the tail of the array (ignored and dropped particles) is not covered by any tile.
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_tail(const __grid_constant__ Geo g, const float4* __restrict__ P, const int* __restrict__ n_deposit,
+       int n, SortTables t) {
+    const int first = *n_deposit;
+    const int len = n - first;
+    const int stride = gridDim.x * blockDim.x;
+    const int rounds = (len + stride - 1) / stride;
+    for (int r = 0; r < rounds; ++r) {
+        const int i = first + r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = i < n;
+        int cls = -1, bucket = 0;
+        if (valid) bucket = bucket_of<DIM>(g, P[i], cls);
+        count_global(t, i, bucket, valid);
+    }
+}
+
+// ---- exclusive scan (used over the tile totals) -----------------------------------------------
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_CHUNK = SCAN_THREADS * SCAN_ITEMS;   // 2048 values per block
 
 __device__ __forceinline__ int warp_inclusive_scan(int v) {
     int lane = threadIdx.x & 31;
@@ -103,17 +173,11 @@ __device__ __forceinline__ int block_exclusive_scan(int v, int& total) {
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_partial(const int* __restrict__ count, int m, int* __restrict__ block_sums) {
+k_scan_partial(const int* __restrict__ in, int m, int* __restrict__ block_sums) {
     int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int s = 0;
-    if (base + SCAN_ITEMS <= m) {
-        const int4* q = reinterpret_cast<const int4*>(count + base);
-        int4 a = q[0], b = q[1];
-        s = a.x + a.y + a.z + a.w + b.x + b.y + b.z + b.w;
-    } else {
-        for (int k = 0; k < SCAN_ITEMS; ++k)
-            if (base + k < m) s += count[base + k];
-    }
+    for (int k = 0; k < SCAN_ITEMS; ++k)
+        if (base + k < m) s += in[base + k];
     int total;
     block_exclusive_scan(s, total);
     if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
@@ -132,37 +196,155 @@ k_scan_sums(int* __restrict__ block_sums, int nb) {
     }
 }
 
+// out[k] = exclusive prefix, out[m] = grand total; the input is zeroed for the next round.
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_final(const int* __restrict__ count, int m, const int* __restrict__ block_sums,
-             int* __restrict__ start) {
+k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, int* __restrict__ out) {
     int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     int s = 0;
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        v[k] = (base + k < m) ? count[base + k] : 0;
+        v[k] = (base + k < m) ? in[base + k] : 0;
         s += v[k];
     }
     int total;
     int ex = block_exclusive_scan(s, total) + block_sums[blockIdx.x];
 #pragma unroll
     for (int k = 0; k < SCAN_ITEMS; ++k) {
-        if (base + k < m) start[base + k] = ex;
+        if (base + k < m) {
+            out[base + k] = ex;
+            in[base + k] = 0;
+        }
         ex += v[k];
     }
-    // start[m] = grand total (written by the thread that owns the last element)
-    if (base <= m - 1 && m - 1 < base + SCAN_ITEMS) start[m] = ex;
+    if (base <= m - 1 && m - 1 < base + SCAN_ITEMS) out[m] = ex;
 }
 
-// ---- reorder ---------------------------------------------------------------------------
+// ---- per-tile order ---------------------------------------------------------------------------
+//
+// ORDER_CELL       (cell, rank): plain cell order (2D / generic path)
+// ORDER_RANK_CELL  (rank, cell): consecutive particles of a tile sit in distinct cells
+// ORDER_RANK_BANK  (rank, round robin over the 8 shared-memory bank groups (x + 2y + 4z) mod 8,
+//                  cell): additionally the 8 lanes of a quarter warp hit 8 different 16-byte bank
+//                  groups of the 10x10x6 float4 node tile (index x + 10y + 100z)
+enum TileOrder : int { ORDER_CELL = 0, ORDER_RANK_CELL = 1, ORDER_RANK_BANK = 2 };
+
+template <int ORDER>
+__global__ void __launch_bounds__(128)
+k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* __restrict__ tile_base,
+            int* __restrict__ cell_off, int* __restrict__ perm, int4* __restrict__ tiles,
+            int* __restrict__ scal) {
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= g.n_tiles + 2) return;
+    const int base = tile_base[t];
+    const int n_t = tile_base[t + 1] - base;
+    if (n_t <= 0) return;
+    const int c_first = t * TILE_CELLS;
+    if (t >= g.n_tiles) {   // pseudo tiles: a single bucket, slots stay in rank order
+        if (lane == 0) {
+            cell_off[c_first] = base;
+            count[c_first] = 0;
+        }
+        for (int r = lane; r < n_t; r += 32) perm[base + r] = base + r;
+        return;
+    }
+    if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, 0);
+    // lane owns the x-row (y, z) = (lane & 7, lane >> 3) of the 8x8x4 tile: cells 8*lane .. 8*lane+7
+    int cnt[8];
+    {
+        int4* cp = reinterpret_cast<int4*>(count + c_first + lane * 8);
+        int4 a = cp[0], b = cp[1];
+        cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
+        cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
+        cp[0] = make_int4(0, 0, 0, 0);      // count[] is all zero again outside a sort
+        cp[1] = make_int4(0, 0, 0, 0);
+    }
+    int st[8];   // cell-sorted offsets (cellStart)
+    {
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine += cnt[j];
+        int ex = base + warp_inclusive_scan(mine) - mine;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            st[j] = ex;
+            ex += cnt[j];
+        }
+        int4* op = reinterpret_cast<int4*>(cell_off + c_first + lane * 8);
+        op[0] = make_int4(st[0], st[1], st[2], st[3]);
+        op[1] = make_int4(st[4], st[5], st[6], st[7]);
+    }
+    if (ORDER == ORDER_CELL) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            for (int r = 0; r < cnt[j]; ++r) perm[st[j] + r] = st[j] + r;
+        return;
+    }
+    int rank_base = base;
+    for (int r = 0;; ++r) {
+        if (ORDER == ORDER_RANK_CELL) {
+            int mine = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) mine += cnt[j] > r;
+            int inc = warp_inclusive_scan(mine);
+            int total = __shfl_sync(0xffffffffu, inc, 31);
+            if (total == 0) break;
+            int dst = rank_base + inc - mine;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (cnt[j] > r) perm[st[j] + r] = dst++;
+            rank_base += total;
+        } else {
+            // bank class of cell x in my row: (x + 2y + 4z) mod 8 with y = lane & 7, z = lane >> 3;
+            // every row holds each class exactly once.  Class lists are merged round robin:
+            // position of the k-th member of class b = sum_b' min(n_b', k) + #{b' < b : n_b' > k}.
+            const int rot = (2 * (lane & 7) + 4 * (lane >> 3)) & 7;
+            int nb[8], kb[8];
+            int total = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                const int x = (b - rot) & 7;          // my cell of class b
+                int have = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j == x) have = cnt[j] > r;
+                const unsigned m = __ballot_sync(0xffffffffu, have);
+                nb[b] = __popc(m);
+                kb[b] = have ? __popc(m & ((1u << lane) - 1u)) : -1;
+                total += nb[b];
+            }
+            if (total == 0) break;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) {
+                if (kb[b] < 0) continue;
+                const int k = kb[b];
+                int pos = 0;
+#pragma unroll
+                for (int b2 = 0; b2 < 8; ++b2) {
+                    pos += min(nb[b2], k);
+                    if (b2 < b && nb[b2] > k) ++pos;
+                }
+                const int x = (b - rot) & 7;
+                int slot = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (j == x) slot = st[j];
+                perm[slot + r] = rank_base + pos;
+            }
+            rank_base += total;
+        }
+    }
+}
 
 template <int DIM>
 __global__ void __launch_bounds__(256)
-k_reorder(Particles src, Particles dst, int n, const int* __restrict__ cell_idx,
-          const int* __restrict__ rank, const int* __restrict__ start) {
+k_reorder_perm(Particles src, Particles dst, int n, const int* __restrict__ gcell,
+               const int* __restrict__ rank, const int* __restrict__ cell_off,
+               const int* __restrict__ perm) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    int d = start[cell_idx[i]] + rank[i];
+    const int d = perm[cell_off[gcell[i]] + rank[i]];
     dst.P[d] = src.P[i];
     dst.V[d] = src.V[i];
     dst.CA[d] = src.CA[i];

@@ -183,7 +183,10 @@ def test_neighbour_sets_bit_exact(pkg, orc, scenes, dim):
             tile = ((z // 4) * tdy + y // 8) * tdx + x // 8
             assert (np.diff(tile) >= 0).all()
         else:
-            assert (np.diff(cidx) >= 0).all()        # 2D keeps the plain cell order
+            x, y = cidx % sz[0], cidx // sz[0]
+            tile = (y // 16) * (-(-sz[0] // 16)) + x // 16
+            local = (y % 16) * 16 + x % 16
+            assert (np.diff(tile * 256 + local) >= 0).all()   # 2D: plain tiled cell order
         sim.substeps(7)
         ref.substeps(7)
     sim.close()
