@@ -87,6 +87,7 @@ struct fluid_sim {
     int* gcell = nullptr;    // per particle: bucket (tile * 256 + cell in tile)
     int* rank = nullptr;     // per particle: rank inside its bucket
     int* perm = nullptr;     // cell-sorted slot -> slot in the tile order
+    int* src = nullptr;      // sorted slot -> storage index in buf[cur]
     int* imm_list = nullptr; // particles that changed tile in the last g2p
     int4* tiles = nullptr;   // active tile list {tile, first slot, count, 0}, rebuilt by every sort
     int* scal = nullptr;     // device scalars: [0] active tiles, [1] immigrants
@@ -173,7 +174,8 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     cudaFree(s->rank);
     cudaFree(s->perm);
     cudaFree(s->imm_list);
-    s->gcell = s->rank = s->perm = s->imm_list = nullptr;
+    cudaFree(s->src);
+    s->gcell = s->rank = s->perm = s->imm_list = s->src = nullptr;
     s->sorted_valid = s->counts_pending = false;
     s->buf[0] = nb[0];
     s->buf[1] = nb[1];
@@ -182,6 +184,7 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     CU_TRY(cudaMalloc(&s->rank, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->perm, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->imm_list, cap * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->src, cap * sizeof(int)));
     s->cap = cap;
     return FLUID_OK;
 }
@@ -279,13 +282,14 @@ __global__ void k_pack_active(const __grid_constant__ Geo g, Particles q, int n,
 
 // ids / cell / key / reference cell index of the sorted p_rect particles (parity taps).
 template <int DIM>
-__global__ void k_debug_keys(const __grid_constant__ Geo g, Particles q,
+__global__ void k_debug_keys(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
                              const int* __restrict__ n_deposit, int* __restrict__ ids,
                              int* __restrict__ cell, int* __restrict__ key,
                              int* __restrict__ ref_index) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;   // sorted slot
     if (i >= *n_deposit) return;
-    float4 p = q.P[i];
+    const int j = src[i];                            // storage index
+    float4 p = q.P[j];
     float pos[3] = {p.x, p.y, p.z};
     int k[3], rel[3] = {0, 0, 0};
     classify<DIM>(g, pos, k);
@@ -298,7 +302,7 @@ __global__ void k_debug_keys(const __grid_constant__ Geo g, Particles q,
         if (key) key[i * DIM + a] = (kf == k[a]) ? k[a] : kf;
         rel[a] = c - g.org[a];
     }
-    if (ids) ids[i] = __float_as_int(q.V[i].w);
+    if (ids) ids[i] = __float_as_int(q.V[j].w);
     if (ref_index) ref_index[i] = ref_cell_index<DIM>(g, rel);
 }
 
@@ -343,11 +347,8 @@ fluid_status sort_finish(fluid_sim* s) {
         k_tile_perm<ORDER_CELL><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
     s->launches += 4;
     if (n > 0) {
-        Particles& src = s->buf[s->cur];
-        Particles& dst = s->buf[s->cur ^ 1];
-        k_reorder_perm<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(src, dst, n, s->gcell, s->rank, s->cell_off, s->perm);
+        k_build_src<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->gcell, s->rank, s->cell_off, s->perm, s->src);
         ++s->launches;
-        s->cur ^= 1;
     }
     CU_TRY(cudaGetLastError());
     s->sorted_valid = true;
@@ -374,11 +375,8 @@ fluid_status sort_cold(fluid_sim* s) {
 // steady state: g2p already counted the particles that stayed in their tile
 template <int DIM>
 fluid_status sort_steady(fluid_sim* s) {
-    const int n = static_cast<int>(s->n);
     k_immigrants<<<s->sm_count * 4, 256, 0, s->stream>>>(sort_tables(s));
-    k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, s->buf[s->cur].P, s->tile_base + s->geo.n_tiles, n,
-                                                   sort_tables(s));
-    s->launches += 2;
+    ++s->launches;
     return sort_finish<DIM>(s);
 }
 
@@ -419,7 +417,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     ST_TRY(ensure_sorted<DIM>(s));
     Particles q = s->buf[s->cur];
     if (dbg && (dbg->ids || dbg->cell || dbg->key)) {
-        k_debug_keys<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, q, n_dep, dbg->ids, dbg->cell,
+        k_debug_keys<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, q, s->src, n_dep, dbg->ids, dbg->cell,
                                                                     dbg->key, nullptr);
         ++s->launches;
     }
@@ -432,25 +430,32 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
         const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);   // never more CTAs than tiles / 4
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
         const int* n_act = s->scal + SCAL_N_ACTIVE;
-        k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->tiles, n_act, s->gmass);
+        k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
+                                                                              s->gmass);
         if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         k_p2g_tiled<<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
-            s->geo, q, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
+            s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
             dbg ? dbg->pressure : nullptr);
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
         // g2p also counts the particles for the next substep's neighbour search
-        k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(s->geo, q, s->tiles, n_act, s->grid,
-                                                                                   d_mouse, sort_tables(s));
+        // and writes the new state at the sorted slots of the other buffer (no reorder pass)
+        Particles qn = s->buf[s->cur ^ 1];
+        k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
+            s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s));
+        // ignored / dropped particles sit behind the tiles: carried over and counted here
+        k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, q, qn, s->src, n_dep, n, sort_tables(s));
+        ++s->launches;
+        s->cur ^= 1;
         s->counts_pending = true;
     } else {
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-        k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid);
+        k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid);
         if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
-        k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid,
+        k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid,
                                                                       dbg ? dbg->density : nullptr,
                                                                       dbg ? dbg->pressure : nullptr);
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
-        k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, n_dep, s->grid, d_mouse);
+        k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid, d_mouse);
         s->sorted_valid = false;   // positions moved; the generic path re-sorts from scratch
     }
     if (timed) {
@@ -488,8 +493,20 @@ fluid_status refresh_counts(fluid_sim* s, int64_t counts[4]) {
     int h[4];
     CU_TRY(cudaMemcpyAsync(h, s->class_count, sizeof(h), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
+    if (h[3] > 0) {
+        // dropped particles are the last h[3] slots of the SORTED order; bring storage into that
+        // order once and cut them off
+        const int n = static_cast<int>(s->n);
+        Particles from = s->buf[s->cur], to = s->buf[s->cur ^ 1];
+        if (s->dim == 3) k_gather_range<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(from, to, s->src, 0, n);
+        else k_gather_range<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(from, to, s->src, 0, n);
+        ++s->launches;
+        CU_TRY(cudaGetLastError());
+        s->cur ^= 1;
+        s->sorted_valid = false;
+    }
     s->dropped_total += h[3];
-    s->n -= h[3];   // sorted order: cells | limbo | dropped
+    s->n -= h[3];
     counts[0] = h[0];
     counts[1] = h[1];
     counts[2] = h[2];
@@ -593,6 +610,7 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->rank);
     cudaFree(s->perm);
     cudaFree(s->imm_list);
+    cudaFree(s->src);
     cudaFree(s->gmass);
     cudaFree(s->tiles);
     cudaFree(s->scal);
@@ -978,9 +996,9 @@ fluid_status fluid_debug_neighbour_table(fluid_sim* s, int64_t capacity, int32_t
     }
     const int* n_dep = s->tile_base + s->geo.n_tiles;
     if (s->dim == 3)
-        k_debug_keys<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n_dep, d_ids, nullptr, nullptr, d_ref);
+        k_debug_keys<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], s->src, n_dep, d_ids, nullptr, nullptr, d_ref);
     else
-        k_debug_keys<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n_dep, d_ids, nullptr, nullptr, d_ref);
+        k_debug_keys<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], s->src, n_dep, d_ids, nullptr, nullptr, d_ref);
     ++s->launches;
     int h_dep = 0;
     fluid_status st = FLUID_OK;

@@ -38,10 +38,11 @@ __device__ __forceinline__ void load_C(const Particles& q, int i, float* C) {
 // p2g_1 (3d:148-183): node.mass += w*m ; node.mom += w*m*(v + C*(x_n - x_p))
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_p2g1_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ n_deposit,
-               float4* __restrict__ grid) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n_deposit) return;
+k_p2g1_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
+               const int* __restrict__ n_deposit, float4* __restrict__ grid) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= *n_deposit) return;
+    const int i = src[d];
     float4 p = q.P[i];
     float4 v = q.V[i];
     float pos[3] = {p.x, p.y, p.z};
@@ -78,11 +79,12 @@ k_p2g1_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict
 // p2g_2 (3d:185-247): density from node masses, Tait pressure, stress, force scatter.
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_p2g2_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ n_deposit,
-               float4* __restrict__ grid, float* __restrict__ dbg_density,
-               float* __restrict__ dbg_pressure) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n_deposit) return;
+k_p2g2_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
+               const int* __restrict__ n_deposit, float4* __restrict__ grid,
+               float* __restrict__ dbg_density, float* __restrict__ dbg_pressure) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= *n_deposit) return;
+    const int i = src[d];
     float4 p = q.P[i];
     float pos[3] = {p.x, p.y, p.z};
     float C[9];
@@ -107,8 +109,8 @@ k_p2g2_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict
             }
     float volume = __fdiv_rn(p.w, density);
     float pressure = tait_pressure(g, density);
-    if (dbg_density) dbg_density[i] = density;
-    if (dbg_pressure) dbg_pressure[i] = pressure;
+    if (dbg_density) dbg_density[d] = density;
+    if (dbg_pressure) dbg_pressure[d] = pressure;
 
     // T = -4 * V * (-p I + mu (C + C^T)) * dt   (3d:222-225)
     float T[9];
@@ -182,10 +184,12 @@ __device__ __forceinline__ bool left_p_rect(const Geo& g, const float* pos) {
 // update_grid + g2p (3d:249-381)
 template <int DIM>
 __global__ void __launch_bounds__(128)
-k_g2p_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ n_deposit,
-              const float4* __restrict__ grid, const float* __restrict__ mouse) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= *n_deposit) return;
+k_g2p_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
+              const int* __restrict__ n_deposit, const float4* __restrict__ grid,
+              const float* __restrict__ mouse) {
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= *n_deposit) return;
+    const int i = src[d];
     float4 p = q.P[i];
     float pos[3] = {p.x, p.y, p.z};
     if (classify_pos<DIM>(g, pos) != CLS_ACTIVE) return;   // g2p walks a_rect blocks only

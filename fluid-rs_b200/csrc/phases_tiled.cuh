@@ -127,8 +127,8 @@ __device__ __forceinline__ void column_passes(bool active, int column, int lane,
 
 __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
-             const int4* __restrict__ tiles, const int* __restrict__ n_active,
-             float* __restrict__ gmass) {
+             const int* __restrict__ src, const int4* __restrict__ tiles,
+             const int* __restrict__ n_active, float* __restrict__ gmass) {
     __shared__ float sm[T3::WARPS * T3::NODES];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = sm + warp * T3::NODES;
@@ -139,12 +139,15 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
         tile_from_list(g, __ldg(&tiles[a]), tc);
         for (int k = lane; k < T3::NODES; k += 32) tile[k] = 0.0f;
         __syncwarp();
+        // software pipeline: index two windows ahead, record one window ahead
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < tc.count) p_next = __ldg(&P[tc.base + lane]);
+        if (lane < tc.count) p_next = __ldg(&P[__ldg(&src[tc.base + lane])]);
+        int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
         for (int it = 0; it < tc.count; it += 32) {
             const bool active = it + lane < tc.count;
             const float4 p = p_next;
-            if (it + 32 + lane < tc.count) p_next = __ldg(&P[tc.base + it + 32 + lane]);   // prefetch
+            if (it + 32 + lane < tc.count) p_next = __ldg(&P[i_next]);
+            if (it + 64 + lane < tc.count) i_next = __ldg(&src[tc.base + it + 64 + lane]);
             TStencil s;
             tile_stencil(g, tc, p.x, p.y, p.z, s);
             const float wzm[3] = {s.wz[0] * p.w, s.wz[1] * p.w, s.wz[2] * p.w};
@@ -211,8 +214,9 @@ __device__ __forceinline__ void load_prec(const Particles& q, int i, bool ok, PR
 }
 
 __global__ void __launch_bounds__(T3::THREADS, 4)
-k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__ tiles,
-            const int* __restrict__ n_active, const float* __restrict__ gmass,
+k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
+            const int4* __restrict__ tiles, const int* __restrict__ n_active,
+            const float* __restrict__ gmass,
             float4* __restrict__ grid, float* __restrict__ dbg_density,
             float* __restrict__ dbg_pressure) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -227,7 +231,8 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
         PRec nxt;
-        load_prec(q, tc.base + lane, lane < tc.count, nxt);
+        load_prec(q, lane < tc.count ? __ldg(&src[tc.base + lane]) : 0, lane < tc.count, nxt);
+        int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
         {   // node masses of the footprint: all loads in flight before the first store
             float mv[FOOT_ITERS];
 #pragma unroll
@@ -248,9 +253,10 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
 
         for (int it = 0; it < tc.count; it += 32) {
             const bool active = it + lane < tc.count;
-            const int i = tc.base + it + lane;
+            const int d = tc.base + it + lane;   // sorted slot
             const PRec cur = nxt;
-            load_prec(q, i + 32, it + 32 + lane < tc.count, nxt);   // prefetch the next window
+            load_prec(q, i_next, it + 32 + lane < tc.count, nxt);   // prefetch the next window
+            if (it + 64 + lane < tc.count) i_next = __ldg(&src[d + 64]);
             TStencil s;
             tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
 
@@ -270,8 +276,8 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
             if (active) {
                 volume = __fdiv_rn(m, density);
                 pressure = tait_pressure(g, density);
-                if (dbg_density) dbg_density[i] = density;
-                if (dbg_pressure) dbg_pressure[i] = pressure;
+                if (dbg_density) dbg_density[d] = density;
+                if (dbg_pressure) dbg_pressure[d] = pressure;
             }
             // M = m C + T,  T = -4 V (-p I + mu (C + C^T)) dt   (3d:222-225), column-major
             const float C[9] = {cur.ca.x, cur.ca.y, cur.ca.z, cur.ca.w, cur.cb.x, cur.cb.y, cur.cb.z, cur.cb.w, cur.cc};
@@ -349,10 +355,10 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
 // gets its new bucket; the ones that stay in this tile are ranked with shared-memory integer
 // atomics (native ATOMS.ADD), the few that change tile or are dropped go to the immigrant list.
 template <bool COUNT>
-__global__ void __launch_bounds__(T3::THREADS)
-k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__ tiles,
-            const int* __restrict__ n_active, const float4* __restrict__ grid,
-            const float* __restrict__ mouse, SortTables st) {
+__global__ void __launch_bounds__(T3::THREADS, 4)
+k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int* __restrict__ src,
+            const int4* __restrict__ tiles, const int* __restrict__ n_active,
+            const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st) {
     __shared__ float4 sm[T3::WARPS * T3::NODES];
     __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -364,43 +370,55 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
+        // q = state before this substep (storage order, read through src);
+        // qn = state after it, written at the sorted slot
+        int i_cur = lane < tc.count ? __ldg(&src[tc.base + lane]) : 0;
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < tc.count) p_next = q.P[tc.base + lane];
+        if (lane < tc.count) p_next = __ldg(&q.P[i_cur]);
+        int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
         if (COUNT) {
 #pragma unroll
             for (int j = 0; j < TILE_CELLS / 32; ++j) scnt[lane + 32 * j] = 0;
         }
-        // node velocities of the footprint, in two batches of independent loads
+        // node records of the footprint: cp.async (LDGSTS) straight into shared memory, all 19 per
+        // lane in flight, zero-filled outside the p_rect grid; then update_grid in place
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            constexpr int HB = (FOOT_ITERS + 1) / 2;
-            float4 nv[HB];
-#pragma unroll
-            for (int j = 0; j < HB; ++j) {
-                const int k = lane + 32 * (half * HB + j);
-                int gi = (half * HB + j) < FOOT_ITERS ? footprint_to_global(g, tc, k) : -1;
-                nv[j] = gi >= 0 ? __ldg(&grid[gi]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < FOOT_ITERS; ++j) {
+            const int k = lane + 32 * j;
+            if (k < T3::NODES) {
+                const int gi = footprint_to_global(g, tc, k);
+                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + k));
+                const float4* gp = grid + (gi >= 0 ? gi : 0);
+                const int bytes = gi >= 0 ? 16 : 0;
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(bytes) : "memory");
             }
-#pragma unroll
-            for (int j = 0; j < HB; ++j) {
-                const int k = lane + 32 * (half * HB + j);
-                float4 nd = nv[j];
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll 4
+        for (int j = 0; j < FOOT_ITERS; ++j) {
+            const int k = lane + 32 * j;
+            if (k < T3::NODES) {
+                float4 nd = vt[k];
                 if (nd.w > 0.0f) {   // update_grid (3d:253-256); one IEEE reciprocal, three multiplies
                     const float inv = __frcp_rn(nd.w);
                     nd.x = nd.x * inv + g.dtg[0];
                     nd.y = nd.y * inv + g.dtg[1];
                     nd.z = nd.z * inv + g.dtg[2];
+                    vt[k] = nd;
                 }
-                if (k < T3::NODES) vt[k] = nd;
             }
         }
         __syncwarp();
 
         for (int it = 0; it < tc.count; it += 32) {
             const bool active = it + lane < tc.count;
-            const int i = tc.base + it + lane;
+            const int d = tc.base + it + lane;   // sorted slot = index in the new buffer
+            const int i = i_cur;                 // storage index in the old buffer
             const float4 p = p_next;
-            if (it + 32 + lane < tc.count) p_next = q.P[i + 32];   // prefetch the next window
+            i_cur = i_next;
+            if (it + 32 + lane < tc.count) p_next = __ldg(&q.P[i_next]);   // prefetch the next window
+            if (it + 64 + lane < tc.count) i_next = __ldg(&src[d + 64]);
             float pos[3] = {p.x, p.y, p.z};
             const bool advance = active && classify_pos<3>(g, pos) == CLS_ACTIVE;   // g2p walks a_rect blocks only
             if (advance) {
@@ -448,12 +466,18 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
                 }
                 integrate_particle<3>(g, pos, vel, mouse);
                 if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
-                const float idw = q.V[i].w;
-                q.P[i] = make_float4(pos[0], pos[1], pos[2], p.w);
-                q.V[i] = make_float4(vel[0], vel[1], vel[2], idw);
-                q.CA[i] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);
-                q.CB[i] = make_float4(4.0f * B[4], 4.0f * B[5], 4.0f * B[6], 4.0f * B[7]);
-                q.CC[i] = 4.0f * B[8];
+                const float idw = __ldg(&q.V[i].w);
+                qn.P[d] = make_float4(pos[0], pos[1], pos[2], p.w);
+                qn.V[d] = make_float4(vel[0], vel[1], vel[2], idw);
+                qn.CA[d] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);
+                qn.CB[d] = make_float4(4.0f * B[4], 4.0f * B[5], 4.0f * B[6], 4.0f * B[7]);
+                qn.CC[d] = 4.0f * B[8];
+            } else if (active) {   // frozen halo particle: carried over unchanged (3d:149 vs 3d:263)
+                qn.P[d] = p;
+                qn.V[d] = __ldg(&q.V[i]);
+                qn.CA[d] = __ldg(&q.CA[i]);
+                qn.CB[d] = __ldg(&q.CB[i]);
+                qn.CC[d] = __ldg(&q.CC[i]);
             }
             if (COUNT) {
                 // bucket of the (possibly moved) particle; frozen halo particles keep theirs
@@ -461,14 +485,14 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, const int4* __restrict__
                 if (active) bucket = bucket_of<3>(g, make_float4(pos[0], pos[1], pos[2], 0.f), cls);
                 const bool stays = active && (bucket >> 8) == tc.tile;
                 const bool leaves = active && !stays;
-                if (active) st.gcell[i] = bucket;
-                if (stays) st.rank[i] = atomicAdd(&scnt[bucket & (TILE_CELLS - 1)], 1);
+                if (active) st.gcell[d] = bucket;
+                if (stays) st.rank[d] = atomicAdd(&scnt[bucket & (TILE_CELLS - 1)], 1);
                 const unsigned lm = __ballot_sync(0xffffffffu, leaves);
                 if (lm) {
                     int slot = 0;
                     if (lane == 0) slot = atomicAdd(&st.scal[SCAL_N_IMM], __popc(lm));
                     slot = __shfl_sync(0xffffffffu, slot, 0);
-                    if (leaves) st.imm_list[slot + __popc(lm & ((1u << lane) - 1u))] = i;
+                    if (leaves) st.imm_list[slot + __popc(lm & ((1u << lane) - 1u))] = d;
                 }
             }
         }

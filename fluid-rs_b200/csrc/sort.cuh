@@ -118,20 +118,33 @@ k_immigrants(SortTables t) {
 }
 
 // Steady state: the tail of the array (ignored and dropped particles) is not covered by any tile.
+// It copies those records from the old buffer (through src) into their slots of the new one, as
+// g2p does for the tiles, and counts them.
 template <int DIM>
 __global__ void __launch_bounds__(256)
-k_tail(const __grid_constant__ Geo g, const float4* __restrict__ P, const int* __restrict__ n_deposit,
-       int n, SortTables t) {
+k_tail(const __grid_constant__ Geo g, Particles from, Particles to, const int* __restrict__ src,
+       const int* __restrict__ n_deposit, int n, SortTables t) {
     const int first = *n_deposit;
     const int len = n - first;
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (len + stride - 1) / stride;
     for (int r = 0; r < rounds; ++r) {
-        const int i = first + r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = i < n;
+        const int d = first + r * stride + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool valid = d < n;
         int cls = -1, bucket = 0;
-        if (valid) bucket = bucket_of<DIM>(g, P[i], cls);
-        count_global(t, i, bucket, valid);
+        if (valid) {
+            const int i = src[d];
+            const float4 p = from.P[i];
+            to.P[d] = p;
+            to.V[d] = from.V[i];
+            to.CA[d] = from.CA[i];
+            if (DIM == 3) {
+                to.CB[d] = from.CB[i];
+                to.CC[d] = from.CC[i];
+            }
+            bucket = bucket_of<DIM>(g, p, cls);
+        }
+        count_global(t, d, bucket, valid);
     }
 }
 
@@ -337,20 +350,31 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
     }
 }
 
-template <int DIM>
+// Sorted slot -> storage index.  The particle streams are never reordered by a separate pass:
+// the tile kernels gather through src[], and g2p writes the advanced particles straight into
+// their sorted slots of the other buffer, so storage order is always last substep's sorted
+// order and the gathers stay nearly coalesced.
 __global__ void __launch_bounds__(256)
-k_reorder_perm(Particles src, Particles dst, int n, const int* __restrict__ gcell,
-               const int* __restrict__ rank, const int* __restrict__ cell_off,
-               const int* __restrict__ perm) {
+k_build_src(int n, const int* __restrict__ gcell, const int* __restrict__ rank,
+            const int* __restrict__ cell_off, const int* __restrict__ perm, int* __restrict__ src) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const int d = perm[cell_off[gcell[i]] + rank[i]];
-    dst.P[d] = src.P[i];
-    dst.V[d] = src.V[i];
-    dst.CA[d] = src.CA[i];
+    src[perm[cell_off[gcell[i]] + rank[i]]] = i;
+}
+
+// Physical gather (only used to compact dropped particles away and for the steady-state tail).
+template <int DIM>
+__global__ void __launch_bounds__(256)
+k_gather_range(Particles from, Particles to, const int* __restrict__ src, int first, int n) {
+    int d = first + blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= n) return;
+    const int i = src[d];
+    to.P[d] = from.P[i];
+    to.V[d] = from.V[i];
+    to.CA[d] = from.CA[i];
     if (DIM == 3) {
-        dst.CB[d] = src.CB[i];
-        dst.CC[d] = src.CC[i];
+        to.CB[d] = from.CB[i];
+        to.CC[d] = from.CC[i];
     }
 }
 
