@@ -31,6 +31,8 @@ struct Geo {
     int res_shift;     // log2(grid_res) when it is a power of two, else -1
     float res_f;       // grid_res as f32 (3d:399)
     float dt, rest_density, mu, stiffness, power, mouse_r2, pclamp;
+    float inv_rest;    // 1 / rest_density
+    int power_is_4;    // eos_power == 4 exactly: (x*x)*(x*x) instead of powf
     float dtg[3];      // dt * gravity (3d:255)
     float clip_lo[3], clip_hi[3];
     float wall_lo[3], wall_hi[3];   // clip +- damp (3d:321-324)
@@ -55,9 +57,9 @@ __device__ __forceinline__ int block_key(float p, float res_f) {
 // Same key from the integer cell: for every f32 pos and integer grid_res,
 //   key_from_pos(pos) == floor_div(floor(pos) as i32, grid_res)
 // because the rounded quotient pos/res never crosses a block face (ulp(res*k)/res > ulp(k)/2);
-// tests/test_oracle.py::test_key_equals_floor_div_of_cell checks it one ulp either side of every
-// face, tests/test_gpu_parity.py::test_fast_key_matches_exact_key checks this function against
-// block_key() on the device.  Saturated cells (|pos| >= 2^31, inf, the drop tombstone) give keys
+// the CPU suite checks the identity one ulp either side of every face
+// (test_key_equals_floor_div_of_cell) and the GPU suite checks this function against block_key()
+// on the device (test_fast_key_matches_exact_key).  Saturated cells (|pos| >= 2^31, inf, the drop tombstone) give keys
 // near +-2^27, outside any rect set_rect accepts, exactly like the exact rule.  The hot kernels
 // use this (shift or integer division) instead of IEEE division + fmodf per axis.
 __device__ __forceinline__ int block_key_of_cell(const int cell, const int res_i, const int res_shift) {
@@ -106,6 +108,15 @@ __device__ __forceinline__ int classify_pos(const Geo& g, const float* pos) {
     return classify_cells<DIM>(g, cell);
 }
 
+// Cell index inside an 8x8x4 tile: column-major (z fastest), the 64 (x,y) columns enumerated so
+// that columns two apart in the enumeration fall into different 16-byte bank groups
+// (x + 2y) mod 8 of the shared-memory node tile (see k_tile_perm / phases_tiled.cuh).
+__device__ __forceinline__ int local_cell_3d(int lx, int ly, int lz) {
+    const int cls = (lx + 2 * ly) & 7;
+    const int e = 16 * (ly >> 1) + 2 * cls + (ly & 1);
+    return lz + 4 * e;
+}
+
 // Tiled cell index (sort key).  rel = cell - origin, clamped into the grid by the caller.
 template <int DIM>
 __device__ __forceinline__ int tiled_cell_index(const Geo& g, const int* rel) {
@@ -116,7 +127,7 @@ __device__ __forceinline__ int tiled_cell_index(const Geo& g, const int* rel) {
         return (ty * g.tdim[0] + tx) * T::CELLS + ly * T::X + lx;
     }
     int tz = rel[2] / T::Z, lz = rel[2] - tz * T::Z;
-    return ((tz * g.tdim[1] + ty) * g.tdim[0] + tx) * T::CELLS + (lz * T::Y + ly) * T::X + lx;
+    return ((tz * g.tdim[1] + ty) * g.tdim[0] + tx) * T::CELLS + local_cell_3d(lx, ly, lz);
 }
 
 // Reference linear node index x + y*sx + z*sx*sy (3d:169-172).
@@ -166,6 +177,21 @@ __device__ __forceinline__ void make_stencil(const Geo& g, const float* pos, Ste
 __device__ __forceinline__ float tait_pressure(const Geo& g, float density) {
     float eos = g.stiffness * (powf(__fdiv_rn(density, g.rest_density), g.power) - 1.0f);
     return fmaxf(g.pclamp, eos);
+}
+
+// Same, for the hot kernel: the reference's default exponent 4 (3d:27) is two multiplies, and
+// rho / rho0 becomes rho * (1 / rho0); both differ from powf / true division by at most a couple
+// of ulp, far inside the 1e-5 parity bound.  Any other exponent takes the powf path.
+__device__ __forceinline__ float tait_pressure_fast(const Geo& g, float density) {
+    const float x = density * g.inv_rest;
+    float xp;
+    if (g.power_is_4) {
+        const float x2 = x * x;
+        xp = x2 * x2;
+    } else {
+        xp = powf(x, g.power);
+    }
+    return fmaxf(g.pclamp, g.stiffness * (xp - 1.0f));
 }
 
 }  // namespace fluid

@@ -96,7 +96,7 @@ struct fluid_sim {
     int* tile_base = nullptr;    // exclusive scan of tile_total; [n_tiles] = number of p_rect particles
     bool sorted_valid = false;   // arrays are in tile order for the current positions
     bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
-    int tile_order = ORDER_RANK_CELL;
+    int tile_order = ORDER_COLUMN_RR;
     int sm_count = 148;
     unsigned grid_mass = 0, grid_p2g = 0, grid_g2p = 0;   // persistent grids: SMs x resident CTAs
 
@@ -338,11 +338,8 @@ fluid_status sort_finish(fluid_sim* s) {
     k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base);
     CU_TRY(cudaMemsetAsync(s->scal, 0, 2 * sizeof(int), s->stream));
     const unsigned pb = blocks_for(static_cast<int64_t>(m) * 32, 128);
-    const int order = DIM == 3 ? s->tile_order : ORDER_CELL;
-    if (order == ORDER_RANK_BANK)
-        k_tile_perm<ORDER_RANK_BANK><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
-    else if (order == ORDER_RANK_CELL)
-        k_tile_perm<ORDER_RANK_CELL><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
+    if (DIM == 3)
+        k_tile_perm<ORDER_COLUMN_RR><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
     else
         k_tile_perm<ORDER_CELL><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
     s->launches += 4;
@@ -581,9 +578,7 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     s->stream = s->own_stream;
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
-    const char* order = std::getenv("FLUID_B200_ORDER");   // 1 = (rank, cell), 2 = (rank, bank class, cell)
-    if (order && order[0] == '2') s->tile_order = ORDER_RANK_BANK;
-    if (order && order[0] == '1') s->tile_order = ORDER_RANK_CELL;
+
     cudaFuncSetAttribute(k_p2g_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
     {   // persistent grids: one wave of resident CTAs per kernel (148 SMs x occupancy)
         cudaDeviceProp prop{};
@@ -701,6 +696,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     g.power = s->cfg.eos_power;
     g.mouse_r2 = s->cfg.mouse_radius * s->cfg.mouse_radius;
     g.pclamp = s->cfg.pressure_clamp;
+    g.inv_rest = 1.0f / s->cfg.rest_density;
+    g.power_is_4 = s->cfg.eos_power == 4.0f ? 1 : 0;
     for (int a = 0; a < 3; ++a) {
         g.dtg[a] = s->cfg.dt * s->cfg.gravity[a];
         g.clip_lo[a] = s->cfg.clip_min[a];

@@ -1,14 +1,21 @@
 // phases_tiled.cuh — the 3D hot path: warp-private shared-memory node tiles, sm_100a.
 //
 // One warp owns one tile of 8x8x4 cells (Tile<3>) and the 10x10x6 nodes its particles can touch
-// (3^3 stencil reach, 3d:157-158).  Particles arrive sorted by (tile, rank-in-cell, cell), so the
-// 32 particles a warp handles in one iteration sit in 32 DISTINCT cells: at stencil offset o lane
-// l updates node cell_l + o, all different, and a plain LDS / FFMA / STS read-modify-write is
-// race free inside the warp — shared-memory float atomics are a CAS loop on sm_100a
-// (ATOMS.CAST.SPIN) and are not used.  A __match_any_sync over the cell ids splits an iteration
-// into passes if two lanes ever share a cell, so correctness never depends on the sort order.
+// (3^3 stencil reach, 3d:157-158).  The sort (sort.cuh, ORDER_COLUMN_RR) deals the tile's
+// particles into windows of <= 32 in which no two particles share an (x,y) column.  A warp
+// processes one window per iteration, one particle per lane: for a fixed stencil offset (ox,oy)
+// the 32 lanes touch 32 different node columns and the three nodes along z belong to the lane
+// alone, so the read-modify-writes into the shared-memory tile are plain LDS / FFMA / STS — three
+// independent chains in flight per lane, one __syncwarp per (ox,oy) — with no atomics (shared
+// float atomics are a CAS loop on sm_100a, ATOMS.CAST.SPIN) and no conflict passes.
 // Tiles are flushed to the dense grid with vector reductions (red.global.add.v4.f32,
-// SASS REDG.E.ADD.F32x4).
+// SASS REDG.E.ADD.F32x4).  Particle streams are gathered through src[] (sorted slot -> storage
+// index); g2p writes the advanced particles at their sorted slots of the other buffer, so no
+// separate reorder pass exists.
+//
+// Shared-memory node index: x + 10*y + 104*z.  The plane stride is padded from 100 to 104
+// (= 0 mod 8) so that the 16-byte bank group of a float4 node, (x + 2y) mod 8, depends on the
+// column only; the sort enumerates columns so that neighbouring lanes fall into different groups.
 //
 // Phase mapping to the reference (3d:110-134):
 //   k_mass_tiled  "p2g 1"  node mass   m_i  = sum_p w_ip m_p                      (3d:164,175)
@@ -17,7 +24,8 @@
 //                          (3d:163,176) plus the force term of p2g_2 (3d:242); the w lane of
 //                          the float4 node carries w_ip m_p again so g2p reads one record
 //   k_g2p_tiled   "update" + "g2p": v_i = mom/m + dt g while loading the tile (3d:253-256),
-//                          gather, C = 4B, advect, mouse, clamp, soft wall (3d:267-343)
+//                          gather, C = 4B, advect, mouse, clamp, soft wall (3d:267-343); it also
+//                          counts the particles for the next substep's neighbour search
 #pragma once
 
 #include "common.cuh"
@@ -29,25 +37,34 @@ namespace fluid {
 struct T3 {
     static constexpr int X = Tile<3>::X, Y = Tile<3>::Y, Z = Tile<3>::Z;
     static constexpr int NX = X + 2, NY = Y + 2, NZ = Z + 2;
-    static constexpr int NODES = NX * NY * NZ;       // 600
+    static constexpr int NODES = NX * NY * NZ;       // 600 footprint nodes
+    static constexpr int PLANE = 104;                // padded z stride in shared memory
+    static constexpr int SLOTS = PLANE * NZ;         // 624 shared-memory slots per tile
     static constexpr int WARPS = 4;                  // tiles per CTA (no CTA-level sync is used)
     static constexpr int THREADS = WARPS * 32;
 };
+constexpr int FOOT_ITERS = (T3::NODES + 31) / 32;    // 19 footprint nodes per lane
 
 struct TileCtx {
     int c0[3];     // first cell of the tile, relative to the grid origin
     int tile;      // tile id
     int base;      // first particle slot
     int count;     // particles in the tile
+    int windows;   // W
+    int per, extra;
+    bool edge;     // the footprint sticks out of the p_rect grid
 };
 
-// Active tiles (those holding particles), listed by k_tile_perm: {tile id, first slot, count, 0}.
-// The tile kernels run persistent warps that stride over this list, so empty tiles cost nothing.
+// Active tiles, listed by k_tile_perm: {tile id, first slot, count, windows}.  The tile kernels
+// run persistent warps that stride over this list, so empty tiles cost nothing.
 __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileCtx& tc) {
     const int t = e.x;
     tc.tile = t;
     tc.base = e.y;
     tc.count = e.z;
+    tc.windows = e.w;
+    tc.per = e.z / e.w;
+    tc.extra = e.z - tc.per * e.w;
     int tx = t % g.tdim[0];
     int r = t / g.tdim[0];
     int ty = r % g.tdim[1];
@@ -55,9 +72,21 @@ __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileC
     tc.c0[0] = tx * T3::X;
     tc.c0[1] = ty * T3::Y;
     tc.c0[2] = tz * T3::Z;
+    tc.edge = tc.c0[0] == 0 || tc.c0[1] == 0 || tc.c0[2] == 0 || tc.c0[0] + T3::X + 1 > g.size[0] ||
+              tc.c0[1] + T3::Y + 1 > g.size[1] || tc.c0[2] + T3::Z + 1 > g.size[2];
 }
 
-// Global node index of local footprint node k, or -1 outside the p_rect grid.
+// window w of the tile: first slot (relative to tc.base) and length
+__device__ __forceinline__ void window_range(const TileCtx& tc, int w, int& off, int& len) {
+    off = w * tc.per + min(w, tc.extra);
+    len = w < tc.windows ? tc.per + (w < tc.extra ? 1 : 0) : 0;
+}
+
+// Footprint node k (0..599): shared-memory slot and global node index (-1 outside the grid).
+__device__ __forceinline__ int footprint_slot(int k) {
+    const int lz = k / (T3::NX * T3::NY);
+    return k + lz * (T3::PLANE - T3::NX * T3::NY);
+}
 __device__ __forceinline__ int footprint_to_global(const Geo& g, const TileCtx& tc, int k) {
     int lx = k % T3::NX;
     int r = k / T3::NX;
@@ -69,14 +98,11 @@ __device__ __forceinline__ int footprint_to_global(const Geo& g, const TileCtx& 
     return g.guard + x + (y + z * g.size[1]) * g.size[0];
 }
 
-constexpr int FOOT_ITERS = (T3::NODES + 31) / 32;   // 19 footprint nodes per lane
-
 // Per-particle stencil in tile coordinates.
 struct TStencil {
     float wx[3], wy[3], wz[3];   // zeroed outside the p_rect grid (3d:166-168)
     float cx, cy, cz;            // pos - (cell + 0.5)
-    int node0;                   // footprint index of stencil offset (0,0,0)
-    int column;                  // (x, y) column inside the tile (conflict detection)
+    int node0;                   // shared-memory slot of stencil offset (0,0,0)
 };
 
 __device__ __forceinline__ void axis_weights(float c, float* w) {
@@ -96,31 +122,21 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
     axis_weights(s.cy, s.wy);
     axis_weights(s.cz, s.wz);
     int rx = rust_as_i32(fx) - g.org[0], ry = rust_as_i32(fy) - g.org[1], rz = rust_as_i32(fz) - g.org[2];
+    if (tc.edge) {   // warp-uniform: only tiles on the rim of the grid can reach outside it
 #pragma unroll
-    for (int o = 0; o < 3; ++o) {
-        int nx = rx - 1 + o, ny = ry - 1 + o, nz = rz - 1 + o;
-        if (nx < 0 || nx >= g.size[0]) s.wx[o] = 0.0f;
-        if (ny < 0 || ny >= g.size[1]) s.wy[o] = 0.0f;
-        if (nz < 0 || nz >= g.size[2]) s.wz[o] = 0.0f;
+        for (int o = 0; o < 3; ++o) {
+            int nx = rx - 1 + o, ny = ry - 1 + o, nz = rz - 1 + o;
+            if (nx < 0 || nx >= g.size[0]) s.wx[o] = 0.0f;
+            if (ny < 0 || ny >= g.size[1]) s.wy[o] = 0.0f;
+            if (nz < 0 || nz >= g.size[2]) s.wz[o] = 0.0f;
+        }
     }
     // the sort put this particle into this tile from the same floor(pos); the clamp only guards
     // shared memory against non-finite positions
     int lx = min(max(rx - tc.c0[0], 0), T3::X - 1);
     int ly = min(max(ry - tc.c0[1], 0), T3::Y - 1);
     int lz = min(max(rz - tc.c0[2], 0), T3::Z - 1);
-    s.node0 = lx + T3::NX * (ly + T3::NY * lz);
-    s.column = lx + T3::X * ly;
-}
-
-// Pass structure of one 32-particle window.  Lanes of one pass sit in DISTINCT (x,y) COLUMNS of
-// the tile: for a fixed (ox,oy) the three nodes oz = 0,1,2 of every lane are then private to that
-// lane, so the three read-modify-writes need no ordering among themselves (three independent
-// LDS/FFMA/STS chains in flight) and one __syncwarp per (ox,oy) suffices: 9 per pass, not 27.
-__device__ __forceinline__ void column_passes(bool active, int column, int lane, int& my_pass,
-                                              int& n_pass) {
-    unsigned peers = __match_any_sync(0xffffffffu, active ? column : (-1 - lane));
-    my_pass = __popc(peers & ((1u << lane) - 1u));
-    n_pass = __reduce_max_sync(0xffffffffu, my_pass) + 1;
+    s.node0 = lx + T3::NX * ly + T3::PLANE * lz;
 }
 
 // ---- p2g 1: node masses ---------------------------------------------------------------------
@@ -129,57 +145,56 @@ __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
              const int* __restrict__ n_active, float* __restrict__ gmass) {
-    __shared__ float sm[T3::WARPS * T3::NODES];
+    __shared__ float sm[T3::WARPS * T3::SLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = sm + warp * T3::NODES;
+    float* tile = sm + warp * T3::SLOTS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
-        for (int k = lane; k < T3::NODES; k += 32) tile[k] = 0.0f;
+        for (int k = lane; k < T3::SLOTS; k += 32) tile[k] = 0.0f;
         __syncwarp();
-        // software pipeline: index two windows ahead, record one window ahead
+        // software pipeline: record one window ahead, index two windows ahead
+        int off, len;
+        window_range(tc, 0, off, len);
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < tc.count) p_next = __ldg(&P[__ldg(&src[tc.base + lane])]);
-        int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
-        for (int it = 0; it < tc.count; it += 32) {
-            const bool active = it + lane < tc.count;
+        if (lane < len) p_next = __ldg(&P[__ldg(&src[tc.base + off + lane])]);
+        window_range(tc, 1, off, len);
+        int i_next = lane < len ? __ldg(&src[tc.base + off + lane]) : 0;
+        for (int w = 0; w < tc.windows; ++w) {
+            window_range(tc, w, off, len);
+            const bool active = lane < len;
             const float4 p = p_next;
-            if (it + 32 + lane < tc.count) p_next = __ldg(&P[i_next]);
-            if (it + 64 + lane < tc.count) i_next = __ldg(&src[tc.base + it + 64 + lane]);
+            window_range(tc, w + 1, off, len);
+            if (lane < len) p_next = __ldg(&P[i_next]);
+            window_range(tc, w + 2, off, len);
+            if (lane < len) i_next = __ldg(&src[tc.base + off + lane]);
             TStencil s;
             tile_stencil(g, tc, p.x, p.y, p.z, s);
             const float wzm[3] = {s.wz[0] * p.w, s.wz[1] * p.w, s.wz[2] * p.w};
-            int my_pass, n_pass;
-            column_passes(active, s.column, lane, my_pass, n_pass);
-            for (int pass = 0; pass < n_pass; ++pass) {
-                const bool go = active && my_pass == pass;
-                asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
 #pragma unroll
-                for (int oy = 0; oy < 3; ++oy)
+            for (int oy = 0; oy < 3; ++oy)
 #pragma unroll
-                    for (int ox = 0; ox < 3; ++ox) {
-                        const float wxy = s.wx[ox] * s.wy[oy];
-                        float* nd = tile + s.node0 + ox + T3::NX * oy;
-                        if (go) {
-                            float a0 = nd[0], a1 = nd[T3::NX * T3::NY], a2 = nd[2 * T3::NX * T3::NY];
-                            a0 += wxy * wzm[0];
-                            a1 += wxy * wzm[1];
-                            a2 += wxy * wzm[2];
-                            nd[0] = a0;
-                            nd[T3::NX * T3::NY] = a1;
-                            nd[2 * T3::NX * T3::NY] = a2;
-                        }
-                        __syncwarp();
+                for (int ox = 0; ox < 3; ++ox) {
+                    const float wxy = s.wx[ox] * s.wy[oy];
+                    float* nd = tile + s.node0 + ox + T3::NX * oy;
+                    if (active) {   // three nodes along z: private to this lane within the window
+                        float a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
+                        a0 += wxy * wzm[0];
+                        a1 += wxy * wzm[1];
+                        a2 += wxy * wzm[2];
+                        nd[0] = a0;
+                        nd[T3::PLANE] = a1;
+                        nd[2 * T3::PLANE] = a2;
                     }
-            }
+                    __syncwarp();
+                }
         }
-        __syncwarp();
 #pragma unroll 4
         for (int j = 0; j < FOOT_ITERS; ++j) {
             const int k = lane + 32 * j;
-            const float v = k < T3::NODES ? tile[k] : 0.0f;
+            const float v = k < T3::NODES ? tile[footprint_slot(k)] : 0.0f;
             if (v != 0.0f) {
                 int gi = footprint_to_global(g, tc, k);
                 if (gi >= 0) atomicAdd(&gmass[gi], v);
@@ -192,8 +207,8 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
 // ---- p2g 2: density, pressure, stress; fused momentum + force scatter ---------------------------
 
 struct P2GSmem {
-    float4 acc[T3::WARPS][T3::NODES];   // {momentum + force, mass} accumulators
-    float mass[T3::WARPS][T3::NODES];   // complete node masses (from k_mass_tiled)
+    float4 acc[T3::WARPS][T3::SLOTS];   // {momentum + force, mass} accumulators
+    float mass[T3::WARPS][T3::SLOTS];   // complete node masses (from k_mass_tiled)
 };
 
 struct PRec {   // one particle's streams
@@ -202,8 +217,6 @@ struct PRec {   // one particle's streams
 };
 
 __device__ __forceinline__ void load_prec(const Particles& q, int i, bool ok, PRec& r) {
-    r.p = r.v = r.ca = r.cb = make_float4(0.f, 0.f, 0.f, 0.f);
-    r.cc = 0.0f;
     if (ok) {
         r.p = __ldg(&q.P[i]);
         r.v = __ldg(&q.V[i]);
@@ -216,9 +229,8 @@ __device__ __forceinline__ void load_prec(const Particles& q, int i, bool ok, PR
 __global__ void __launch_bounds__(T3::THREADS, 4)
 k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
-            const float* __restrict__ gmass,
-            float4* __restrict__ grid, float* __restrict__ dbg_density,
-            float* __restrict__ dbg_pressure) {
+            const float* __restrict__ gmass, float4* __restrict__ grid,
+            float* __restrict__ dbg_density, float* __restrict__ dbg_pressure) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -226,13 +238,17 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
     float* ms = sm.mass[warp];
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
-    constexpr int PLANE = T3::NX * T3::NY;
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
+        int off, len;
+        window_range(tc, 0, off, len);
         PRec nxt;
-        load_prec(q, lane < tc.count ? __ldg(&src[tc.base + lane]) : 0, lane < tc.count, nxt);
-        int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
+        nxt.p = nxt.v = nxt.ca = nxt.cb = make_float4(0.f, 0.f, 0.f, 0.f);
+        nxt.cc = 0.0f;
+        load_prec(q, lane < len ? __ldg(&src[tc.base + off + lane]) : 0, lane < len, nxt);
+        window_range(tc, 1, off, len);
+        int i_next = lane < len ? __ldg(&src[tc.base + off + lane]) : 0;
         {   // node masses of the footprint: all loads in flight before the first store
             float mv[FOOT_ITERS];
 #pragma unroll
@@ -244,38 +260,43 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             for (int j = 0; j < FOOT_ITERS; ++j) {
                 const int k = lane + 32 * j;
                 if (k < T3::NODES) {
-                    ms[k] = mv[j];
-                    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    const int sl = footprint_slot(k);
+                    ms[sl] = mv[j];
+                    acc[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
         }
         __syncwarp();
 
-        for (int it = 0; it < tc.count; it += 32) {
-            const bool active = it + lane < tc.count;
-            const int d = tc.base + it + lane;   // sorted slot
+        for (int w = 0; w < tc.windows; ++w) {
+            window_range(tc, w, off, len);
+            const bool active = lane < len;
+            const int d = tc.base + off + lane;   // sorted slot
             const PRec cur = nxt;
-            load_prec(q, i_next, it + 32 + lane < tc.count, nxt);   // prefetch the next window
-            if (it + 64 + lane < tc.count) i_next = __ldg(&src[d + 64]);
+            window_range(tc, w + 1, off, len);
+            load_prec(q, i_next, lane < len, nxt);            // prefetch the next window
+            window_range(tc, w + 2, off, len);
+            if (lane < len) i_next = __ldg(&src[tc.base + off + lane]);
             TStencil s;
             tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
 
-            // density = sum_i m_i w_ip (3d:198-215)
+            // density = sum_i m_i w_ip (3d:198-215), summed x -> y -> z
             float density = 0.0f;
 #pragma unroll
-            for (int oz = 0; oz < 3; ++oz)
+            for (int oz = 0; oz < 3; ++oz) {
+                float plane = 0.0f;
 #pragma unroll
                 for (int oy = 0; oy < 3; ++oy) {
-                    const float wyz = s.wy[oy] * s.wz[oz];
-#pragma unroll
-                    for (int ox = 0; ox < 3; ++ox)
-                        density += ms[s.node0 + ox + T3::NX * oy + PLANE * oz] * (s.wx[ox] * wyz);
+                    const float* row = ms + s.node0 + T3::NX * oy + T3::PLANE * oz;
+                    plane += (row[0] * s.wx[0] + row[1] * s.wx[1] + row[2] * s.wx[2]) * s.wy[oy];
                 }
+                density += plane * s.wz[oz];
+            }
             const float m = cur.p.w;
             float volume = 0.0f, pressure = 0.0f;
             if (active) {
-                volume = __fdiv_rn(m, density);
-                pressure = tait_pressure(g, density);
+                volume = m * __frcp_rn(density);
+                pressure = tait_pressure_fast(g, density);
                 if (dbg_density) dbg_density[d] = density;
                 if (dbg_pressure) dbg_pressure[d] = pressure;
             }
@@ -297,49 +318,39 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             b[0] = m * cur.v.x + M[0] * dx0 + M[3] * dy0 + M[6] * dz0;
             b[1] = m * cur.v.y + M[1] * dx0 + M[4] * dy0 + M[7] * dz0;
             b[2] = m * cur.v.z + M[2] * dx0 + M[5] * dy0 + M[8] * dz0;
-            const float wzm[3] = {s.wz[0] * m, s.wz[1] * m, s.wz[2] * m};
-
-            int my_pass, n_pass;
-            column_passes(active, s.column, lane, my_pass, n_pass);
-            for (int pass = 0; pass < n_pass; ++pass) {
-                const bool go = active && my_pass == pass;
-                // n_pass is 1 unless two lanes share a column: keep the per-node values out of
-                // registers across passes (the compiler would hoist them as loop invariants)
-                asm volatile("" : "+f"(b[0]), "+f"(b[1]), "+f"(b[2]));
-                asm volatile("" : "+f"(s.wx[0]), "+f"(s.wx[1]), "+f"(s.wx[2]));
+            // per-z factors: node k gets wz_k * A + (k * wz_k) * G with A = wxy*c, G = wxy*M2
+            const float q1 = s.wz[1], q2 = 2.0f * s.wz[2];
 #pragma unroll
-                for (int oy = 0; oy < 3; ++oy) {
-                    const float r0 = b[0] + oy * M[3], r1 = b[1] + oy * M[4], r2 = b[2] + oy * M[5];
+            for (int oy = 0; oy < 3; ++oy) {
+                const float r0 = b[0] + oy * M[3], r1 = b[1] + oy * M[4], r2 = b[2] + oy * M[5];
 #pragma unroll
-                    for (int ox = 0; ox < 3; ++ox) {
-                        const float wxy = s.wx[ox] * s.wy[oy];
-                        const float c0 = r0 + ox * M[0], c1 = r1 + ox * M[1], c2 = r2 + ox * M[2];
-                        float4* nd = acc + s.node0 + ox + T3::NX * oy;
-                        if (go) {
-                            // three nodes along z: private to this lane within the pass
-                            float4 a0 = nd[0], a1 = nd[PLANE], a2 = nd[2 * PLANE];
-                            const float w0 = wxy * s.wz[0], w1 = wxy * s.wz[1], w2 = wxy * s.wz[2];
-                            a0.x += w0 * c0;              a0.y += w0 * c1;              a0.z += w0 * c2;
-                            a1.x += w1 * (c0 + M[6]);     a1.y += w1 * (c1 + M[7]);     a1.z += w1 * (c2 + M[8]);
-                            a2.x += w2 * (c0 + 2.f * M[6]); a2.y += w2 * (c1 + 2.f * M[7]); a2.z += w2 * (c2 + 2.f * M[8]);
-                            a0.w += wxy * wzm[0];
-                            a1.w += wxy * wzm[1];
-                            a2.w += wxy * wzm[2];
-                            nd[0] = a0;
-                            nd[PLANE] = a1;
-                            nd[2 * PLANE] = a2;
-                        }
-                        __syncwarp();
+                for (int ox = 0; ox < 3; ++ox) {
+                    const float wxy = s.wx[ox] * s.wy[oy];
+                    const float A0 = wxy * (r0 + ox * M[0]), A1 = wxy * (r1 + ox * M[1]), A2 = wxy * (r2 + ox * M[2]);
+                    const float G0 = wxy * M[6], G1 = wxy * M[7], G2 = wxy * M[8];
+                    const float mw = wxy * m;
+                    float4* nd = acc + s.node0 + ox + T3::NX * oy;
+                    if (active) {
+                        // three nodes along z: private to this lane within the window
+                        float4 a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
+                        a0.x += s.wz[0] * A0;  a0.y += s.wz[0] * A1;  a0.z += s.wz[0] * A2;  a0.w += s.wz[0] * mw;
+                        a1.x += s.wz[1] * A0 + q1 * G0;  a1.y += s.wz[1] * A1 + q1 * G1;
+                        a1.z += s.wz[1] * A2 + q1 * G2;  a1.w += s.wz[1] * mw;
+                        a2.x += s.wz[2] * A0 + q2 * G0;  a2.y += s.wz[2] * A1 + q2 * G1;
+                        a2.z += s.wz[2] * A2 + q2 * G2;  a2.w += s.wz[2] * mw;
+                        nd[0] = a0;
+                        nd[T3::PLANE] = a1;
+                        nd[2 * T3::PLANE] = a2;
                     }
+                    __syncwarp();
                 }
             }
         }
-        __syncwarp();
 #pragma unroll 4
         for (int j = 0; j < FOOT_ITERS; ++j) {
             const int k = lane + 32 * j;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < T3::NODES) v = acc[k];
+            if (k < T3::NODES) v = acc[footprint_slot(k)];
             if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
                 int gi = footprint_to_global(g, tc, k);
                 if (gi >= 0) atomicAdd(&grid[gi], v);
@@ -359,19 +370,19 @@ __global__ void __launch_bounds__(T3::THREADS, 4)
 k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st) {
-    __shared__ float4 sm[T3::WARPS * T3::NODES];
+    __shared__ float4 sm[T3::WARPS * T3::SLOTS];
     __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float4* vt = sm + warp * T3::NODES;
+    float4* vt = sm + warp * T3::SLOTS;
     int* scnt = scnt_all + warp * TILE_CELLS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
-    constexpr int PLANE = T3::NX * T3::NY;
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
         // q = state before this substep (storage order, read through src);
-        // qn = state after it, written at the sorted slot
+        // qn = state after it, written at the sorted slot.  g2p has no write conflicts, so it walks
+        // the tile's slots 32 at a time regardless of the window structure.
         int i_cur = lane < tc.count ? __ldg(&src[tc.base + lane]) : 0;
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < tc.count) p_next = __ldg(&q.P[i_cur]);
@@ -387,7 +398,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             const int k = lane + 32 * j;
             if (k < T3::NODES) {
                 const int gi = footprint_to_global(g, tc, k);
-                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + k));
+                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + footprint_slot(k)));
                 const float4* gp = grid + (gi >= 0 ? gi : 0);
                 const int bytes = gi >= 0 ? 16 : 0;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(bytes) : "memory");
@@ -399,13 +410,14 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         for (int j = 0; j < FOOT_ITERS; ++j) {
             const int k = lane + 32 * j;
             if (k < T3::NODES) {
-                float4 nd = vt[k];
+                const int sl = footprint_slot(k);
+                float4 nd = vt[sl];
                 if (nd.w > 0.0f) {   // update_grid (3d:253-256); one IEEE reciprocal, three multiplies
                     const float inv = __frcp_rn(nd.w);
                     nd.x = nd.x * inv + g.dtg[0];
                     nd.y = nd.y * inv + g.dtg[1];
                     nd.z = nd.z * inv + g.dtg[2];
-                    vt[k] = nd;
+                    vt[sl] = nd;
                 }
             }
         }
@@ -431,7 +443,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
                     float Pz[3] = {0.f, 0.f, 0.f}, Pdx[3] = {0.f, 0.f, 0.f}, Pdy[3] = {0.f, 0.f, 0.f};
 #pragma unroll
                     for (int oy = 0; oy < 3; ++oy) {
-                        const float4* row = vt + s.node0 + T3::NX * oy + PLANE * oz;
+                        const float4* row = vt + s.node0 + T3::NX * oy + T3::PLANE * oz;
                         const float4 n0 = row[0], n1 = row[1], n2 = row[2];
                         float a0[3] = {n0.x * s.wx[0], n0.y * s.wx[0], n0.z * s.wx[0]};
                         float a2[3] = {n2.x * s.wx[2], n2.y * s.wx[2], n2.z * s.wx[2]};

@@ -235,12 +235,23 @@ k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, in
 
 // ---- per-tile order ---------------------------------------------------------------------------
 //
-// ORDER_CELL       (cell, rank): plain cell order (2D / generic path)
-// ORDER_RANK_CELL  (rank, cell): consecutive particles of a tile sit in distinct cells
-// ORDER_RANK_BANK  (rank, round robin over the 8 shared-memory bank groups (x + 2y + 4z) mod 8,
-//                  cell): additionally the 8 lanes of a quarter warp hit 8 different 16-byte bank
-//                  groups of the 10x10x6 float4 node tile (index x + 10y + 100z)
-enum TileOrder : int { ORDER_CELL = 0, ORDER_RANK_CELL = 1, ORDER_RANK_BANK = 2 };
+// ORDER_CELL       (cell, rank): plain cell order (2D / generic path).
+// ORDER_COLUMN_RR  3D tiled path.  The tile's particles are laid out column-major (cells of one
+//                  (x,y) column are consecutive: local_cell_3d) into a sequence q = 0..N-1 and dealt
+//                  round robin into W = max(ceil(N/32), max particles in one column) windows:
+//                  window = q mod W, lane = q div W.  Two particles of one column are less than W
+//                  apart in q, so a window never holds two particles of the same column: for a fixed
+//                  stencil offset the 32 lanes of a window update 32 different nodes (and the three
+//                  nodes along z of every lane are private to it) — the shared-memory
+//                  read-modify-writes of phases_tiled.cuh need no atomics and no conflict passes.
+//                  The tile list carries W: {tile, first slot, N, W}; window w holds the slots
+//                  [w*(N/W) + min(w, N%W), +N/W + (w < N%W)).
+enum TileOrder : int { ORDER_CELL = 0, ORDER_COLUMN_RR = 1 };
+
+__device__ __forceinline__ int window_offset(int n, int w_count, int w) {
+    const int q = n / w_count, r = n - q * w_count;
+    return w * q + min(w, r);
+}
 
 template <int ORDER>
 __global__ void __launch_bounds__(128)
@@ -262,8 +273,7 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         for (int r = lane; r < n_t; r += 32) perm[base + r] = base + r;
         return;
     }
-    if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, 0);
-    // lane owns the x-row (y, z) = (lane & 7, lane >> 3) of the 8x8x4 tile: cells 8*lane .. 8*lane+7
+    // lane owns 8 consecutive cells (3D: two (x,y) columns of 4 cells)
     int cnt[8];
     {
         int4* cp = reinterpret_cast<int4*>(count + c_first + lane * 8);
@@ -273,80 +283,35 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         cp[0] = make_int4(0, 0, 0, 0);      // count[] is all zero again outside a sort
         cp[1] = make_int4(0, 0, 0, 0);
     }
-    int st[8];   // cell-sorted offsets (cellStart)
-    {
-        int mine = 0;
+    int st[8];   // cell-sorted offsets (cellStart), relative to the tile
+    int mine = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) mine += cnt[j];
-        int ex = base + warp_inclusive_scan(mine) - mine;
+    for (int j = 0; j < 8; ++j) mine += cnt[j];
+    {
+        int ex = warp_inclusive_scan(mine) - mine;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             st[j] = ex;
             ex += cnt[j];
         }
         int4* op = reinterpret_cast<int4*>(cell_off + c_first + lane * 8);
-        op[0] = make_int4(st[0], st[1], st[2], st[3]);
-        op[1] = make_int4(st[4], st[5], st[6], st[7]);
+        op[0] = make_int4(base + st[0], base + st[1], base + st[2], base + st[3]);
+        op[1] = make_int4(base + st[4], base + st[5], base + st[6], base + st[7]);
     }
     if (ORDER == ORDER_CELL) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            for (int r = 0; r < cnt[j]; ++r) perm[st[j] + r] = st[j] + r;
+        if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, (n_t + 31) / 32);
+        for (int r = 0; r < mine; ++r) perm[base + st[0] + r] = base + st[0] + r;
         return;
     }
-    int rank_base = base;
-    for (int r = 0;; ++r) {
-        if (ORDER == ORDER_RANK_CELL) {
-            int mine = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) mine += cnt[j] > r;
-            int inc = warp_inclusive_scan(mine);
-            int total = __shfl_sync(0xffffffffu, inc, 31);
-            if (total == 0) break;
-            int dst = rank_base + inc - mine;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-                if (cnt[j] > r) perm[st[j] + r] = dst++;
-            rank_base += total;
-        } else {
-            // bank class of cell x in my row: (x + 2y + 4z) mod 8 with y = lane & 7, z = lane >> 3;
-            // every row holds each class exactly once.  Class lists are merged round robin:
-            // position of the k-th member of class b = sum_b' min(n_b', k) + #{b' < b : n_b' > k}.
-            const int rot = (2 * (lane & 7) + 4 * (lane >> 3)) & 7;
-            int nb[8], kb[8];
-            int total = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                const int x = (b - rot) & 7;          // my cell of class b
-                int have = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j == x) have = cnt[j] > r;
-                const unsigned m = __ballot_sync(0xffffffffu, have);
-                nb[b] = __popc(m);
-                kb[b] = have ? __popc(m & ((1u << lane) - 1u)) : -1;
-                total += nb[b];
-            }
-            if (total == 0) break;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) {
-                if (kb[b] < 0) continue;
-                const int k = kb[b];
-                int pos = 0;
-#pragma unroll
-                for (int b2 = 0; b2 < 8; ++b2) {
-                    pos += min(nb[b2], k);
-                    if (b2 < b && nb[b2] > k) ++pos;
-                }
-                const int x = (b - rot) & 7;
-                int slot = 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j)
-                    if (j == x) slot = st[j];
-                perm[slot + r] = rank_base + pos;
-            }
-            rank_base += total;
-        }
+    const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
+    const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
+    if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, w_count);
+    const int per = n_t / w_count, extra = n_t - per * w_count;
+    for (int r = 0; r < mine; ++r) {
+        const int q = st[0] + r;              // position in the column-major sequence
+        const int lane_pos = q / w_count;
+        const int w = q - lane_pos * w_count;
+        perm[base + q] = base + w * per + min(w, extra) + lane_pos;
     }
 }
 

@@ -401,3 +401,35 @@ def test_tiled_and_generic_paths_agree(pkg, scenes, monkeypatch):
         out.append(r)
         sim.close()
     assert np.abs(out[0] - out[1]).max() < 1e-4
+
+
+def test_fast_key_matches_exact_key(pkg, orc, scenes):
+    """The hot kernels classify particles from the integer cell (shift / integer floor division)
+    instead of f32 div_euclid.  Put particles one ulp either side of every block face, including the
+    a_rect / p_rect boundaries, and check keys (debug tap: exact rule, cross-checked on the device
+    against the integer rule) and the class counts the sort produces against the oracle."""
+    for res in (16, 10):
+        sc = scenes.default_3d()
+        cfg = dict(sc.cfg)
+        cfg["grid_res"] = res
+        cfg["clip_min"] = [-300.0] * 3
+        cfg["clip_max"] = [300.0] * 3
+        faces = np.arange(-3, 9, dtype=np.float32) * np.float32(res)
+        xs = np.concatenate([faces, np.nextafter(faces, np.float32(-1e9)), np.nextafter(faces, np.float32(1e9))])
+        rng = np.random.default_rng(4)
+        rec = np.zeros((xs.size * 3, 16), dtype=np.float32)
+        rec[:, :3] = rng.uniform(1.0, 60.0, (xs.size * 3, 3)).astype(np.float32)
+        for a in range(3):
+            rec[a * xs.size:(a + 1) * xs.size, a] = xs
+        rec[:, -1] = 1.0
+        sim, ref = build_pair(pkg, orc, cfg, rec, [0, 0, 0], [64, 64, 64])
+        c = sim.particle_counts()
+        assert c["active"] == ref.count(0) and c["active"] + c["frozen"] == ref.count(1)
+        t = sim.debug_substep()
+        r = ref.read(which=1, debug=True)
+        go, ro = np.argsort(t["ids"]), np.argsort(r["ids"])
+        assert np.array_equal(t["ids"][go], r["ids"][ro])
+        np.testing.assert_array_equal(t["key"][go], r["key"][ro])
+        np.testing.assert_array_equal(t["cell"][go], r["cell"][ro])
+        sim.close()
+        ref.close()
