@@ -108,13 +108,13 @@ __device__ __forceinline__ int classify_pos(const Geo& g, const float* pos) {
     return classify_cells<DIM>(g, cell);
 }
 
-// Cell index inside an 8x8x4 tile: column-major (z fastest), the 64 (x,y) columns enumerated so
-// that columns two apart in the enumeration fall into different 16-byte bank groups
-// (x + 2y) mod 8 of the shared-memory node tile (see k_tile_perm / phases_tiled.cuh).
+// Cell index inside an 8x8x4 tile: class-major.  The bank class of a cell is the 16-byte bank
+// group (x + 2y) mod 8 of its node column in the shared-memory tile (index x + 10y + 104z); cells
+// are numbered class, then y (which fixes the column inside the class), then z: 32 cells per class,
+// 4 per column.  k_tile_perm builds windows that hold each class evenly (sort.cuh).
 __device__ __forceinline__ int local_cell_3d(int lx, int ly, int lz) {
     const int cls = (lx + 2 * ly) & 7;
-    const int e = 16 * (ly >> 1) + 2 * cls + (ly & 1);
-    return lz + 4 * e;
+    return lz + 4 * (ly + 8 * cls);
 }
 
 // Tiled cell index (sort key).  rel = cell - origin, clamped into the grid by the caller.

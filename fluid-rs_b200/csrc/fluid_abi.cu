@@ -96,7 +96,7 @@ struct fluid_sim {
     int* tile_base = nullptr;    // exclusive scan of tile_total; [n_tiles] = number of p_rect particles
     bool sorted_valid = false;   // arrays are in tile order for the current positions
     bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
-    int tile_order = ORDER_COLUMN_RR;
+    int tile_order = ORDER_CLASS_RR;
     int sm_count = 148;
     unsigned grid_mass = 0, grid_p2g = 0, grid_g2p = 0;   // persistent grids: SMs x resident CTAs
 
@@ -337,11 +337,11 @@ fluid_status sort_finish(fluid_sim* s) {
     k_scan_sums<<<1, 1024, 0, s->stream>>>(s->block_sums, static_cast<int>(nb));
     k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base);
     CU_TRY(cudaMemsetAsync(s->scal, 0, 2 * sizeof(int), s->stream));
-    const unsigned pb = blocks_for(static_cast<int64_t>(m) * 32, 128);
+    const unsigned pb = blocks_for(static_cast<int64_t>(m) * 32, PERM_WARPS * 32);
     if (DIM == 3)
-        k_tile_perm<ORDER_COLUMN_RR><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
+        k_tile_perm<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
     else
-        k_tile_perm<ORDER_CELL><<<pb, 128, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
+        k_tile_perm<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
     s->launches += 4;
     if (n > 0) {
         k_build_src<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->gcell, s->rank, s->cell_off, s->perm, s->src);

@@ -1,7 +1,7 @@
 // phases_tiled.cuh — the 3D hot path: warp-private shared-memory node tiles, sm_100a.
 //
 // One warp owns one tile of 8x8x4 cells (Tile<3>) and the 10x10x6 nodes its particles can touch
-// (3^3 stencil reach, 3d:157-158).  The sort (sort.cuh, ORDER_COLUMN_RR) deals the tile's
+// (3^3 stencil reach, 3d:157-158).  The sort (sort.cuh, ORDER_CLASS_RR) deals the tile's
 // particles into windows of <= 32 in which no two particles share an (x,y) column.  A warp
 // processes one window per iteration, one particle per lane: for a fixed stencil offset (ox,oy)
 // the 32 lanes touch 32 different node columns and the three nodes along z belong to the lane

@@ -235,29 +235,32 @@ k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, in
 
 // ---- per-tile order ---------------------------------------------------------------------------
 //
-// ORDER_CELL       (cell, rank): plain cell order (2D / generic path).
-// ORDER_COLUMN_RR  3D tiled path.  The tile's particles are laid out column-major (cells of one
-//                  (x,y) column are consecutive: local_cell_3d) into a sequence q = 0..N-1 and dealt
-//                  round robin into W = max(ceil(N/32), max particles in one column) windows:
-//                  window = q mod W, lane = q div W.  Two particles of one column are less than W
-//                  apart in q, so a window never holds two particles of the same column: for a fixed
-//                  stencil offset the 32 lanes of a window update 32 different nodes (and the three
-//                  nodes along z of every lane are private to it) — the shared-memory
-//                  read-modify-writes of phases_tiled.cuh need no atomics and no conflict passes.
-//                  The tile list carries W: {tile, first slot, N, W}; window w holds the slots
-//                  [w*(N/W) + min(w, N%W), +N/W + (w < N%W)).
-enum TileOrder : int { ORDER_CELL = 0, ORDER_COLUMN_RR = 1 };
+// ORDER_CELL      (cell, rank): plain cell order (2D / generic path).
+// ORDER_CLASS_RR  3D tiled path.  Cells are numbered class-major (local_cell_3d: bank class, column,
+//                 z), so the cell-sorted sequence q = 0..N-1 of a tile lists class 0's columns first,
+//                 then class 1's, ...  It is dealt round robin into
+//                     W = max(ceil(N/32), max particles in one column)  windows:  window = q mod W.
+//                 * Two particles of one (x,y) column are less than W apart in q, so a window never
+//                   holds two particles of the same column: for a fixed stencil offset the 32 lanes of
+//                   a window update 32 different node columns (and the three nodes along z of a lane
+//                   are private to it) — the shared-memory read-modify-writes of phases_tiled.cuh
+//                   need no atomics and no conflict passes.
+//                 * Every window receives floor or ceil(N_b / W) particles of each bank class b; inside
+//                   the window they are merged round robin over the classes, so the 8 lanes of a
+//                   quarter warp hit 8 different 16-byte bank groups of the float4 node tile.
+//                 The tile list carries W: {tile, first slot, N, W}; window w holds the slots
+//                 [w*(N/W) + min(w, N%W), + N/W + (w < N%W)).
+enum TileOrder : int { ORDER_CELL = 0, ORDER_CLASS_RR = 1 };
 
-__device__ __forceinline__ int window_offset(int n, int w_count, int w) {
-    const int q = n / w_count, r = n - q * w_count;
-    return w * q + min(w, r);
-}
+constexpr int PERM_WARPS = 4;
+constexpr int PERM_MAX_W = 32;   // windows per tile covered by the in-window merge table
 
 template <int ORDER>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(PERM_WARPS * 32)
 k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* __restrict__ tile_base,
             int* __restrict__ cell_off, int* __restrict__ perm, int4* __restrict__ tiles,
             int* __restrict__ scal) {
+    __shared__ __align__(16) int tab_all[PERM_WARPS][PERM_MAX_W * 8];
     const int lane = threadIdx.x & 31;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (t >= g.n_tiles + 2) return;
@@ -273,7 +276,7 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         for (int r = lane; r < n_t; r += 32) perm[base + r] = base + r;
         return;
     }
-    // lane owns 8 consecutive cells (3D: two (x,y) columns of 4 cells)
+    // lane owns 8 consecutive cells (3D: two (x,y) columns of one bank class, 4 cells each)
     int cnt[8];
     {
         int4* cp = reinterpret_cast<int4*>(count + c_first + lane * 8);
@@ -283,35 +286,74 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         cp[0] = make_int4(0, 0, 0, 0);      // count[] is all zero again outside a sort
         cp[1] = make_int4(0, 0, 0, 0);
     }
-    int st[8];   // cell-sorted offsets (cellStart), relative to the tile
     int mine = 0;
 #pragma unroll
     for (int j = 0; j < 8; ++j) mine += cnt[j];
+    const int q_first = warp_inclusive_scan(mine) - mine;   // cell-sorted offset of my first cell
     {
-        int ex = warp_inclusive_scan(mine) - mine;
+        int ex = base + q_first;
+        int st[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             st[j] = ex;
             ex += cnt[j];
         }
-        int4* op = reinterpret_cast<int4*>(cell_off + c_first + lane * 8);
-        op[0] = make_int4(base + st[0], base + st[1], base + st[2], base + st[3]);
-        op[1] = make_int4(base + st[4], base + st[5], base + st[6], base + st[7]);
+        int4* op = reinterpret_cast<int4*>(cell_off + c_first + lane * 8);   // cellStart
+        op[0] = make_int4(st[0], st[1], st[2], st[3]);
+        op[1] = make_int4(st[4], st[5], st[6], st[7]);
     }
     if (ORDER == ORDER_CELL) {
         if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, (n_t + 31) / 32);
-        for (int r = 0; r < mine; ++r) perm[base + st[0] + r] = base + st[0] + r;
+        for (int r = 0; r < mine; ++r) perm[base + q_first + r] = base + q_first + r;
         return;
     }
     const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
     const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
     if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, w_count);
     const int per = n_t / w_count, extra = n_t - per * w_count;
+
+    // class totals N_b (lanes 4b..4b+3 hold class b) and class starts S_b
+    int n_cls = mine;
+    n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 1);
+    n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 2);
+    const int s_cls = __shfl_sync(0xffffffffu, q_first, lane & ~3);   // start of my class
+    int* tab = tab_all[(threadIdx.x >> 5)];
+    const bool merge = w_count <= PERM_MAX_W;
+    if (merge) {
+        // tab[w*8 + b] = members of class b in window w: those q in [S_b, S_b + N_b) with q = w (mod W)
+        const int b = lane & 7;
+        const int nb = __shfl_sync(0xffffffffu, n_cls, 4 * b);
+        const int sb = __shfl_sync(0xffffffffu, s_cls, 4 * b);
+        for (int w = lane >> 3; w < w_count; w += 4) {
+            int off = (w - sb) % w_count;
+            if (off < 0) off += w_count;
+            tab[w * 8 + b] = off < nb ? (nb - off + w_count - 1) / w_count : 0;
+        }
+    }
+    __syncwarp();
+    const int my_cls = lane >> 2;
+    int w = (q_first) % w_count;
     for (int r = 0; r < mine; ++r) {
-        const int q = st[0] + r;              // position in the column-major sequence
-        const int lane_pos = q / w_count;
-        const int w = q - lane_pos * w_count;
-        perm[base + q] = base + w * per + min(w, extra) + lane_pos;
+        const int q = q_first + r;              // position in the class-major sequence
+        int pos;
+        if (merge) {
+            int off = (w - s_cls) % w_count;
+            if (off < 0) off += w_count;
+            const int k = (q - (s_cls + off)) / w_count;   // my index among my class in window w
+            const int4 ta = *reinterpret_cast<const int4*>(tab + w * 8);
+            const int4 tb = *reinterpret_cast<const int4*>(tab + w * 8 + 4);
+            const int n[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
+            pos = 0;
+#pragma unroll
+            for (int b2 = 0; b2 < 8; ++b2) {
+                pos += min(n[b2], k);
+                if (b2 < my_cls && n[b2] > k) ++pos;
+            }
+        } else {
+            pos = q / w_count;
+        }
+        perm[base + q] = base + w * per + min(w, extra) + pos;
+        if (++w == w_count) w = 0;
     }
 }
 
