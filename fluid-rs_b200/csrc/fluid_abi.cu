@@ -94,6 +94,9 @@ struct fluid_sim {
     int* cell_off = nullptr; // per bucket: first cell-sorted slot (cellStart)
     int* tile_total = nullptr;
     int* tile_base = nullptr;    // exclusive scan of tile_total; [n_tiles] = number of p_rect particles
+    unsigned char* dirty[2] = {nullptr, nullptr};   // node blocks touched by the current / previous sort
+    int dirty_cur = 0;
+    bool grid_clean = false;     // every node outside the dirty blocks is zero
     bool sorted_valid = false;   // arrays are in tile order for the current positions
     bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
     int tile_order = ORDER_CLASS_RR;
@@ -338,10 +341,14 @@ fluid_status sort_finish(fluid_sim* s) {
     k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base);
     CU_TRY(cudaMemsetAsync(s->scal, 0, 2 * sizeof(int), s->stream));
     const unsigned pb = blocks_for(static_cast<int64_t>(m) * 32, PERM_WARPS * 32);
-    if (DIM == 3)
-        k_tile_perm<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
-    else
-        k_tile_perm<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal);
+    if (DIM == 3) {
+        s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
+        k_tile_perm<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal,
+                                                                          s->dirty[s->dirty_cur]);
+    } else {
+        k_tile_perm<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal,
+                                                                      nullptr);
+    }
     s->launches += 4;
     if (n > 0) {
         k_build_src<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->gcell, s->rank, s->cell_off, s->perm, s->src);
@@ -421,9 +428,18 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     if (timed) CU_TRY(cudaEventRecord(ev[1], s->stream));
     // clear_grid (3d:136-146)
     const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
-    CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
     if (DIM == 3 && s->tiled) {
-        CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
+        if (!s->grid_clean) {   // first substep after set_rect / a generic-path substep: wipe everything once
+            CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+            CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
+            CU_TRY(cudaMemsetAsync(s->dirty[s->dirty_cur ^ 1], 0, s->geo.n_tiles, s->stream));
+            s->grid_clean = true;
+        } else {
+            // only the node blocks the previous or the coming deposits can touch
+            k_clear_tiles<<<blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128), 128, 0, s->stream>>>(
+                s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
+            ++s->launches;
+        }
         const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);   // never more CTAs than tiles / 4
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
         const int* n_act = s->scal + SCAL_N_ACTIVE;
@@ -445,6 +461,8 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
         s->cur ^= 1;
         s->counts_pending = true;
     } else {
+        CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+        s->grid_clean = false;
         if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
         k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid);
         if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
@@ -614,6 +632,8 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->tile_total);
     cudaFree(s->tile_base);
     cudaFree(s->block_sums);
+    cudaFree(s->dirty[0]);
+    cudaFree(s->dirty[1]);
     cudaFree(s->class_count);
     cudaFree(s->grid);
     cudaFree(s->d_mouse);
@@ -715,6 +735,10 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     cudaFree(s->tile_total);
     cudaFree(s->tile_base);
     cudaFree(s->block_sums);
+    cudaFree(s->dirty[0]);
+    cudaFree(s->dirty[1]);
+    s->dirty[0] = s->dirty[1] = nullptr;
+    s->grid_clean = false;
     s->grid = nullptr;
     s->gmass = nullptr;
     s->tiles = nullptr;
@@ -727,6 +751,10 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
     if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
     CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + 2) * sizeof(int4)));
+    for (int b = 0; b < 2; ++b) {
+        CU_TRY(cudaMalloc(&s->dirty[b], g.n_tiles + 8));
+        CU_TRY(cudaMemsetAsync(s->dirty[b], 0, g.n_tiles + 8, s->stream));
+    }
     CU_TRY(cudaMalloc(&s->count, (m + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->cell_off, (m + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->tile_total, (n_pt + 8) * sizeof(int)));

@@ -139,6 +139,35 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
     s.node0 = lx + T3::NX * ly + T3::PLANE * lz;
 }
 
+// ---- clear: zero the 8x8x4 node blocks marked dirty by the sort (clear_grid, 3d:136-146) ----------
+// A block is dirty when a tile of its 3x3x3 neighbourhood holds particles now or held some in the
+// previous substep (flags of two consecutive sorts are kept: `dirty_prev | dirty_now`).
+__global__ void __launch_bounds__(128)
+k_clear_tiles(const __grid_constant__ Geo g, const unsigned char* __restrict__ dirty_now,
+              unsigned char* __restrict__ dirty_prev, float4* __restrict__ grid,
+              float* __restrict__ gmass) {
+    const int lane = threadIdx.x & 31;
+    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (t >= g.n_tiles) return;
+    const bool was = dirty_prev[t] != 0;
+    if (!was && dirty_now[t] == 0) return;
+    __syncwarp();
+    if (lane == 0) dirty_prev[t] = 0;   // dirty_prev becomes the next sort's dirty_now
+    const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
+    // 256 nodes: lane -> (x = lane & 7, y = (lane >> 3) + 4*j, z): 8 passes of 32 nodes
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int x = tx * T3::X + (lane & 7);
+        const int y = ty * T3::Y + (lane >> 3) + 4 * (j & 1);
+        const int z = tz * T3::Z + (j >> 1);
+        if (x < g.size[0] && y < g.size[1] && z < g.size[2]) {
+            const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
+            grid[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+            gmass[gi] = 0.0f;
+        }
+    }
+}
+
 // ---- p2g 1: node masses ---------------------------------------------------------------------
 
 __global__ void __launch_bounds__(T3::THREADS)

@@ -259,7 +259,7 @@ template <int ORDER>
 __global__ void __launch_bounds__(PERM_WARPS * 32)
 k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* __restrict__ tile_base,
             int* __restrict__ cell_off, int* __restrict__ perm, int4* __restrict__ tiles,
-            int* __restrict__ scal) {
+            int* __restrict__ scal, unsigned char* __restrict__ dirty) {
     __shared__ __align__(16) int tab_all[PERM_WARPS][PERM_MAX_W * 8];
     const int lane = threadIdx.x & 31;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -275,6 +275,14 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         }
         for (int r = lane; r < n_t; r += 32) perm[base + r] = base + r;
         return;
+    }
+    if (dirty && lane < 27) {
+        // the particles of this tile deposit into the node blocks of its 3x3x3 tile neighbourhood:
+        // mark them for k_clear_tiles (clear_grid, 3d:136-146, only where something was written)
+        const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
+        const int nx = tx + lane % 3 - 1, ny = ty + (lane / 3) % 3 - 1, nz = tz + lane / 9 - 1;
+        if (nx >= 0 && ny >= 0 && nz >= 0 && nx < g.tdim[0] && ny < g.tdim[1] && nz < g.tdim[2])
+            dirty[(nz * g.tdim[1] + ny) * g.tdim[0] + nx] = 1;
     }
     // lane owns 8 consecutive cells (3D: two (x,y) columns of one bank class, 4 cells each)
     int cnt[8];
