@@ -127,3 +127,14 @@ def test_splitmix_known_values(scenes):
     # splitmix64 reference outputs for state 0: first output 0xE220A8397B1DCDAF
     z = scenes.splitmix64(np.array([0], dtype=np.uint64))
     assert int(z[0]) == 0xE220A8397B1DCDAF
+
+
+def test_cpp_host_mirror_links_against_the_library(pkg, tmp_path):
+    """fluid-rs_b200/host/simulation.hpp (C++ mirror of `Simulation`) compiles and links against the
+    C ABI library: declarations in the header and exported symbols agree at link time."""
+    exe = tmp_path / "headless"
+    src = ROOT / "fluid-rs_b200" / "host" / "headless_main.cpp"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", "-I", str(ROOT / "include"), str(src), "-L",
+                        str(pkg.LIB_PATH.parent), "-lfluid_b200", f"-Wl,-rpath,{pkg.LIB_PATH.parent}",
+                        "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
