@@ -18,6 +18,7 @@ from pathlib import Path
 import numpy as np
 
 from . import scenes  # noqa: F401  (re-export)
+from . import slab  # noqa: F401  (z-slab multi-GPU driver)
 
 _HERE = Path(__file__).resolve().parent
 LIB_PATH = _HERE / "csrc" / "libfluid_b200.so"
@@ -92,11 +93,13 @@ SIGNATURES = {
     "fluid_debug_neighbour_table": (C.c_int, [C.c_void_p, C.c_int64, _ip, _ip, _i64p]),
     "fluid_read_grid": (C.c_int, [C.c_void_p, _fp, C.c_int64, _i64p]),
     "fluid_launch_count": (C.c_int, [C.c_void_p, _i64p]),
-    "fluid_slab_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
-    "fluid_slab_halo": (C.c_int, [C.c_void_p, C.c_int32, _vpp, _vpp, _i64p]),
+    "fluid_slab_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
+    "fluid_reserve": (C.c_int, [C.c_void_p, C.c_int64]),
+    "fluid_slab_planes": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, _vpp, _vpp, _i64p]),
     "fluid_slab_phase": (C.c_int, [C.c_void_p, C.c_int32, _fp]),
-    "fluid_slab_accumulate_halo": (C.c_int, [C.c_void_p, C.c_int32]),
-    "fluid_slab_migrants": (C.c_int, [C.c_void_p, C.c_int32, _vpp, _i64p]),
+    "fluid_slab_accumulate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
+    "fluid_slab_migrants": (C.c_int, [C.c_void_p, _vpp, _i64p, _vpp, _i64p]),
+    "fluid_slab_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
 }
 
 

@@ -26,7 +26,8 @@ struct Geo {
     int n_tiles;
     int n_cells_pad;   // n_tiles * 256: length of the tiled cell index space
     int guard;         // guard nodes before/after the grid array (zero-weight overreach)
-    int slab_lo, slab_hi;   // owned cell range along the last axis (world cells); open if unset
+    int slab_on;            // z-slab decomposition active
+    int slab_lo, slab_hi;   // owned cells [lo, hi) along z, relative to the grid origin
     int res_i;         // grid_res
     int res_shift;     // log2(grid_res) when it is a power of two, else -1
     float res_f;       // grid_res as f32 (3d:399)

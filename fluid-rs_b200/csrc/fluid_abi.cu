@@ -123,6 +123,14 @@ struct fluid_sim {
     cudaEvent_t ev[N_EVENTS]{};
     bool timers_recorded = false;
     cudaEvent_t* last_ev = nullptr;    // event set of the last timed substep
+    cudaEvent_t* cur_ev = nullptr;     // event set of the substep in progress (split substeps)
+    bool cur_timed = false;
+    // z-slab decomposition
+    float* mig_rec[2] = {nullptr, nullptr};   // packed records of the particles leaving through z_lo / z_hi
+    int mig_cap = 0;
+    bool has_nb[2] = {false, false};
+    float* halo_mass_recv[2] = {nullptr, nullptr};
+    float4* halo_node_recv[2] = {nullptr, nullptr};
     // profile mode: a pool of event sets, drained into sums when full or when read
     bool profiling = false;
     std::vector<cudaEvent_t> pool;     // PROFILE_POOL * N_EVENTS
@@ -133,7 +141,6 @@ struct fluid_sim {
     int64_t launches = 0;
     int32_t next_id = 0;
     int64_t dropped_total = 0;
-    int slab_lo = INT_MIN, slab_hi = INT_MAX;
 };
 
 namespace {
@@ -334,12 +341,12 @@ SortTables sort_tables(fluid_sim* s) {
 template <int DIM>
 fluid_status sort_finish(fluid_sim* s) {
     const int n = static_cast<int>(s->n);
-    const int m = s->geo.n_tiles + 2;
+    const int m = s->geo.n_tiles + N_PSEUDO;
     const unsigned nb = static_cast<unsigned>(s->n_scan_blocks);
     k_scan_partial<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums);
     k_scan_sums<<<1, 1024, 0, s->stream>>>(s->block_sums, static_cast<int>(nb));
     k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base);
-    CU_TRY(cudaMemsetAsync(s->scal, 0, 2 * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
     const unsigned pb = blocks_for(static_cast<int64_t>(m) * 32, PERM_WARPS * 32);
     if (DIM == 3) {
         s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
@@ -364,9 +371,9 @@ fluid_status sort_finish(fluid_sim* s) {
 template <int DIM>
 fluid_status sort_cold(fluid_sim* s) {
     const int n = static_cast<int>(s->n);
-    const int64_t buckets = static_cast<int64_t>(s->geo.n_tiles + 2) * TILE_CELLS;
+    const int64_t buckets = static_cast<int64_t>(s->geo.n_tiles + N_PSEUDO) * TILE_CELLS;
     CU_TRY(cudaMemsetAsync(s->count, 0, buckets * sizeof(int), s->stream));
-    CU_TRY(cudaMemsetAsync(s->tile_total, 0, (s->geo.n_tiles + 2) * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->tile_total, 0, (s->geo.n_tiles + N_PSEUDO) * sizeof(int), s->stream));
     CU_TRY(cudaMemsetAsync(s->class_count, 0, 4 * sizeof(int), s->stream));
     if (n > 0) {
         k_classify_all<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur].P, n, sort_tables(s),
@@ -405,80 +412,110 @@ fluid_status profile_drain(fluid_sim* s) {
     return FLUID_OK;
 }
 
+// One substep = clear -> p2g 1 -> p2g 2 -> update -> g2p (3d:111-133).  `phases` selects the parts
+// (slab runs exchange halo planes between them): 1 = sort + clear + p2g 1, 2 = p2g 2, 4 = update + g2p.
 template <int DIM>
-fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const DebugTaps* dbg) {
+fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const DebugTaps* dbg, int phases = 7) {
     if (!s->rect_set || s->n == 0) return FLUID_OK;   // no blocks to walk (3d:149 over an empty rect)
     const int n = static_cast<int>(s->n);
     const int* n_dep = s->tile_base + s->geo.n_tiles;
-    cudaEvent_t* ev = s->ev;
-    if (s->profiling) {
-        if (s->pool_used == PROFILE_POOL) ST_TRY(profile_drain(s));
-        ev = &s->pool[s->pool_used * N_EVENTS];
-        ++s->pool_used;
-        timed = true;
+    const bool tiled = DIM == 3 && s->tiled;
+    if (!tiled && phases != 7) return fail(FLUID_ERR_STATE, "split substeps need the tiled 3D path");
+    if (phases & 1) {
+        s->cur_ev = s->ev;
+        s->cur_timed = timed;
+        if (s->profiling) {
+            if (s->pool_used == PROFILE_POOL) ST_TRY(profile_drain(s));
+            s->cur_ev = &s->pool[s->pool_used * N_EVENTS];
+            ++s->pool_used;
+            s->cur_timed = true;
+        }
     }
-    if (timed) CU_TRY(cudaEventRecord(ev[0], s->stream));
-    ST_TRY(ensure_sorted<DIM>(s));
-    Particles q = s->buf[s->cur];
-    if (dbg && (dbg->ids || dbg->cell || dbg->key)) {
-        k_debug_keys<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, q, s->src, n_dep, dbg->ids, dbg->cell,
-                                                                    dbg->key, nullptr);
-        ++s->launches;
-    }
-    if (timed) CU_TRY(cudaEventRecord(ev[1], s->stream));
-    // clear_grid (3d:136-146)
+    cudaEvent_t* ev = s->cur_ev;
+    timed = s->cur_timed;
     const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
-    if (DIM == 3 && s->tiled) {
-        if (!s->grid_clean) {   // first substep after set_rect / a generic-path substep: wipe everything once
-            CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
-            CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
-            CU_TRY(cudaMemsetAsync(s->dirty[s->dirty_cur ^ 1], 0, s->geo.n_tiles, s->stream));
-            s->grid_clean = true;
-        } else {
-            // only the node blocks the previous or the coming deposits can touch
-            k_clear_tiles<<<blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128), 128, 0, s->stream>>>(
-                s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
+    const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);   // never more CTAs than tiles / 4
+    const int* n_act = s->scal + SCAL_N_ACTIVE;
+    if (phases & 1) {
+        if (timed) CU_TRY(cudaEventRecord(ev[0], s->stream));
+        ST_TRY(ensure_sorted<DIM>(s));
+        Particles q = s->buf[s->cur];
+        if (dbg && (dbg->ids || dbg->cell || dbg->key)) {
+            k_debug_keys<DIM><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, q, s->src, n_dep, dbg->ids, dbg->cell,
+                                                                        dbg->key, nullptr);
             ++s->launches;
         }
-        const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);   // never more CTAs than tiles / 4
-        if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-        const int* n_act = s->scal + SCAL_N_ACTIVE;
-        k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                              s->gmass);
-        if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
-        k_p2g_tiled<<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
-            s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
-            dbg ? dbg->pressure : nullptr);
-        if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
-        // g2p also counts the particles for the next substep's neighbour search
-        // and writes the new state at the sorted slots of the other buffer (no reorder pass)
-        Particles qn = s->buf[s->cur ^ 1];
-        k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-            s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s));
-        // ignored / dropped particles sit behind the tiles: carried over and counted here
-        k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, q, qn, s->src, n_dep, n, sort_tables(s));
+        if (timed) CU_TRY(cudaEventRecord(ev[1], s->stream));
+        // clear_grid (3d:136-146)
+        if (tiled) {
+            if (!s->grid_clean) {   // first substep after set_rect / a generic-path substep: wipe everything once
+                CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+                CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
+                CU_TRY(cudaMemsetAsync(s->dirty[s->dirty_cur ^ 1], 0, s->geo.n_tiles, s->stream));
+                s->grid_clean = true;
+            } else {
+                // only the node blocks the previous or the coming deposits can touch
+                k_clear_tiles<<<blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128), 128, 0, s->stream>>>(
+                    s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
+                ++s->launches;
+            }
+            if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
+            k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
+                                                                                  s->gmass);
+            ++s->launches;
+            if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
+        } else {
+            CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+            s->grid_clean = false;
+            if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
+            k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid);
+            ++s->launches;
+            if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
+        }
+    }
+    if (phases & 2) {
+        Particles q = s->buf[s->cur];
+        if (tiled)
+            k_p2g_tiled<<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
+                s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
+                dbg ? dbg->pressure : nullptr);
+        else
+            k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid,
+                                                                          dbg ? dbg->density : nullptr,
+                                                                          dbg ? dbg->pressure : nullptr);
         ++s->launches;
-        s->cur ^= 1;
-        s->counts_pending = true;
-    } else {
-        CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
-        s->grid_clean = false;
-        if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-        k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid);
-        if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
-        k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid,
-                                                                      dbg ? dbg->density : nullptr,
-                                                                      dbg ? dbg->pressure : nullptr);
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
-        k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid, d_mouse);
-        s->sorted_valid = false;   // positions moved; the generic path re-sorts from scratch
     }
-    if (timed) {
-        CU_TRY(cudaEventRecord(ev[5], s->stream));
-        s->last_ev = ev;
-        s->timers_recorded = true;
+    if (phases & 4) {
+        Particles q = s->buf[s->cur];
+        if (tiled) {
+            // g2p also counts the particles for the next substep's neighbour search and writes the new
+            // state at the sorted slots of the other buffer (no reorder pass)
+            Particles qn = s->buf[s->cur ^ 1];
+            SlabBufs sb{};
+            sb.rec[0] = s->mig_rec[0];
+            sb.rec[1] = s->mig_rec[1];
+            sb.cap = s->mig_cap;
+            k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
+                s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb);
+            // ignored (and, outside slab runs, dropped) particles sit behind the tiles: carried over
+            // and counted here; a slab run ends dropped / migrated particles at this point
+            const int* n_end = s->geo.slab_on ? s->tile_base + s->geo.n_tiles + 1 : nullptr;
+            k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, q, qn, s->src, n_dep, n_end, n, sort_tables(s));
+            s->launches += 2;
+            s->cur ^= 1;
+            s->counts_pending = true;
+        } else {
+            k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid, d_mouse);
+            ++s->launches;
+            s->sorted_valid = false;   // positions moved; the generic path re-sorts from scratch
+        }
+        if (timed) {
+            CU_TRY(cudaEventRecord(ev[5], s->stream));
+            s->last_ev = ev;
+            s->timers_recorded = true;
+        }
     }
-    s->launches += 3;
     CU_TRY(cudaGetLastError());
     return FLUID_OK;
 }
@@ -529,6 +566,54 @@ fluid_status refresh_counts(fluid_sim* s, int64_t counts[4]) {
     return FLUID_OK;
 }
 
+}  // namespace
+
+namespace {
+template <typename T>
+__device__ __forceinline__ bool nonzero(const T& v);
+template <> __device__ __forceinline__ bool nonzero<float>(const float& v) { return v != 0.0f; }
+template <> __device__ __forceinline__ bool nonzero<float4>(const float4& v) {
+    return v.x != 0.0f || v.y != 0.0f || v.z != 0.0f || v.w != 0.0f;
+}
+__device__ __forceinline__ void add_to(float& a, const float& b) { a += b; }
+__device__ __forceinline__ void add_to(float4& a, const float4& b) { a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w; }
+
+// own planes += the neighbour's partial sums; a + b == b + a, so both ranks end with the same bits.
+template <typename T>
+__global__ void k_accumulate_planes(const __grid_constant__ Geo g, T* __restrict__ own, const T* __restrict__ recv,
+                                    int64_t n, int z_first, unsigned char* __restrict__ dirty) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const T v = recv[e];
+    if (!nonzero<T>(v)) return;
+    T a = own[e];
+    add_to(a, v);
+    own[e] = a;
+    const int plane = g.size[0] * g.size[1];
+    const int z = z_first + static_cast<int>(e / plane);
+    const int r = static_cast<int>(e % plane);
+    const int x = r % g.size[0], y = r / g.size[0];
+    dirty[((z / T3::Z) * g.tdim[1] + y / T3::Y) * g.tdim[0] + x / T3::X] = 1;   // cleared next substep
+}
+
+__global__ void k_append_migrants(const __grid_constant__ Geo g, const float* __restrict__ rec, int m, Particles to,
+                                  int first, SortTables t, bool count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = j < m;
+    int cls = -1, bucket = 0;
+    const int d = first + j;
+    if (valid) {
+        const float* r = rec + static_cast<size_t>(j) * MIG_WORDS;
+        const float4 p = make_float4(r[0], r[1], r[2], r[15]);
+        to.P[d] = p;
+        to.V[d] = make_float4(r[3], r[4], r[5], r[16]);
+        to.CA[d] = make_float4(r[6], r[7], r[8], r[9]);
+        to.CB[d] = make_float4(r[10], r[11], r[12], r[13]);
+        to.CC[d] = r[14];
+        bucket = bucket_of<3>(g, p, cls);
+    }
+    if (count) count_global(t, d, bucket, valid);   // `count` is uniform over the grid
+}
 }  // namespace
 
 // =========================================================================================
@@ -634,6 +719,11 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->block_sums);
     cudaFree(s->dirty[0]);
     cudaFree(s->dirty[1]);
+    for (int sd = 0; sd < 2; ++sd) {
+        cudaFree(s->mig_rec[sd]);
+        cudaFree(s->halo_mass_recv[sd]);
+        cudaFree(s->halo_node_recv[sd]);
+    }
     cudaFree(s->class_count);
     cudaFree(s->grid);
     cudaFree(s->d_mouse);
@@ -702,8 +792,9 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     g.n_tiles = static_cast<int>(tiles);
     g.n_cells_pad = static_cast<int>(tiles * 256);
     g.guard = 1 + g.size[0] + (D == 3 ? g.size[0] * g.size[1] : 0);
-    g.slab_lo = s->slab_lo;
-    g.slab_hi = s->slab_hi;
+    g.slab_on = 0;   // set_rect resets the decomposition: call fluid_slab_set again
+    g.slab_lo = 0;
+    g.slab_hi = 0;
     g.res_f = res;
     g.res_i = s->cfg.grid_res;
     g.res_shift = -1;
@@ -745,12 +836,12 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     s->count = s->cell_off = s->tile_total = s->tile_base = s->block_sums = nullptr;
     s->rect_set = false;
     s->sorted_valid = s->counts_pending = false;
-    const int64_t n_pt = static_cast<int64_t>(g.n_tiles) + 2;            // tiles + the two pseudo tiles
+    const int64_t n_pt = static_cast<int64_t>(g.n_tiles) + N_PSEUDO;     // tiles + the pseudo tiles
     const int64_t m = n_pt * TILE_CELLS;                                  // buckets
     const int64_t nb = (n_pt + SCAN_CHUNK - 1) / SCAN_CHUNK;
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
     if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
-    CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + 2) * sizeof(int4)));
+    CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + N_PSEUDO) * sizeof(int4)));
     for (int b = 0; b < 2; ++b) {
         CU_TRY(cudaMalloc(&s->dirty[b], g.n_tiles + 8));
         CU_TRY(cudaMemsetAsync(s->dirty[b], 0, g.n_tiles + 8, s->stream));
@@ -1070,22 +1161,150 @@ fluid_status fluid_launch_count(const fluid_sim* s, int64_t* launches) {
     return FLUID_OK;
 }
 
-// ---- z-slab decomposition: not built yet (round-1 scope note in DESIGN.md) -----------------
-fluid_status fluid_slab_set(fluid_sim* s, int32_t, int32_t) {
+// ---- z-slab decomposition ----------------------------------------------
+
+fluid_status fluid_reserve(fluid_sim* s, int64_t capacity) {
+    if (!s || capacity < 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_reserve: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    return ensure_capacity(s, capacity);
+}
+
+fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t has_lower, int32_t has_upper) {
     if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_set: null handle");
-    return fail(FLUID_ERR_STATE, "fluid_slab_set: slab decomposition is not implemented yet");
+    if (s->dim != 3 || !s->tiled) return fail(FLUID_ERR_STATE, "fluid_slab_set: needs the tiled 3D path");
+    if (!s->rect_set) return fail(FLUID_ERR_STATE, "fluid_slab_set: call set_rect first");
+    CU_TRY(cudaSetDevice(s->device));
+    const int lo = z_lo - s->geo.org[2], hi = z_hi - s->geo.org[2];
+    if (lo < 0 || hi > s->geo.size[2] || lo >= hi || (lo % T3::Z) != 0 || (has_upper && (hi % T3::Z) != 0))
+        return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_set: slab must lie in the grid with faces on tile boundaries (multiples of 4 cells from the grid origin)");
+    if ((has_lower && lo < 2) || (has_upper && hi > s->geo.size[2] - 2))
+        return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_set: an interface needs a node plane on either side");
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->geo.slab_on = 1;
+    s->geo.slab_lo = lo;
+    s->geo.slab_hi = hi;
+    s->has_nb[0] = has_lower != 0;
+    s->has_nb[1] = has_upper != 0;
+    const int64_t plane2 = 2LL * s->geo.size[0] * s->geo.size[1];
+    if (s->mig_cap == 0) s->mig_cap = 1 << 18;
+    for (int sd = 0; sd < 2; ++sd) {
+        cudaFree(s->mig_rec[sd]);
+        cudaFree(s->halo_mass_recv[sd]);
+        cudaFree(s->halo_node_recv[sd]);
+        s->mig_rec[sd] = nullptr;
+        s->halo_mass_recv[sd] = nullptr;
+        s->halo_node_recv[sd] = nullptr;
+        if (!s->has_nb[sd]) continue;
+        CU_TRY(cudaMalloc(&s->mig_rec[sd], static_cast<int64_t>(s->mig_cap) * MIG_WORDS * sizeof(float)));
+        CU_TRY(cudaMalloc(&s->halo_mass_recv[sd], plane2 * sizeof(float)));
+        CU_TRY(cudaMalloc(&s->halo_node_recv[sd], plane2 * sizeof(float4)));
+    }
+    s->sorted_valid = s->counts_pending = false;
+    return FLUID_OK;
 }
-fluid_status fluid_slab_halo(fluid_sim*, int32_t, void**, void**, int64_t*) {
-    return fail(FLUID_ERR_STATE, "fluid_slab_halo: slab decomposition is not implemented yet");
+
+fluid_status fluid_slab_planes(fluid_sim* s, int32_t side, int32_t kind, void** d_own, void** d_recv, int64_t* n_elems) {
+    if (!s || side < 0 || side > 1 || kind < 0 || kind > 1 || !d_own || !d_recv || !n_elems)
+        return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_planes: bad argument");
+    if (!s->geo.slab_on || !s->has_nb[side]) return fail(FLUID_ERR_STATE, "fluid_slab_planes: no neighbour on that side");
+    const int zb = side == 0 ? s->geo.slab_lo : s->geo.slab_hi;      // interface, relative cell
+    const int64_t plane = static_cast<int64_t>(s->geo.size[0]) * s->geo.size[1];
+    const int64_t first = s->geo.guard + (zb - 1) * plane;          // node planes zb-1 and zb
+    *n_elems = 2 * plane;
+    if (kind == 0) {
+        *d_own = s->gmass + first;
+        *d_recv = s->halo_mass_recv[side];
+    } else {
+        *d_own = s->grid + first;
+        *d_recv = s->halo_node_recv[side];
+    }
+    return FLUID_OK;
 }
-fluid_status fluid_slab_phase(fluid_sim*, int32_t, const float*) {
-    return fail(FLUID_ERR_STATE, "fluid_slab_phase: slab decomposition is not implemented yet");
+
+fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy) {
+    if (!s || phase < 0 || phase > 2) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_phase: bad argument");
+    if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_phase: fluid_slab_set has not been called");
+    CU_TRY(cudaSetDevice(s->device));
+    const float* d_mouse = nullptr;
+    if (phase == 2) ST_TRY(upload_mouse(s, mouse_xy, &d_mouse));
+    if (s->n == 0) {
+        // a rank may hold no particles yet still has to take part in the exchanges: its planes must be zero
+        if (phase == 0 && !s->grid_clean) {
+            const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+            CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+            CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
+            CU_TRY(cudaMemsetAsync(s->dirty[0], 0, s->geo.n_tiles, s->stream));
+            CU_TRY(cudaMemsetAsync(s->dirty[1], 0, s->geo.n_tiles, s->stream));
+            s->grid_clean = true;
+        } else if (phase == 0) {
+            k_clear_tiles<<<blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128), 128, 0, s->stream>>>(
+                s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
+            s->dirty_cur ^= 1;
+            CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
+        }
+        return FLUID_OK;
+    }
+    return substep_impl<3>(s, d_mouse, false, nullptr, 1 << phase);
 }
-fluid_status fluid_slab_accumulate_halo(fluid_sim*, int32_t) {
-    return fail(FLUID_ERR_STATE, "fluid_slab_accumulate_halo: slab decomposition is not implemented yet");
+
+fluid_status fluid_slab_accumulate(fluid_sim* s, int32_t side, int32_t kind) {
+    if (!s || side < 0 || side > 1 || kind < 0 || kind > 1) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_accumulate: bad argument");
+    if (!s->geo.slab_on || !s->has_nb[side]) return fail(FLUID_ERR_STATE, "fluid_slab_accumulate: no neighbour on that side");
+    CU_TRY(cudaSetDevice(s->device));
+    const int zb = side == 0 ? s->geo.slab_lo : s->geo.slab_hi;
+    const int64_t plane = static_cast<int64_t>(s->geo.size[0]) * s->geo.size[1];
+    const int64_t first = s->geo.guard + (zb - 1) * plane;
+    const int64_t n = 2 * plane;
+    unsigned char* dirty = s->dirty[s->dirty_cur];
+    if (kind == 0)
+        k_accumulate_planes<float><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->gmass + first, s->halo_mass_recv[side], n, zb - 1, dirty);
+    else
+        k_accumulate_planes<float4><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid + first, s->halo_node_recv[side], n, zb - 1, dirty);
+    ++s->launches;
+    CU_TRY(cudaGetLastError());
+    return FLUID_OK;
 }
-fluid_status fluid_slab_migrants(fluid_sim*, int32_t, void**, int64_t*) {
-    return fail(FLUID_ERR_STATE, "fluid_slab_migrants: slab decomposition is not implemented yet");
+
+fluid_status fluid_slab_migrants(fluid_sim* s, void** d_lower, int64_t* n_lower, void** d_upper, int64_t* n_upper) {
+    if (!s || !d_lower || !n_lower || !d_upper || !n_upper) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_migrants: null argument");
+    if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_migrants: fluid_slab_set has not been called");
+    CU_TRY(cudaSetDevice(s->device));
+    int h_scal[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int h_base[4] = {0, 0, 0, 0};   // tile_base[n_tiles .. n_tiles+3]: ignored | dropped | migrated | total
+    CU_TRY(cudaMemcpyAsync(h_scal, s->scal, sizeof(h_scal), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaMemcpyAsync(h_base, s->tile_base + s->geo.n_tiles, sizeof(h_base), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    if (h_scal[SCAL_MIG_OVERFLOW]) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_migrants: more particles left the slab in one substep than the migrant buffer holds");
+    *d_lower = s->mig_rec[0];
+    *d_upper = s->mig_rec[1];
+    *n_lower = h_scal[SCAL_MIG_LO];
+    *n_upper = h_scal[SCAL_MIG_HI];
+    if (s->n > 0 && s->counts_pending) {
+        // the buffer g2p + k_tail just wrote ends where this substep's sort put the dropped bucket
+        s->dropped_total += h_base[2] - h_base[1];
+        s->n = h_base[1];
+    }
+    return FLUID_OK;
+}
+
+fluid_status fluid_slab_append(fluid_sim* s, const void* d_records, int64_t n) {
+    if (!s || n < 0 || (n > 0 && !d_records)) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_append: bad argument");
+    if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_append: fluid_slab_set has not been called");
+    if (n == 0) return FLUID_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    if (s->n + n > s->cap) return fail(FLUID_ERR_OUT_OF_MEMORY, "fluid_slab_append: particle capacity exhausted (fluid_reserve more head room)");
+    // With a live sort state the records join it (bucket + rank by global atomics, like k_tail);
+    // without one (this rank was empty, or particles were just added) they are only stored and the
+    // next substep sorts from scratch.
+    const bool join = s->sorted_valid && s->counts_pending;
+    k_append_migrants<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, static_cast<const float*>(d_records),
+                                                                static_cast<int>(n), s->buf[s->cur],
+                                                                static_cast<int>(s->n), sort_tables(s), join);
+    if (!join) s->sorted_valid = s->counts_pending = false;
+    ++s->launches;
+    CU_TRY(cudaGetLastError());
+    s->n += n;
+    return FLUID_OK;
 }
 
 }  // extern "C"

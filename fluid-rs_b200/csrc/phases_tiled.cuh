@@ -391,6 +391,12 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
 
 // ---- update + g2p -----------------------------------------------------------------------------
 
+// Slab runs: the particles that leave this rank's slab are packed here for the neighbour rank.
+struct SlabBufs {
+    float* rec[2];   // 17 words per record (16 f32 + id), through the lower / upper face
+    int cap;
+};
+
 // COUNT: also start the next substep's neighbour search (sort.cuh): every particle of the tile
 // gets its new bucket; the ones that stay in this tile are ranked with shared-memory integer
 // atomics (native ATOMS.ADD), the few that change tile or are dropped go to the immigrant list.
@@ -398,7 +404,7 @@ template <bool COUNT>
 __global__ void __launch_bounds__(T3::THREADS, 4)
 k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
-            const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st) {
+            const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb) {
     __shared__ float4 sm[T3::WARPS * T3::SLOTS];
     __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -528,6 +534,35 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
                 const bool leaves = active && !stays;
                 if (active) st.gcell[d] = bucket;
                 if (stays) st.rank[d] = atomicAdd(&scnt[bucket & (TILE_CELLS - 1)], 1);
+                if (g.slab_on) {
+                    // left this rank's slab (bucket_of said "migrated"): hand the record to the neighbour
+                    int side = -1;
+                    if (advance && bucket == migrated_bucket(g))
+                        side = rust_as_i32(floorf(pos[2])) - g.org[2] < g.slab_lo ? 0 : 1;
+#pragma unroll
+                    for (int sd = 0; sd < 2; ++sd) {
+                        const unsigned mm = __ballot_sync(0xffffffffu, side == sd);
+                        if (mm == 0) continue;
+                        int slot = 0;
+                        if (lane == 0) slot = atomicAdd(&st.scal[SCAL_MIG_LO + sd], __popc(mm));
+                        slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(mm & ((1u << lane) - 1u));
+                        if (side == sd) {
+                            if (slot < sb.cap) {
+                                float* r = sb.rec[sd] + static_cast<size_t>(slot) * MIG_WORDS;
+                                const float4 a = qn.P[d], v = qn.V[d], ca = qn.CA[d], cb = qn.CB[d];
+                                r[0] = a.x; r[1] = a.y; r[2] = a.z;
+                                r[3] = v.x; r[4] = v.y; r[5] = v.z;
+                                r[6] = ca.x; r[7] = ca.y; r[8] = ca.z; r[9] = ca.w;
+                                r[10] = cb.x; r[11] = cb.y; r[12] = cb.z; r[13] = cb.w;
+                                r[14] = qn.CC[d];
+                                r[15] = a.w;
+                                r[16] = v.w;   // id bits
+                            } else {
+                                st.scal[SCAL_MIG_OVERFLOW] = 1;
+                            }
+                        }
+                    }
+                }
                 const unsigned lm = __ballot_sync(0xffffffffu, leaves);
                 if (lm) {
                     int slot = 0;

@@ -44,12 +44,15 @@ struct SortTables {
 };
 
 constexpr int TILE_CELLS = 256;
-constexpr int SCAL_N_ACTIVE = 0, SCAL_N_IMM = 1;
+constexpr int N_PSEUDO = 3;   // pseudo tiles behind the real ones: ignored, dropped, migrated away
+constexpr int SCAL_N_ACTIVE = 0, SCAL_N_IMM = 1, SCAL_MIG_LO = 2, SCAL_MIG_HI = 3, SCAL_MIG_OVERFLOW = 4;
+constexpr int MIG_WORDS = 17;   // packed migrant record: 16 f32 + id
 
 __device__ __forceinline__ bool is_tombstone(float x) { return isinf(x) && x > 0.0f; }
 
 __device__ __forceinline__ int limbo_bucket(const Geo& g) { return g.n_cells_pad; }
 __device__ __forceinline__ int dropped_bucket(const Geo& g) { return g.n_cells_pad + TILE_CELLS; }
+__device__ __forceinline__ int migrated_bucket(const Geo& g) { return g.n_cells_pad + 2 * TILE_CELLS; }
 
 // Bucket and class of a position (exact integer rules, common.cuh).
 template <int DIM>
@@ -68,6 +71,10 @@ __device__ __forceinline__ int bucket_of(const Geo& g, const float4 p, int& cls)
 #pragma unroll
     for (int a = 0; a < DIM; ++a)   // key in p_rect => cell inside the grid; the clamp guards memory only
         rel[a] = min(max(cell[a] - g.org[a], 0), g.size[a] - 1);
+    if (DIM == 3 && g.slab_on && (rel[2] < g.slab_lo || rel[2] >= g.slab_hi)) {
+        cls = CLS_LIMBO;   // another rank's slab: not ours to deposit or advance
+        return migrated_bucket(g);
+    }
     return tiled_cell_index<DIM>(g, rel);
 }
 
@@ -123,8 +130,10 @@ k_immigrants(SortTables t) {
 template <int DIM>
 __global__ void __launch_bounds__(256)
 k_tail(const __grid_constant__ Geo g, Particles from, Particles to, const int* __restrict__ src,
-       const int* __restrict__ n_deposit, int n, SortTables t) {
+       const int* __restrict__ n_deposit, const int* __restrict__ n_end, int n, SortTables t) {
     const int first = *n_deposit;
+    // slab runs carry only the ignored particles over: dropped and migrated ones end here
+    if (n_end) n = min(n, *n_end);
     const int len = n - first;
     const int stride = gridDim.x * blockDim.x;
     const int rounds = (len + stride - 1) / stride;
@@ -263,7 +272,7 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
     __shared__ __align__(16) int tab_all[PERM_WARPS][PERM_MAX_W * 8];
     const int lane = threadIdx.x & 31;
     const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= g.n_tiles + 2) return;
+    if (t >= g.n_tiles + N_PSEUDO) return;
     const int base = tile_base[t];
     const int n_t = tile_base[t + 1] - base;
     if (n_t <= 0) return;

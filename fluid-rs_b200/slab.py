@@ -1,0 +1,227 @@
+"""z-slab decomposition across the GPUs of one box.
+
+One process per GPU (torch.distributed, NCCL over NVLink).  Every rank holds the same dense node
+grid geometry and owns the particles whose cell floor(pos.z) lies in its slab.  Per substep:
+
+    phase 0  sort + clear + p2g 1     -> exchange the two MASS planes of each interface, add
+    phase 1  p2g 2                    -> exchange the two NODE planes of each interface, add
+    phase 2  update + g2p             -> particles that left the slab go to the neighbour
+
+The reference's own analogue is the +-1 block halo ring (`p_rect` vs `a_rect`, 3d:84-86) in which
+particles deposit but are not advanced, and the per-block mailboxes `swap_mul` (3d:327-358).
+
+The exchange protocol (`SlabDriver`) only needs an engine object with
+    phase(i), planes(side, kind) -> (own, recv) tensors, accumulate(side, kind),
+    migrants() -> (lower, upper) tensors of packed records, append(tensor)
+so it runs unchanged over NCCL with the CUDA engine and over gloo with a CPU mock (tests).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+MIG_WORDS = 17     # packed migrant record: 16 f32 + id bits
+TILE_Z = 4         # slab faces sit on tile boundaries (multiples of 4 cells from the grid origin)
+
+
+def plan_slabs(fill_lo: float, fill_hi: float, origin_z: int, size_z: int, world: int):
+    """Split the grid's z range [origin_z, origin_z + size_z) into `world` slabs (world cells).
+    Interior faces divide the filled range [fill_lo, fill_hi) evenly, rounded to multiples of 4 cells
+    from the grid origin; the first and last slab extend to the ends of the grid."""
+    faces = [origin_z]
+    for r in range(1, world):
+        z = fill_lo + (fill_hi - fill_lo) * r / world
+        rel = int(round((z - origin_z) / TILE_Z)) * TILE_Z
+        rel = min(max(rel, faces[-1] - origin_z + TILE_Z), size_z - TILE_Z * (world - r))
+        faces.append(origin_z + rel)
+    faces.append(origin_z + size_z)
+    return [(faces[r], faces[r + 1]) for r in range(world)]
+
+
+class SlabDriver:
+    """The per-substep exchange protocol, independent of device and backend."""
+
+    def __init__(self, engine, rank: int, world: int, dist=None, device="cpu"):
+        self.e = engine
+        self.rank, self.world = rank, world
+        self.dist = dist
+        self.device = device
+        self.nb = [rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None]
+        self.migrated_out = 0
+        self.migrated_in = 0
+
+    # -- halo planes -----------------------------------------------------------------------------
+    def exchange_planes(self, kind: int):
+        """Both ranks of an interface hold partial sums of its two node planes: swap and add."""
+        dist = self.dist
+        ops, sides = [], []
+        for side in (0, 1):
+            if self.nb[side] is None:
+                continue
+            own, recv = self.e.planes(side, kind)
+            ops.append(dist.P2POp(dist.isend, own, self.nb[side]))
+            ops.append(dist.P2POp(dist.irecv, recv, self.nb[side]))
+            sides.append(side)
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for side in sides:
+            self.e.accumulate(side, kind)
+
+    # -- migration -------------------------------------------------------------------------------
+    def migrate(self):
+        import torch
+        dist = self.dist
+        out = self.e.migrants()                      # [lower, upper] tensors (n * 17 words), may be empty
+        n_out = [int(t.numel()) // MIG_WORDS for t in out]
+        # 1. counts
+        send_cnt = [torch.tensor([n_out[s]], dtype=torch.int64, device=self.device) for s in (0, 1)]
+        recv_cnt = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in (0, 1)]
+        ops = []
+        for side in (0, 1):
+            if self.nb[side] is None:
+                continue
+            ops.append(dist.P2POp(dist.isend, send_cnt[side], self.nb[side]))
+            ops.append(dist.P2POp(dist.irecv, recv_cnt[side], self.nb[side]))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        n_in = [int(recv_cnt[s].item()) if self.nb[s] is not None else 0 for s in (0, 1)]
+        # 2. records
+        bufs = [self.e.recv_buffer(side, n_in[side]) if n_in[side] else None for side in (0, 1)]
+        ops = []
+        for side in (0, 1):
+            if self.nb[side] is None:
+                continue
+            if n_out[side]:
+                ops.append(dist.P2POp(dist.isend, out[side], self.nb[side]))
+            if n_in[side]:
+                ops.append(dist.P2POp(dist.irecv, bufs[side], self.nb[side]))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for side in (0, 1):
+            if n_in[side]:
+                self.e.append(bufs[side])
+        self.migrated_out += sum(n_out)
+        self.migrated_in += sum(n_in)
+
+    def substep(self, mouse=None):
+        self.e.phase(0, None)
+        self.exchange_planes(0)
+        self.e.phase(1, None)
+        self.exchange_planes(1)
+        self.e.phase(2, mouse)
+        self.migrate()
+
+
+class _DevArray:
+    """Zero-copy view of device memory for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr: int, n: int, typestr: str = "<f4"):
+        self.__cuda_array_interface__ = dict(shape=(n,), typestr=typestr, data=(int(ptr), False), version=2)
+
+
+class CudaSlabEngine:
+    """Adapter: the C ABI's fluid_slab_* calls behind the SlabDriver's engine interface."""
+
+    def __init__(self, pkg, sim):
+        self.pkg, self.sim = pkg, sim
+        self.L = pkg.lib()
+        self._recv = [None, None]
+
+    def _chk(self, st):
+        if st != 0:
+            raise self.pkg.FluidError(st, self.L.fluid_last_error().decode())
+
+    def phase(self, i, mouse):
+        mp = None
+        if mouse is not None:
+            m = np.ascontiguousarray(mouse, dtype=np.float32)
+            mp = m.ctypes.data_as(C.POINTER(C.c_float))
+        self._chk(self.L.fluid_slab_phase(self.sim._h, i, mp))
+
+    def planes(self, side, kind):
+        import torch
+        own, recv, n = C.c_void_p(), C.c_void_p(), C.c_int64()
+        self._chk(self.L.fluid_slab_planes(self.sim._h, side, kind, C.byref(own), C.byref(recv), C.byref(n)))
+        words = n.value * (4 if kind == 1 else 1)
+        return (torch.as_tensor(_DevArray(own.value, words), device="cuda"),
+                torch.as_tensor(_DevArray(recv.value, words), device="cuda"))
+
+    def accumulate(self, side, kind):
+        self._chk(self.L.fluid_slab_accumulate(self.sim._h, side, kind))
+
+    def migrants(self):
+        import torch
+        lo, hi, nlo, nhi = C.c_void_p(), C.c_void_p(), C.c_int64(), C.c_int64()
+        self._chk(self.L.fluid_slab_migrants(self.sim._h, C.byref(lo), C.byref(nlo), C.byref(hi), C.byref(nhi)))
+        out = []
+        for ptr, n in ((lo, nlo.value), (hi, nhi.value)):
+            if n and ptr.value:
+                out.append(torch.as_tensor(_DevArray(ptr.value, n * MIG_WORDS), device="cuda"))
+            else:
+                out.append(torch.empty(0, dtype=torch.float32, device="cuda"))
+        return out
+
+    def recv_buffer(self, side, n):
+        import torch
+        need = n * MIG_WORDS
+        if self._recv[side] is None or self._recv[side].numel() < need:
+            self._recv[side] = torch.empty(max(need, 1 << 16), dtype=torch.float32, device="cuda")
+        return self._recv[side][:need]
+
+    def append(self, t):
+        self._chk(self.L.fluid_slab_append(self.sim._h, C.c_void_p(t.data_ptr()), t.numel() // MIG_WORDS))
+
+
+class SlabSimulation:
+    """`Simulation` spread over the ranks of a torch.distributed process group, one z-slab each."""
+
+    def __init__(self, pkg, cfg, rect_min, rect_max, fill_lo_z, fill_hi_z, rank, world, dist, device: int,
+                 reserve: int = 0):
+        import torch
+        self.pkg, self.rank, self.world = pkg, rank, world
+        self.sim = pkg.Simulation.new(cfg, device=device)
+        self.stream = torch.cuda.Stream(device=device)
+        torch.cuda.set_stream(self.stream)
+        self.sim.set_stream(self.stream.cuda_stream)
+        self.sim.set_rect(rect_min, rect_max)
+        r = self.sim.rects()
+        self.slabs = plan_slabs(fill_lo_z, fill_hi_z, int(r["origin"][2]), int(r["size"][2]), world)
+        self.z_lo, self.z_hi = self.slabs[rank]
+        L = pkg.lib()
+        if reserve:
+            st = L.fluid_reserve(self.sim._h, int(reserve))
+            if st != 0:
+                raise pkg.FluidError(st, L.fluid_last_error().decode())
+        st = L.fluid_slab_set(self.sim._h, self.z_lo, self.z_hi, int(rank > 0), int(rank < world - 1))
+        if st != 0:
+            raise pkg.FluidError(st, L.fluid_last_error().decode())
+        self.driver = SlabDriver(CudaSlabEngine(pkg, self.sim), rank, world, dist, device=f"cuda:{device}")
+        self.iterations = int(self.sim.config.iterations)
+
+    def owns(self, records: np.ndarray) -> np.ndarray:
+        cz = np.floor(records[:, 2]).astype(np.int64)
+        return (cz >= self.z_lo) & (cz < self.z_hi)
+
+    def add_particles(self, records, ids=None):
+        """Adds the records that fall into this rank's slab (callers may pass the whole scene)."""
+        records = np.ascontiguousarray(records, dtype=np.float32).reshape(-1, 16)
+        keep = self.owns(records)
+        if ids is not None:
+            ids = np.ascontiguousarray(ids, dtype=np.int32)[keep]
+        if keep.any():
+            self.sim.add_particles(records[keep], ids)
+        return int(keep.sum())
+
+    def substeps(self, n, mouse=None):
+        for _ in range(n):
+            self.driver.substep(mouse)
+
+    def step(self, mouse=None):
+        self.substeps(self.iterations, mouse)
+
+    def close(self):
+        self.sim.close()

@@ -159,25 +159,37 @@ fluid_status fluid_read_grid(fluid_sim* sim, float* nodes, int64_t capacity_node
 fluid_status fluid_launch_count(const fluid_sim* sim, int64_t* launches);
 
 /* ---- multi-GPU: z-slab decomposition (no reference equivalent) --- */
-/* Restrict this handle to the slab of node planes [z_lo, z_hi) (cells, world coords; for 2D
- * the slab axis is y).  Particles whose cell is outside the slab are exported by
- * fluid_slab_collect_migrants.  The caller (one process per GPU) moves halo planes and
- * migrants between ranks (NCCL / peer copies) using the device pointers returned here. */
-fluid_status fluid_slab_set(fluid_sim* sim, int32_t lo, int32_t hi);
-/* Device pointer + node count of the `which` halo plane pair: 0 = low side, 1 = high side.
- * Each is two contiguous node planes of float4 {momentum.xyz, mass}: the plane just outside
- * the slab followed/preceded by the outermost owned plane. */
-fluid_status fluid_slab_halo(fluid_sim* sim, int32_t which, void** d_send, void** d_recv,
-                             int64_t* n_float4);
-/* Split substep for slab runs: phase A = sort + clear + p2g 1 (then exchange+add halos),
- * phase B = p2g 2 (then exchange+add halos), phase C = update + g2p + migrant collection. */
+/* One process per GPU.  Every rank creates its handle with the SAME config and set_rect (so all
+ * ranks index the same dense node grid) and owns the particles whose cell floor(pos.z) lies in
+ * [z_lo, z_hi) (world cells; z_lo - grid origin must be a multiple of 4, the tile depth).  Only
+ * particles inside the slab are advanced; one that leaves it is handed to the neighbour.
+ *
+ * Per substep the caller drives (the host binding fluid-rs_b200/slab.py does exactly this):
+ *   fluid_slab_phase(0)  sort + clear + p2g 1        -> exchange + accumulate MASS planes
+ *   fluid_slab_phase(1)  p2g 2                       -> exchange + accumulate NODE planes
+ *   fluid_slab_phase(2)  update + g2p, migrants packed
+ *   fluid_slab_migrants  counts (synchronises)       -> exchange migrant records
+ *   fluid_slab_append    received records join this rank's particles
+ * The node planes shared with a neighbour across the interface at cell z_b are z_b - 1 and z_b
+ * (stencil reach 1, 3d:157-158): two contiguous planes of the dense grid. */
+fluid_status fluid_slab_set(fluid_sim* sim, int32_t z_lo, int32_t z_hi, int32_t has_lower, int32_t has_upper);
+/* Make room for `capacity` particles now, so that appending migrants never reallocates. */
+fluid_status fluid_reserve(fluid_sim* sim, int64_t capacity);
+/* Shared planes of interface `side` (0 = at z_lo, 1 = at z_hi).  kind 0: node masses (float per
+ * node), kind 1: node records (float4 {momentum.xyz, mass}).  *d_own points INTO the grid (this
+ * rank's partial sums, send it as is), *d_recv is a staging buffer of the same size for the
+ * neighbour's partial sums; *n_elems counts floats (kind 0) or float4s (kind 1). */
+fluid_status fluid_slab_planes(fluid_sim* sim, int32_t side, int32_t kind, void** d_own, void** d_recv,
+                               int64_t* n_elems);
 fluid_status fluid_slab_phase(fluid_sim* sim, int32_t phase, const float* mouse_xy);
-/* Add the received halo planes (d_recv buffers) into the grid. */
-fluid_status fluid_slab_accumulate_halo(fluid_sim* sim, int32_t which);
-/* Migrants leaving through side `which` after phase C: device pointer to packed records
- * (17 words: 16 floats + id) and their count (host value, synchronises the stream). */
-fluid_status fluid_slab_migrants(fluid_sim* sim, int32_t which, void** d_records,
-                                 int64_t* n);
+/* own planes += received planes (and mark the touched node blocks for the next clear). */
+fluid_status fluid_slab_accumulate(fluid_sim* sim, int32_t side, int32_t kind);
+/* After phase 2: device pointers to the packed records (17 words: 16 f32 + id) of the particles that
+ * left through the lower / upper face and their counts.  Synchronises the stream. */
+fluid_status fluid_slab_migrants(fluid_sim* sim, void** d_lower, int64_t* n_lower, void** d_upper,
+                                 int64_t* n_upper);
+/* Append n packed 17-word records that are resident in device memory. */
+fluid_status fluid_slab_append(fluid_sim* sim, const void* d_records, int64_t n);
 
 #ifdef __cplusplus
 }
