@@ -191,11 +191,8 @@ def run_ours(args):
     if args.gpus != world and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
     torch.cuda.set_device(local_rank)
-    dist = None
     if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        raise SystemExit("multi-GPU slab decomposition is not wired into bench.py yet")
+        return run_slabs(args, pkg, world, rank, local_rank)
 
     sc = scenes.dam_break_for_gpus(args.gpus) if not args.scene else getattr(scenes, args.scene)()
     iters = sc.cfg["iterations"]
@@ -308,6 +305,137 @@ def run_ours(args):
     if rank == 0:
         print(json.dumps(line))
     sim.close()
+
+
+def run_slabs(args, pkg, world, rank, local_rank):
+    """N > 1: z-slab decomposition, one rank per GPU, 2^24 particles per GPU (weak scaling; N = 8 is
+    BASELINE config 5).  Halo planes and migrating particles move over NCCL (NVLink)."""
+    import torch
+    import torch.distributed as dist
+    scenes = pkg.scenes
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    sc = scenes.dam_break_for_gpus(world)
+    iters = sc.cfg["iterations"]
+    rf = scenes.rec_floats(3)
+    fill_lo, fill_hi = float(sc.fill_lo[2]), float(sc.fill_hi[2])
+    # every rank computes the same plan and the same per-rank particle counts
+    tmp = pkg.Simulation.new(sc.cfg, device=local_rank)
+    tmp.set_rect(sc.rect_min, sc.rect_max)
+    r = tmp.rects()
+    tmp.close()
+    slabs = pkg.slab.plan_slabs(fill_lo, fill_hi, int(r["origin"][2]), int(r["size"][2]), world)
+    spans = [(max(a, fill_lo), min(b, fill_hi)) for a, b in slabs]
+    n_rank = [int(round(sc.n * (hi - lo) / (fill_hi - fill_lo))) for lo, hi in spans]
+    n_rank[-1] += sc.n - sum(n_rank)
+    n_local, id0 = n_rank[rank], sum(n_rank[:rank])
+
+    sim = pkg.slab.SlabSimulation(pkg, sc.cfg, sc.rect_min, sc.rect_max, fill_lo, fill_hi, rank, world, dist,
+                                  local_rank, reserve=int(n_local * 1.25) + (1 << 20))
+    host = torch.empty((n_local, rf), dtype=torch.float32, pin_memory=True)
+    hnp = host.numpy()
+    lo = [float(sc.fill_lo[0]), float(sc.fill_lo[1]), spans[rank][0]]
+    hi = [float(sc.fill_hi[0]), float(sc.fill_hi[1]), spans[rank][1]]
+    chunk = 1 << 21
+    for s0 in range(0, n_local, chunk):
+        c = min(chunk, n_local - s0)
+        hnp[s0:s0 + c] = scenes.box_records(3, lo, hi, n_local, seed=scenes.SEED + 1000 * (rank + 1), start=s0, count=c)
+    ids = torch.arange(id0, id0 + n_local, dtype=torch.int32)
+    back = torch.empty((n_local + (1 << 20), rf), dtype=torch.float32, pin_memory=True)
+
+    def load():
+        sim.sim.clear_particles()
+        L = pkg.lib()
+        import ctypes as C
+        st = L.fluid_add_particles(sim.sim._h, C.cast(C.c_void_p(host.data_ptr()), C.POINTER(C.c_float)),
+                                   C.cast(C.c_void_p(ids.data_ptr()), C.POINTER(C.c_int32)), n_local)
+        assert st == 0, L.fluid_last_error()
+
+    load()
+    stream = sim.stream
+    for _ in range(args.warmup):
+        sim.step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = sim.sim.launch_count()
+    sim.sim.profile(True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0.record(stream)
+    for _ in range(args.steps):
+        sim.step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    ms_t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    prof = sim.sim.profile_read()
+    sim.sim.profile(False)
+    launches_t = torch.tensor([sim.sim.launch_count() - launches0], device="cuda", dtype=torch.int64)
+    dist.all_reduce(launches_t)
+    clocks = sampler.stop()
+    cnt = torch.tensor([sim.sim.particle_counts()["active"], sim.driver.migrated_out], device="cuda", dtype=torch.int64)
+    dist.all_reduce(cnt)
+    assert int(cnt[0].item()) == sc.n, (int(cnt[0].item()), sc.n)
+    value = sc.n * iters * args.steps / (ms * 1e-3)
+
+    peak, peak_src = measured_peaks()
+    nsub = max(prof["substeps"], 1)
+    per_phase_ms = {k: prof[k] / nsub * 1e3 for k in ("sort", "clear", "p2g 1", "p2g 2", "update", "g2p")}
+    dom = max(("clear", "p2g 1", "p2g 2", "g2p"), key=lambda k: per_phase_ms[k])
+    achieved = ALG_BYTES[dom] * n_local / (per_phase_ms[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_particle": ALG_BYTES[dom], "ms_per_launch": per_phase_ms[dom],
+                "step_frac": value * ALG_BYTES_STEP / 1e9 / (peak * world),
+                "per_phase_ms": per_phase_ms,
+                "note": "rank 0's kernels; phase brackets in slab runs include the halo exchange that follows the phase"}
+
+    # end to end: every step uploads this rank's records from pinned memory and reads every record back
+    e2e_steps = max(2, min(args.steps, 3))
+
+    def e2e_step():
+        load()
+        sim.step()
+        n = sim.sim.read_particles_into(back.data_ptr(), back.shape[0])
+        return n
+
+    e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e2e_t = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_value = sc.n * iters * e2e_steps / float(e2e_t.item())
+    rec_bytes = n_local * rf * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(sc.describe(), substeps_per_step=iters,
+                       l2="inputs larger than L2 (particle state 1.1 GB, node grid > 1 GB per GPU)",
+                       parallelism=f"z-slabs x{world}", particles_per_gpu=n_rank,
+                       slabs=[list(x) for x in slabs]),
+        "roofline": roofline, "cpu_baseline": None,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes, "d2h_bytes_per_step": rec_bytes,
+                "steps": e2e_steps, "what": "per rank: clear + add_particles(pinned host records) + step() + "
+                                            "read_particles(all records); bytes are per rank"},
+        "gpu_launches": int(launches_t.item()), "clocks": clocks, "ms_per_substep": ms / args.steps / iters,
+        "migrated_particles": int(cnt[1].item()),
+    }
+    if rank == 0:
+        print(json.dumps(line))
+    sim.close()
+    dist.barrier()
+    dist.destroy_process_group()
 
 
 def main():

@@ -269,10 +269,9 @@ __global__ void k_pack_active(const __grid_constant__ Geo g, Particles q, int n,
     bool take = false;
     if (i < n) {
         float4 p = q.P[i];
-        if (!is_tombstone(p.x)) {
-            float pos[3] = {p.x, p.y, p.z};
-            take = classify_pos<DIM>(g, pos) == CLS_ACTIVE;
-        }
+        int cls = -1;
+        (void)bucket_of<DIM>(g, p, cls);   // same rule as the sort (tombstones, rects, slab ownership)
+        take = cls == CLS_ACTIVE;
     }
     unsigned m = __ballot_sync(0xffffffffu, take);
     int lane = threadIdx.x & 31;

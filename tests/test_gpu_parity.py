@@ -433,3 +433,19 @@ def test_fast_key_matches_exact_key(pkg, orc, scenes):
         np.testing.assert_array_equal(t["cell"][go], r["cell"][ro])
         sim.close()
         ref.close()
+
+
+# ---- multi-GPU (needs >= 2 devices; run with `gpurun --gpus 2`) ---------------------------------------
+
+def test_two_gpu_slab_run_matches_single_gpu():
+    import subprocess
+    import sys
+    from pathlib import Path
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    root = Path(__file__).resolve().parent.parent
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(root / "tests" / "slab_check.py")],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "SLAB CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
