@@ -313,6 +313,9 @@ def run_slabs(args, pkg, world, rank, local_rank):
     import torch
     import torch.distributed as dist
     scenes = pkg.scenes
+    # stdout carries exactly one JSON line: keep NCCL's version banner (NCCL_DEBUG=VERSION) out of it
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     sc = scenes.dam_break_for_gpus(world)
     iters = sc.cfg["iterations"]
