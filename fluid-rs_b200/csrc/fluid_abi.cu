@@ -346,7 +346,9 @@ fluid_status sort_finish(fluid_sim* s) {
     k_scan_sums<<<1, 1024, 0, s->stream>>>(s->block_sums, static_cast<int>(nb));
     k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base);
     CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
-    const unsigned pb = blocks_for(static_cast<int64_t>(m) * 32, PERM_WARPS * 32);
+    // persistent: one wave of CTAs, each warp scans 32 tiles per step
+    const unsigned pb = std::min<unsigned>(blocks_for(static_cast<int64_t>((m + 31) / 32) * 32, PERM_WARPS * 32),
+                                           static_cast<unsigned>(s->sm_count * 8));
     if (DIM == 3) {
         s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
         k_tile_perm<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal,
@@ -454,7 +456,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                 s->grid_clean = true;
             } else {
                 // only the node blocks the previous or the coming deposits can touch
-                k_clear_tiles<<<blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128), 128, 0, s->stream>>>(
+                k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>((s->geo.n_tiles + 31) / 32) * 32, 128), static_cast<unsigned>(s->sm_count * 8)), 128, 0, s->stream>>>(
                     s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
                 ++s->launches;
             }
@@ -1236,7 +1238,7 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
             CU_TRY(cudaMemsetAsync(s->dirty[1], 0, s->geo.n_tiles, s->stream));
             s->grid_clean = true;
         } else if (phase == 0) {
-            k_clear_tiles<<<blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128), 128, 0, s->stream>>>(
+            k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>((s->geo.n_tiles + 31) / 32) * 32, 128), static_cast<unsigned>(s->sm_count * 8)), 128, 0, s->stream>>>(
                 s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
             s->dirty_cur ^= 1;
             CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));

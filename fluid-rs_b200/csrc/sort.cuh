@@ -271,11 +271,25 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
             int* __restrict__ scal, unsigned char* __restrict__ dirty) {
     __shared__ __align__(16) int tab_all[PERM_WARPS][PERM_MAX_W * 8];
     const int lane = threadIdx.x & 31;
-    const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (t >= g.n_tiles + N_PSEUDO) return;
-    const int base = tile_base[t];
-    const int n_t = tile_base[t + 1] - base;
-    if (n_t <= 0) return;
+    // persistent warps: each scans 32 tiles at a time (one per lane) and works through the non-empty ones
+    const int n_all = g.n_tiles + N_PSEUDO;
+    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int chunk = warp_global * 32; chunk < n_all; chunk += n_warps * 32) {
+    const int my_t = chunk + lane;
+    int my_base = 0, my_n = 0;
+    if (my_t < n_all) {
+        my_base = tile_base[my_t];
+        my_n = tile_base[my_t + 1] - my_base;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, my_n > 0);
+    while (todo) {
+    const int sel = __ffs(todo) - 1;
+    todo &= todo - 1;
+    const int t = chunk + sel;
+    const int base = __shfl_sync(0xffffffffu, my_base, sel);
+    const int n_t = __shfl_sync(0xffffffffu, my_n, sel);
+    __syncwarp();
     const int c_first = t * TILE_CELLS;
     if (t >= g.n_tiles) {   // pseudo tiles: a single bucket, slots stay in rank order
         if (lane == 0) {
@@ -283,7 +297,7 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
             count[c_first] = 0;
         }
         for (int r = lane; r < n_t; r += 32) perm[base + r] = base + r;
-        return;
+        continue;
     }
     if (dirty && lane < 27) {
         // the particles of this tile deposit into the node blocks of its 3x3x3 tile neighbourhood:
@@ -322,7 +336,7 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
     if (ORDER == ORDER_CELL) {
         if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, (n_t + 31) / 32);
         for (int r = 0; r < mine; ++r) perm[base + q_first + r] = base + q_first + r;
-        return;
+        continue;
     }
     const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
     const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
@@ -372,6 +386,8 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         perm[base + q] = base + w * per + min(w, extra) + pos;
         if (++w == w_count) w = 0;
     }
+    }   // tiles of this chunk
+    }   // chunks
 }
 
 // Sorted slot -> storage index.  The particle streams are never reordered by a separate pass:
