@@ -94,6 +94,8 @@ struct fluid_sim {
     int* cell_off = nullptr; // per bucket: first cell-sorted slot (cellStart)
     int* tile_total = nullptr;
     int* tile_base = nullptr;    // exclusive scan of tile_total; [n_tiles] = number of p_rect particles
+    int* cand = nullptr;         // tiles that hold particles (from the scan), input list of k_tile_perm
+    int* dirty_list = nullptr;   // node blocks to clear this substep
     unsigned char* dirty[2] = {nullptr, nullptr};   // node blocks touched by the current / previous sort
     int dirty_cur = 0;
     bool grid_clean = false;     // every node outside the dirty blocks is zero
@@ -342,20 +344,21 @@ fluid_status sort_finish(fluid_sim* s) {
     const int n = static_cast<int>(s->n);
     const int m = s->geo.n_tiles + N_PSEUDO;
     const unsigned nb = static_cast<unsigned>(s->n_scan_blocks);
+    CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
     k_scan_partial<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums);
     k_scan_sums<<<1, 1024, 0, s->stream>>>(s->block_sums, static_cast<int>(nb));
-    k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base);
-    CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
-    // persistent: one wave of CTAs, each warp scans 32 tiles per step
-    const unsigned pb = std::min<unsigned>(blocks_for(static_cast<int64_t>((m + 31) / 32) * 32, PERM_WARPS * 32),
-                                           static_cast<unsigned>(s->sm_count * 8));
+    k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base, s->cand,
+                                                    s->scal + SCAL_N_CAND);
+    // persistent warps over the candidate list: one resident wave of small CTAs
+    const unsigned pb = std::min<unsigned>(blocks_for(static_cast<int64_t>(m) * 32, PERM_WARPS * 32),
+                                           static_cast<unsigned>(s->sm_count * 16));
     if (DIM == 3) {
         s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
         k_tile_perm<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal,
-                                                                          s->dirty[s->dirty_cur]);
+                                                                          s->dirty[s->dirty_cur], s->cand);
     } else {
         k_tile_perm<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal,
-                                                                      nullptr);
+                                                                      nullptr, s->cand);
     }
     s->launches += 4;
     if (n > 0) {
@@ -456,9 +459,12 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                 s->grid_clean = true;
             } else {
                 // only the node blocks the previous or the coming deposits can touch
-                k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>((s->geo.n_tiles + 31) / 32) * 32, 128), static_cast<unsigned>(s->sm_count * 8)), 128, 0, s->stream>>>(
-                    s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
-                ++s->launches;
+                k_dirty_list<<<blocks_for(s->geo.n_tiles, 256), 256, 0, s->stream>>>(
+                    s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY);
+                k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
+                                                  static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
+                    s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass);
+                s->launches += 2;
             }
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
             k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
@@ -720,6 +726,8 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->block_sums);
     cudaFree(s->dirty[0]);
     cudaFree(s->dirty[1]);
+    cudaFree(s->cand);
+    cudaFree(s->dirty_list);
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -829,6 +837,9 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     cudaFree(s->block_sums);
     cudaFree(s->dirty[0]);
     cudaFree(s->dirty[1]);
+    cudaFree(s->cand);
+    cudaFree(s->dirty_list);
+    s->cand = s->dirty_list = nullptr;
     s->dirty[0] = s->dirty[1] = nullptr;
     s->grid_clean = false;
     s->grid = nullptr;
@@ -843,6 +854,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
     if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
     CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + N_PSEUDO) * sizeof(int4)));
+    CU_TRY(cudaMalloc(&s->cand, (n_pt + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->dirty_list, (n_pt + 8) * sizeof(int)));
     for (int b = 0; b < 2; ++b) {
         CU_TRY(cudaMalloc(&s->dirty[b], g.n_tiles + 8));
         CU_TRY(cudaMemsetAsync(s->dirty[b], 0, g.n_tiles + 8, s->stream));
@@ -1238,10 +1251,13 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
             CU_TRY(cudaMemsetAsync(s->dirty[1], 0, s->geo.n_tiles, s->stream));
             s->grid_clean = true;
         } else if (phase == 0) {
-            k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>((s->geo.n_tiles + 31) / 32) * 32, 128), static_cast<unsigned>(s->sm_count * 8)), 128, 0, s->stream>>>(
-                s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->grid, s->gmass);
-            s->dirty_cur ^= 1;
             CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
+            k_dirty_list<<<blocks_for(s->geo.n_tiles, 256), 256, 0, s->stream>>>(
+                s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY);
+            k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
+                                              static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
+                s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass);
+            s->dirty_cur ^= 1;
         }
         return FLUID_OK;
     }

@@ -52,7 +52,6 @@ struct TileCtx {
     int count;     // particles in the tile
     int windows;   // W
     int per, extra;
-    int node0;     // global index of the footprint's first node (valid when !edge)
     bool edge;     // the footprint sticks out of the p_rect grid
 };
 
@@ -75,23 +74,12 @@ __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileC
     tc.c0[2] = tz * T3::Z;
     tc.edge = tc.c0[0] == 0 || tc.c0[1] == 0 || tc.c0[2] == 0 || tc.c0[0] + T3::X + 1 > g.size[0] ||
               tc.c0[1] + T3::Y + 1 > g.size[1] || tc.c0[2] + T3::Z + 1 > g.size[2];
-    tc.node0 = g.guard + (tc.c0[0] - 1) + ((tc.c0[1] - 1) + (tc.c0[2] - 1) * g.size[1]) * g.size[0];
 }
 
 // window w of the tile: first slot (relative to tc.base) and length
 __device__ __forceinline__ void window_range(const TileCtx& tc, int w, int& off, int& len) {
     off = w * tc.per + min(w, tc.extra);
     len = w < tc.windows ? tc.per + (w < tc.extra ? 1 : 0) : 0;
-}
-
-// Offsets of the 600 footprint nodes from the footprint's first node, shared by every interior tile:
-// filled once per CTA, turns the per-node index arithmetic of tile init / flush into one add.
-__device__ __forceinline__ void fill_foot_table(const Geo& g, int* tab) {
-    for (int k = threadIdx.x; k < T3::NODES; k += blockDim.x) {
-        int lx = k % T3::NX, r = k / T3::NX, ly = r % T3::NY, lz = r / T3::NY;
-        tab[k] = lx + (ly + lz * g.size[1]) * g.size[0];
-    }
-    __syncthreads();   // the only CTA-wide barrier: before any warp starts its tiles
 }
 
 // Footprint node k (0..599): shared-memory slot and global node index (-1 outside the grid).
@@ -108,11 +96,6 @@ __device__ __forceinline__ int footprint_to_global(const Geo& g, const TileCtx& 
     if (k >= T3::NODES || x < 0 || y < 0 || z < 0 || x >= g.size[0] || y >= g.size[1] || z >= g.size[2])
         return -1;
     return g.guard + x + (y + z * g.size[1]) * g.size[0];
-}
-// same, through the per-CTA offset table for tiles whose footprint lies inside the grid
-__device__ __forceinline__ int footprint_node(const Geo& g, const TileCtx& tc, int k, const int* tab) {
-    if (tc.edge) return footprint_to_global(g, tc, k);
-    return k < T3::NODES ? tc.node0 + tab[k] : -1;
 }
 
 // Per-particle stencil in tile coordinates.
@@ -159,37 +142,43 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
 // ---- clear: zero the 8x8x4 node blocks marked dirty by the sort (clear_grid, 3d:136-146) ----------
 // A block is dirty when a tile of its 3x3x3 neighbourhood holds particles now or held some in the
 // previous substep (flags of two consecutive sorts are kept: `dirty_prev | dirty_now`).
-__global__ void __launch_bounds__(128)
-k_clear_tiles(const __grid_constant__ Geo g, const unsigned char* __restrict__ dirty_now,
-              unsigned char* __restrict__ dirty_prev, float4* __restrict__ grid,
-              float* __restrict__ gmass) {
+__global__ void __launch_bounds__(256)
+k_dirty_list(const __grid_constant__ Geo g, const unsigned char* __restrict__ dirty_now,
+             unsigned char* __restrict__ dirty_prev, int* __restrict__ list, int* __restrict__ n_list) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    bool d = false;
+    if (t < g.n_tiles) {
+        const bool was = dirty_prev[t] != 0;
+        d = was || dirty_now[t] != 0;
+        if (was) dirty_prev[t] = 0;   // dirty_prev becomes the next sort's dirty_now
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, d);
     const int lane = threadIdx.x & 31;
-    // persistent warps: 32 tile flags per step (one per lane), then the warp clears the dirty ones
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int slot = 0;
+    if (lane == 0 && m) slot = atomicAdd(n_list, __popc(m));
+    slot = __shfl_sync(0xffffffffu, slot, 0);
+    if (d) list[slot + __popc(m & ((1u << lane) - 1u))] = t;
+}
+
+__global__ void __launch_bounds__(128)
+k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const int* __restrict__ n_list,
+              float4* __restrict__ grid, float* __restrict__ gmass) {
+    const int lane = threadIdx.x & 31;
+    const int n = *n_list;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int chunk = warp_global * 32; chunk < g.n_tiles; chunk += n_warps * 32) {
-        const int my_t = chunk + lane;
-        bool is_dirty = false;
-        if (my_t < g.n_tiles) {
-            is_dirty = dirty_prev[my_t] != 0 || dirty_now[my_t] != 0;
-            if (dirty_prev[my_t]) dirty_prev[my_t] = 0;   // dirty_prev becomes the next sort's dirty_now
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, is_dirty);
-        while (todo) {
-            const int t = chunk + __ffs(todo) - 1;
-            todo &= todo - 1;
-            const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
-            // 256 nodes: lane -> x = lane & 7, y = (lane >> 3) + 4*(j & 1), z = j >> 1
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n; a += n_warps) {
+        const int t = list[a];
+        const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
+        // 256 nodes: lane -> x = lane & 7, y = (lane >> 3) + 4*(j & 1), z = j >> 1
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int x = tx * T3::X + (lane & 7);
-                const int y = ty * T3::Y + (lane >> 3) + 4 * (j & 1);
-                const int z = tz * T3::Z + (j >> 1);
-                if (x < g.size[0] && y < g.size[1] && z < g.size[2]) {
-                    const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
-                    grid[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    gmass[gi] = 0.0f;
-                }
+        for (int j = 0; j < 8; ++j) {
+            const int x = tx * T3::X + (lane & 7);
+            const int y = ty * T3::Y + (lane >> 3) + 4 * (j & 1);
+            const int z = tz * T3::Z + (j >> 1);
+            if (x < g.size[0] && y < g.size[1] && z < g.size[2]) {
+                const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
+                grid[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                gmass[gi] = 0.0f;
             }
         }
     }
@@ -202,8 +191,6 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
              const int* __restrict__ n_active, float* __restrict__ gmass) {
     __shared__ float sm[T3::WARPS * T3::SLOTS];
-    __shared__ int foot[T3::NODES];
-    fill_foot_table(g, foot);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = sm + warp * T3::SLOTS;
     const int n_act = *n_active;
@@ -254,7 +241,7 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
             const int k = lane + 32 * j;
             const float v = k < T3::NODES ? tile[footprint_slot(k)] : 0.0f;
             if (v != 0.0f) {
-                int gi = footprint_node(g, tc, k, foot);
+                int gi = footprint_to_global(g, tc, k);
                 if (gi >= 0) atomicAdd(&gmass[gi], v);
             }
         }
@@ -291,8 +278,6 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             float* __restrict__ dbg_density, float* __restrict__ dbg_pressure) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
-    __shared__ int foot[T3::NODES];
-    fill_foot_table(g, foot);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* acc = sm.acc[warp];
     float* ms = sm.mass[warp];
@@ -313,7 +298,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             float mv[FOOT_ITERS];
 #pragma unroll
             for (int j = 0; j < FOOT_ITERS; ++j) {
-                int gi = footprint_node(g, tc, lane + 32 * j, foot);
+                int gi = footprint_to_global(g, tc, lane + 32 * j);
                 mv[j] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
             }
 #pragma unroll
@@ -412,7 +397,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (k < T3::NODES) v = acc[footprint_slot(k)];
             if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
-                int gi = footprint_node(g, tc, k, foot);
+                int gi = footprint_to_global(g, tc, k);
                 if (gi >= 0) atomicAdd(&grid[gi], v);
             }
         }
@@ -438,8 +423,6 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb) {
     __shared__ float4 sm[T3::WARPS * T3::SLOTS];
     __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
-    __shared__ int foot[T3::NODES];
-    fill_foot_table(g, foot);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* vt = sm + warp * T3::SLOTS;
     int* scnt = scnt_all + warp * TILE_CELLS;
@@ -465,7 +448,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         for (int j = 0; j < FOOT_ITERS; ++j) {
             const int k = lane + 32 * j;
             if (k < T3::NODES) {
-                const int gi = footprint_node(g, tc, k, foot);
+                const int gi = footprint_to_global(g, tc, k);
                 const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + footprint_slot(k)));
                 const float4* gp = grid + (gi >= 0 ? gi : 0);
                 const int bytes = gi >= 0 ? 16 : 0;

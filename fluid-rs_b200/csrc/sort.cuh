@@ -46,6 +46,7 @@ struct SortTables {
 constexpr int TILE_CELLS = 256;
 constexpr int N_PSEUDO = 3;   // pseudo tiles behind the real ones: ignored, dropped, migrated away
 constexpr int SCAL_N_ACTIVE = 0, SCAL_N_IMM = 1, SCAL_MIG_LO = 2, SCAL_MIG_HI = 3, SCAL_MIG_OVERFLOW = 4;
+constexpr int SCAL_N_CAND = 5, SCAL_N_DIRTY = 6;
 constexpr int MIG_WORDS = 17;   // packed migrant record: 16 f32 + id
 
 __device__ __forceinline__ bool is_tombstone(float x) { return isinf(x) && x > 0.0f; }
@@ -219,8 +220,11 @@ k_scan_sums(int* __restrict__ block_sums, int nb) {
 }
 
 // out[k] = exclusive prefix, out[m] = grand total; the input is zeroed for the next round.
+// The indices of the non-zero inputs (tiles that hold particles) are appended to cand[] so that the
+// per-tile kernel can run persistent warps over a dense list instead of one CTA per (mostly empty) tile.
 __global__ void __launch_bounds__(SCAN_THREADS)
-k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, int* __restrict__ out) {
+k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, int* __restrict__ out,
+             int* __restrict__ cand, int* __restrict__ n_cand) {
     int base = blockIdx.x * SCAN_CHUNK + threadIdx.x * SCAN_ITEMS;
     int v[SCAN_ITEMS];
     int s = 0;
@@ -240,6 +244,20 @@ k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, in
         ex += v[k];
     }
     if (base <= m - 1 && m - 1 < base + SCAN_ITEMS) out[m] = ex;
+    if (cand) {
+        int nz = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) nz += v[k] > 0;
+        const int lane = threadIdx.x & 31;
+        const int inc = warp_inclusive_scan(nz);
+        const int warp_total = __shfl_sync(0xffffffffu, inc, 31);
+        int slot = 0;
+        if (lane == 31 && warp_total) slot = atomicAdd(n_cand, warp_total);
+        slot = __shfl_sync(0xffffffffu, slot, 31) + inc - nz;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k)
+            if (v[k] > 0) cand[slot++] = base + k;
+    }
 }
 
 // ---- per-tile order ---------------------------------------------------------------------------
@@ -268,28 +286,16 @@ template <int ORDER>
 __global__ void __launch_bounds__(PERM_WARPS * 32)
 k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* __restrict__ tile_base,
             int* __restrict__ cell_off, int* __restrict__ perm, int4* __restrict__ tiles,
-            int* __restrict__ scal, unsigned char* __restrict__ dirty) {
+            int* __restrict__ scal, unsigned char* __restrict__ dirty, const int* __restrict__ cand) {
     __shared__ __align__(16) int tab_all[PERM_WARPS][PERM_MAX_W * 8];
     const int lane = threadIdx.x & 31;
-    // persistent warps: each scans 32 tiles at a time (one per lane) and works through the non-empty ones
-    const int n_all = g.n_tiles + N_PSEUDO;
-    const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    // persistent warps over the list of tiles that hold particles (k_scan_final)
+    const int n_cand = scal[SCAL_N_CAND];
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int chunk = warp_global * 32; chunk < n_all; chunk += n_warps * 32) {
-    const int my_t = chunk + lane;
-    int my_base = 0, my_n = 0;
-    if (my_t < n_all) {
-        my_base = tile_base[my_t];
-        my_n = tile_base[my_t + 1] - my_base;
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, my_n > 0);
-    while (todo) {
-    const int sel = __ffs(todo) - 1;
-    todo &= todo - 1;
-    const int t = chunk + sel;
-    const int base = __shfl_sync(0xffffffffu, my_base, sel);
-    const int n_t = __shfl_sync(0xffffffffu, my_n, sel);
-    __syncwarp();
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_cand; a += n_warps) {
+    const int t = cand[a];
+    const int base = tile_base[t];
+    const int n_t = tile_base[t + 1] - base;
     const int c_first = t * TILE_CELLS;
     if (t >= g.n_tiles) {   // pseudo tiles: a single bucket, slots stay in rank order
         if (lane == 0) {
@@ -386,8 +392,8 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         perm[base + q] = base + w * per + min(w, extra) + pos;
         if (++w == w_count) w = 0;
     }
-    }   // tiles of this chunk
-    }   // chunks
+    __syncwarp();   // tab is reused by the next tile
+    }
 }
 
 // Sorted slot -> storage index.  The particle streams are never reordered by a separate pass:
