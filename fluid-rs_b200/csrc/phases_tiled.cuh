@@ -44,6 +44,8 @@ struct T3 {
     static constexpr int THREADS = WARPS * 32;
 };
 constexpr int FOOT_ITERS = (T3::NODES + 31) / 32;    // 19 footprint nodes per lane
+constexpr int FOOT_ROWS = T3::NY * T3::NZ;           // 60 rows of 10 nodes
+constexpr int FOOT_STEPS = FOOT_ROWS / 3;            // a warp takes 3 rows (30 lanes) per step
 
 struct TileCtx {
     int c0[3];     // first cell of the tile, relative to the grid origin
@@ -96,6 +98,30 @@ __device__ __forceinline__ int footprint_to_global(const Geo& g, const TileCtx& 
     if (k >= T3::NODES || x < 0 || y < 0 || z < 0 || x >= g.size[0] || y >= g.size[1] || z >= g.size[2])
         return -1;
     return g.guard + x + (y + z * g.size[1]) * g.size[0];
+}
+
+// Row-wise walk over the footprint: step `it` (0..19), lanes 0..29 -> row 3*it + lane/10, x = lane%10.
+// Returns the shared-memory slot; `gi` receives the global node index (-1 outside the grid / idle lane).
+struct FootLane {
+    int x, rsub;   // lane % 10, lane / 10 (3 for the two idle lanes)
+};
+__device__ __forceinline__ FootLane foot_lane(int lane) {
+    FootLane f;
+    f.rsub = lane / T3::NX;
+    f.x = lane - f.rsub * T3::NX;
+    return f;
+}
+__device__ __forceinline__ int foot_step(const Geo& g, const TileCtx& tc, const FootLane& f, int it, int& gi) {
+    const int r = 3 * it + f.rsub;
+    const int lz = (r * 205) >> 11;          // r / 10 for r < 64
+    const int ly = r - lz * T3::NY;
+    gi = -1;
+    if (f.rsub < 3) {
+        const int x = tc.c0[0] - 1 + f.x, y = tc.c0[1] - 1 + ly, z = tc.c0[2] - 1 + lz;
+        if (!tc.edge || (x >= 0 && y >= 0 && z >= 0 && x < g.size[0] && y < g.size[1] && z < g.size[2]))
+            gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
+    }
+    return f.x + T3::NX * ly + T3::PLANE * lz;
 }
 
 // Per-particle stencil in tile coordinates.
@@ -224,25 +250,27 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                 for (int ox = 0; ox < 3; ++ox) {
                     const float wxy = s.wx[ox] * s.wy[oy];
                     float* nd = tile + s.node0 + ox + T3::NX * oy;
-                    if (active) {   // three nodes along z: private to this lane within the window
-                        float a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
-                        a0 += wxy * wzm[0];
-                        a1 += wxy * wzm[1];
-                        a2 += wxy * wzm[2];
-                        nd[0] = a0;
-                        nd[T3::PLANE] = a1;
-                        nd[2 * T3::PLANE] = a2;
-                    }
+                    // three nodes along z: private to this lane within the window.  Loads and math
+                    // run for every lane (idle lanes point at a valid column), only the stores are
+                    // predicated: no branch in the chain.
+                    float a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
+                    a0 += wxy * wzm[0];
+                    a1 += wxy * wzm[1];
+                    a2 += wxy * wzm[2];
+                    if (active) nd[0] = a0;
+                    if (active) nd[T3::PLANE] = a1;
+                    if (active) nd[2 * T3::PLANE] = a2;
                     __syncwarp();
                 }
         }
+        const FootLane fl = foot_lane(lane);
 #pragma unroll 4
-        for (int j = 0; j < FOOT_ITERS; ++j) {
-            const int k = lane + 32 * j;
-            const float v = k < T3::NODES ? tile[footprint_slot(k)] : 0.0f;
-            if (v != 0.0f) {
-                int gi = footprint_to_global(g, tc, k);
-                if (gi >= 0) atomicAdd(&gmass[gi], v);
+        for (int it = 0; it < FOOT_STEPS; ++it) {
+            int gi;
+            const int sl = foot_step(g, tc, fl, it, gi);
+            if (gi >= 0) {
+                const float v = tile[sl];
+                if (v != 0.0f) atomicAdd(&gmass[gi], v);
             }
         }
         __syncwarp();
@@ -294,19 +322,21 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         load_prec(q, lane < len ? __ldg(&src[tc.base + off + lane]) : 0, lane < len, nxt);
         window_range(tc, 1, off, len);
         int i_next = lane < len ? __ldg(&src[tc.base + off + lane]) : 0;
+        const FootLane fl = foot_lane(lane);
         {   // node masses of the footprint: all loads in flight before the first store
-            float mv[FOOT_ITERS];
+            float mv[FOOT_STEPS];
 #pragma unroll
-            for (int j = 0; j < FOOT_ITERS; ++j) {
-                int gi = footprint_to_global(g, tc, lane + 32 * j);
-                mv[j] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
+            for (int it = 0; it < FOOT_STEPS; ++it) {
+                int gi;
+                (void)foot_step(g, tc, fl, it, gi);
+                mv[it] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
             }
 #pragma unroll
-            for (int j = 0; j < FOOT_ITERS; ++j) {
-                const int k = lane + 32 * j;
-                if (k < T3::NODES) {
-                    const int sl = footprint_slot(k);
-                    ms[sl] = mv[j];
+            for (int it = 0; it < FOOT_STEPS; ++it) {
+                int gi;
+                const int sl = foot_step(g, tc, fl, it, gi);
+                if (fl.rsub < 3) {
+                    ms[sl] = mv[it];
                     acc[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -375,30 +405,28 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                     const float G0 = wxy * M[6], G1 = wxy * M[7], G2 = wxy * M[8];
                     const float mw = wxy * m;
                     float4* nd = acc + s.node0 + ox + T3::NX * oy;
-                    if (active) {
-                        // three nodes along z: private to this lane within the window
-                        float4 a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
-                        a0.x += s.wz[0] * A0;  a0.y += s.wz[0] * A1;  a0.z += s.wz[0] * A2;  a0.w += s.wz[0] * mw;
-                        a1.x += s.wz[1] * A0 + q1 * G0;  a1.y += s.wz[1] * A1 + q1 * G1;
-                        a1.z += s.wz[1] * A2 + q1 * G2;  a1.w += s.wz[1] * mw;
-                        a2.x += s.wz[2] * A0 + q2 * G0;  a2.y += s.wz[2] * A1 + q2 * G1;
-                        a2.z += s.wz[2] * A2 + q2 * G2;  a2.w += s.wz[2] * mw;
-                        nd[0] = a0;
-                        nd[T3::PLANE] = a1;
-                        nd[2 * T3::PLANE] = a2;
-                    }
+                    // three nodes along z: private to this lane within the window; loads and math are
+                    // unconditional (idle lanes point at a valid column), only the stores are predicated
+                    float4 a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
+                    a0.x += s.wz[0] * A0;  a0.y += s.wz[0] * A1;  a0.z += s.wz[0] * A2;  a0.w += s.wz[0] * mw;
+                    a1.x += s.wz[1] * A0 + q1 * G0;  a1.y += s.wz[1] * A1 + q1 * G1;
+                    a1.z += s.wz[1] * A2 + q1 * G2;  a1.w += s.wz[1] * mw;
+                    a2.x += s.wz[2] * A0 + q2 * G0;  a2.y += s.wz[2] * A1 + q2 * G1;
+                    a2.z += s.wz[2] * A2 + q2 * G2;  a2.w += s.wz[2] * mw;
+                    if (active) nd[0] = a0;
+                    if (active) nd[T3::PLANE] = a1;
+                    if (active) nd[2 * T3::PLANE] = a2;
                     __syncwarp();
                 }
             }
         }
 #pragma unroll 4
-        for (int j = 0; j < FOOT_ITERS; ++j) {
-            const int k = lane + 32 * j;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (k < T3::NODES) v = acc[footprint_slot(k)];
-            if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
-                int gi = footprint_to_global(g, tc, k);
-                if (gi >= 0) atomicAdd(&grid[gi], v);
+        for (int it = 0; it < FOOT_STEPS; ++it) {
+            int gi;
+            const int sl = foot_step(g, tc, fl, it, gi);
+            if (gi >= 0) {
+                const float4 v = acc[sl];
+                if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) atomicAdd(&grid[gi], v);
             }
         }
         __syncwarp();
@@ -444,12 +472,13 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         }
         // node records of the footprint: cp.async (LDGSTS) straight into shared memory, all 19 per
         // lane in flight, zero-filled outside the p_rect grid; then update_grid in place
+        const FootLane fl = foot_lane(lane);
 #pragma unroll
-        for (int j = 0; j < FOOT_ITERS; ++j) {
-            const int k = lane + 32 * j;
-            if (k < T3::NODES) {
-                const int gi = footprint_to_global(g, tc, k);
-                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + footprint_slot(k)));
+        for (int it = 0; it < FOOT_STEPS; ++it) {
+            int gi;
+            const int sl = foot_step(g, tc, fl, it, gi);
+            if (fl.rsub < 3) {
+                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + sl));
                 const float4* gp = grid + (gi >= 0 ? gi : 0);
                 const int bytes = gi >= 0 ? 16 : 0;
                 asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(bytes) : "memory");
@@ -458,10 +487,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 4
-        for (int j = 0; j < FOOT_ITERS; ++j) {
-            const int k = lane + 32 * j;
-            if (k < T3::NODES) {
-                const int sl = footprint_slot(k);
+        for (int it = 0; it < FOOT_STEPS; ++it) {
+            int gi;
+            const int sl = foot_step(g, tc, fl, it, gi);
+            if (fl.rsub < 3) {
                 float4 nd = vt[sl];
                 if (nd.w > 0.0f) {   // update_grid (3d:253-256); one IEEE reciprocal, three multiplies
                     const float inv = __frcp_rn(nd.w);

@@ -279,6 +279,12 @@ k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, in
 //                 [w*(N/W) + min(w, N%W), + N/W + (w < N%W)).
 enum TileOrder : int { ORDER_CELL = 0, ORDER_CLASS_RR = 1 };
 
+// floor(x / w) for 0 <= x < 8192, 1 <= w <= 32 without an integer division: (x + 0.5) / w is at least
+// 0.5/32 away from an integer while the float product is off by less than 2^-10.
+__device__ __forceinline__ int small_div(int x, float inv_w) {
+    return __float2int_rz((static_cast<float>(x) + 0.5f) * inv_w);
+}
+
 constexpr int PERM_WARPS = 4;
 constexpr int PERM_MAX_W = 32;   // windows per tile covered by the in-window merge table
 
@@ -355,28 +361,31 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
     n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 2);
     const int s_cls = __shfl_sync(0xffffffffu, q_first, lane & ~3);   // start of my class
     int* tab = tab_all[(threadIdx.x >> 5)];
-    const bool merge = w_count <= PERM_MAX_W;
+    const bool merge = w_count <= PERM_MAX_W && n_t < 8192;
+    const float inv_w = 1.0f / static_cast<float>(w_count);
     if (merge) {
         // tab[w*8 + b] = members of class b in window w: those q in [S_b, S_b + N_b) with q = w (mod W)
         const int b = lane & 7;
         const int nb = __shfl_sync(0xffffffffu, n_cls, 4 * b);
         const int sb = __shfl_sync(0xffffffffu, s_cls, 4 * b);
+        const int sb_mod = sb - small_div(sb, inv_w) * w_count;
         for (int w = lane >> 3; w < w_count; w += 4) {
-            int off = (w - sb) % w_count;
+            int off = w - sb_mod;
             if (off < 0) off += w_count;
-            tab[w * 8 + b] = off < nb ? (nb - off + w_count - 1) / w_count : 0;
+            tab[w * 8 + b] = off < nb ? small_div(nb - off + w_count - 1, inv_w) : 0;
         }
     }
     __syncwarp();
     const int my_cls = lane >> 2;
-    int w = (q_first) % w_count;
+    const int s_mod = merge ? s_cls - small_div(s_cls, inv_w) * w_count : 0;
+    int w = merge ? q_first - small_div(q_first, inv_w) * w_count : q_first % w_count;
     for (int r = 0; r < mine; ++r) {
         const int q = q_first + r;              // position in the class-major sequence
         int pos;
         if (merge) {
-            int off = (w - s_cls) % w_count;
+            int off = w - s_mod;
             if (off < 0) off += w_count;
-            const int k = (q - (s_cls + off)) / w_count;   // my index among my class in window w
+            const int k = small_div(q - (s_cls + off), inv_w);   // my index among my class in window w
             const int4 ta = *reinterpret_cast<const int4*>(tab + w * 8);
             const int4 tb = *reinterpret_cast<const int4*>(tab + w * 8 + 4);
             const int n[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
