@@ -342,6 +342,8 @@ def run_slabs(args, pkg, world, rank, local_rank):
     for s0 in range(0, n_local, chunk):
         c = min(chunk, n_local - s0)
         hnp[s0:s0 + c] = scenes.box_records(3, lo, hi, n_local, seed=scenes.SEED + 1000 * (rank + 1), start=s0, count=c)
+        # lo + u*(hi-lo) can round up to exactly hi (once in 2^24): keep every particle inside this rank's cells
+        np.minimum(hnp[s0:s0 + c, 2], np.nextafter(np.float32(hi[2]), np.float32(lo[2])), out=hnp[s0:s0 + c, 2])
     ids = torch.arange(id0, id0 + n_local, dtype=torch.int32)
     back = torch.empty((n_local + (1 << 20), rf), dtype=torch.float32, pin_memory=True)
 
