@@ -91,6 +91,9 @@ SIGNATURES = {
     "fluid_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), _i64p]),
     "fluid_debug_substep": (C.c_int, [C.c_void_p, _fp, C.c_int64, _ip, _ip, _ip, _fp, _fp, _i64p]),
     "fluid_debug_neighbour_table": (C.c_int, [C.c_void_p, C.c_int64, _ip, _ip, _i64p]),
+    "fluid_render_frame": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_int32, _ip]),
+    "fluid_frame_char": (C.c_char, [C.c_int32]),
+    "fluid_debug_tiles": (C.c_int, [C.c_void_p, C.c_int64, _ip, _i64p]),
     "fluid_read_grid": (C.c_int, [C.c_void_p, _fp, C.c_int64, _i64p]),
     "fluid_launch_count": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_slab_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
@@ -279,6 +282,18 @@ class Simulation:
         d["substeps"] = n.value
         return d
 
+    # ---- headless frame: `draw` without a terminal (3d:461-500) --------------------------------
+    def frame_counts(self, viewport=(64.0, 64.0), cols: int = 80, rows: int = 40) -> np.ndarray:
+        vp = np.ascontiguousarray(viewport, dtype=np.float32)
+        out = np.zeros((rows, cols), dtype=np.int32)
+        _check(lib().fluid_render_frame(self._h, _as_fp(vp), cols, rows, out.ctypes.data_as(_ip)))
+        return out
+
+    def frame_text(self, viewport=(64.0, 64.0), cols: int = 80, rows: int = 40) -> str:
+        ramp = " .-=*%$#"
+        c = np.clip(self.frame_counts(viewport, cols, rows), 0, 7)
+        return "\n".join("".join(ramp[v] for v in row) for row in c)
+
     # ---- plumbing ----------------------------------------------------------------------
     def set_stream(self, cuda_stream: int | None):
         _check(lib().fluid_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
@@ -351,6 +366,14 @@ class Simulation:
                                          _as_fp(den), _as_fp(prs), C.byref(w)))
         n = w.value
         return dict(ids=ids[:n], cell=cell[:n], key=key[:n], density=den[:n], pressure=prs[:n])
+
+    def debug_tiles(self):
+        """Active tile list {tile, first slot, N, W} of the current sort (after neighbour_table())."""
+        n = C.c_int64()
+        _check(lib().fluid_debug_tiles(self._h, 0, None, C.byref(n)))
+        out = np.empty((max(n.value, 1), 4), dtype=np.int32)
+        _check(lib().fluid_debug_tiles(self._h, n.value, out.ctypes.data_as(_ip), C.byref(n)))
+        return out[: n.value]
 
     def neighbour_table(self):
         c = self.particle_counts()

@@ -623,6 +623,22 @@ __global__ void k_append_migrants(const __grid_constant__ Geo g, const float* __
 }
 }  // namespace
 
+// `draw`'s binning (3d:472-481): console_xy = (pos.xy / viewport * console) as ivec2
+template <int DIM>
+__global__ void k_render_frame(const __grid_constant__ Geo g, Particles q, int n, float vx, float vy, int cols, int rows,
+                               int* __restrict__ counts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = q.P[i];
+    int cls = -1;
+    (void)bucket_of<DIM>(g, p, cls);
+    if (cls != CLS_ACTIVE) return;   // iter_particle yields a_rect blocks only (3d:383-387)
+    const int cx = rust_as_i32(__fmul_rn(__fdiv_rn(p.x, vx), static_cast<float>(cols)));
+    const int cy = rust_as_i32(__fmul_rn(__fdiv_rn(p.y, vy), static_cast<float>(rows)));
+    if (cx < 0 || cy < 0 || cx >= cols || cy >= rows) return;
+    atomicAdd(&counts[cy * cols + cx], 1);
+}
+
 // =========================================================================================
 extern "C" {
 
@@ -1146,6 +1162,47 @@ fluid_status fluid_debug_neighbour_table(fluid_sim* s, int64_t capacity, int32_t
     cudaFree(d_ids);
     cudaFree(d_ref);
     return st;
+}
+
+char fluid_frame_char(int32_t n) {   // 3d:488-497
+    static const char ramp[] = " .-=*%$#";
+    return ramp[n < 1 ? 0 : (n > 7 ? 7 : n)];
+}
+
+fluid_status fluid_render_frame(fluid_sim* s, const float viewport_xy[2], int32_t cols, int32_t rows, int32_t* counts) {
+    if (!s || !viewport_xy || !counts || cols <= 0 || rows <= 0 || static_cast<int64_t>(cols) * rows > (1 << 24))
+        return fail(FLUID_ERR_INVALID_ARG, "fluid_render_frame: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    const int64_t bins = static_cast<int64_t>(cols) * rows;
+    std::memset(counts, 0, bins * sizeof(int32_t));
+    if (s->n == 0 || !s->rect_set) return FLUID_OK;
+    ST_TRY(ensure_stage(s, 0, bins));
+    CU_TRY(cudaMemsetAsync(s->d_stage_ids, 0, bins * sizeof(int), s->stream));
+    const int n = static_cast<int>(s->n);
+    if (s->dim == 3)
+        k_render_frame<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n, viewport_xy[0], viewport_xy[1], cols, rows, s->d_stage_ids);
+    else
+        k_render_frame<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->buf[s->cur], n, viewport_xy[0], viewport_xy[1], cols, rows, s->d_stage_ids);
+    ++s->launches;
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(counts, s->d_stage_ids, bins * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    return FLUID_OK;
+}
+
+fluid_status fluid_debug_tiles(fluid_sim* s, int64_t capacity_tiles, int32_t* tiles4, int64_t* n_tiles) {
+    if (!s || capacity_tiles < 0 || !n_tiles) return fail(FLUID_ERR_INVALID_ARG, "fluid_debug_tiles: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    *n_tiles = 0;
+    if (!s->rect_set || !s->sorted_valid) return FLUID_OK;
+    int h = 0;
+    CU_TRY(cudaMemcpyAsync(&h, s->scal + SCAL_N_ACTIVE, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    *n_tiles = h;
+    if (!tiles4) return FLUID_OK;
+    if (h > capacity_tiles) return fail(FLUID_ERR_TOO_SMALL, "fluid_debug_tiles: capacity too small");
+    if (h > 0) CU_TRY(cudaMemcpy(tiles4, s->tiles, static_cast<size_t>(h) * sizeof(int4), cudaMemcpyDeviceToHost));
+    return FLUID_OK;
 }
 
 fluid_status fluid_read_grid(fluid_sim* s, float* nodes, int64_t capacity_nodes, int64_t* n_nodes) {

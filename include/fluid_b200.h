@@ -137,6 +137,16 @@ const char*  fluid_phase_label(int32_t phase);
 fluid_status fluid_profile_enable(fluid_sim* sim, int32_t on);
 fluid_status fluid_profile_read(fluid_sim* sim, double seconds[6], int64_t* n_substeps);
 
+/* ---- headless frame: the binning of `draw` (3d:461-500) without a terminal ------------------- */
+/* counts[row*cols + col] = number of a_rect particles whose
+ *   console_xy = (pos.xy / viewport * (cols, rows)) as ivec2     (3d:473, truncating cast)
+ * falls on that character cell; particles outside the console are skipped (3d:475-477).
+ * The reference's main uses viewport (64,64) and an 80 x 40 console (3d:539-540). */
+fluid_status fluid_render_frame(fluid_sim* sim, const float viewport_xy[2], int32_t cols, int32_t rows,
+                                int32_t* counts);
+/* The character `draw` prints for a bin count (3d:488-497): " .-=*%$#". */
+char         fluid_frame_char(int32_t count);
+
 /* ---- parity / debug (no reference equivalent; test harness only) ---------------------- */
 /* Run ONE substep and return, per p_rect particle in the engine's sorted order:
  * id, cell (floor(pos), 3d:153), block key (3d:398-401), density and pressure (locals at
@@ -150,6 +160,12 @@ fluid_status fluid_debug_substep(fluid_sim* sim, const float* mouse_xy, int64_t 
  * the engine's tiled cell order; `cell_index` lets a checker rebuild cellStart/cellEnd. */
 fluid_status fluid_debug_neighbour_table(fluid_sim* sim, int64_t capacity, int32_t* ids,
                                          int32_t* cell_index, int64_t* n_written);
+/* Active tile list of the current sort (3D tiled path): per tile {tile id, first sorted slot,
+ * particles N, windows W}.  Window w of a tile holds the sorted slots
+ * [first + w*(N/W) + min(w, N%W), + N/W + (w < N%W)).  With fluid_debug_neighbour_table this lets a
+ * checker verify the invariant the shared-memory accumulation relies on: no two particles of one
+ * window share an (x,y) cell column.  Call right after fluid_debug_neighbour_table. */
+fluid_status fluid_debug_tiles(fluid_sim* sim, int64_t capacity_tiles, int32_t* tiles4, int64_t* n_tiles);
 /* Node grid after the last substep, reference layout: vel_or_momentum[dim] then mass, per
  * node, x fastest (3d:169-172).  `stage`: 0 = as left by the last substep (velocities after
  * update where mass>0). capacity in nodes. */
