@@ -37,10 +37,37 @@ sys.path.insert(0, str(ROOT))
 METRIC = "particle-updates/sec (3D WCSPH-reference step: MLS-MPM substeps)"
 UNIT = "particle-updates/s"
 
-# Algorithmic bytes per particle-substep, SURVEY.md section 8(d) (3D, A/N = 1):
-#   p2g 1: 64 B particle read + 32 B node RMW; p2g 2: 52 B + 12 B mass read... per-phase split
-ALG_BYTES = {"clear": 16.0, "p2g 1": 64.0 + 32.0, "p2g 2": 52.0 + 28.0, "update": 0.0, "g2p": 72.0 + 16.0}
-ALG_BYTES_STEP = 280.0     # sum of the above = 188 + 92
+# Algorithmic bytes per particle-substep (3D, A/N = 1).  The whole step uses SURVEY.md section 8(d):
+# 188 B of particle streams + 92 B of node traffic = 280 B.  Per kernel the same stream table is
+# re-cut along OUR kernel boundaries: the momentum scatter of p2g_1 runs inside
+# the "p2g 2" kernel, so that kernel reads the particle once (64 B), the node mass (4 B) and does the
+# node read-modify-write (32 B) = 100 B; "p2g 1" (mass only) reads pos+mass (16 B) and RMWs the node
+# mass (8 B); clear writes the node record and the node mass (20 B); update+g2p is SURVEY's 88 B.
+ALG_BYTES = {"clear": 20.0, "p2g 1": 24.0, "p2g 2": 100.0, "update": 0.0, "g2p": 88.0}
+ALG_BYTES_STEP = 280.0
+KERNEL_OF_PHASE = {"clear": "k_clear_tiles", "p2g 1": "k_mass_tiled", "p2g 2": "k_p2g_tiled", "g2p": "k_g2p_tiled"}
+NCU_CAPTURE = "profiles/r01_ncu_full_16M_v10.csv"   # ncu --set full, config 4, same kernels
+
+
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu
+    --set full capture (profiles/), or None."""
+    import csv
+    f = ROOT / NCU_CAPTURE
+    if not f.exists():
+        return None
+    rows = list(csv.reader(f.read_text().splitlines()))
+    hdr = rows[0]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = None
+    for r in rows[1:]:
+        if kernel in r[0]:
+            tot = 0.0
+            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                for i, h in enumerate(hdr):
+                    if h.startswith(name + " ["):
+                        tot += float(r[i]) * scale[h[h.index("[") + 1:-1]]
+    return tot
 
 
 def measured_peaks():
@@ -248,9 +275,11 @@ def run_ours(args):
     dom = max(("clear", "p2g 1", "p2g 2", "g2p"), key=lambda k: per_phase_ms[k])
     achieved = ALG_BYTES[dom] * sc.n / (per_phase_ms[dom] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "bound": "hbm", "kernel": f"{KERNEL_OF_PHASE[dom]} ({dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": ncu_traffic(KERNEL_OF_PHASE[dom]) if sc.n == (1 << 24) else None,
+        "traffic_source": NCU_CAPTURE, "peak_source": peak_src,
         "alg_bytes_per_particle": ALG_BYTES[dom], "ms_per_launch": per_phase_ms[dom],
+        "limiter": "shared-memory (LSU) pipe, not HBM: ncu l1tex data-pipe wavefronts 84% of peak, dram 27%",
         "step_frac": value * ALG_BYTES_STEP / 1e9 / peak,
         "per_phase_ms": per_phase_ms,
     }
@@ -392,8 +421,10 @@ def run_slabs(args, pkg, world, rank, local_rank):
     per_phase_ms = {k: prof[k] / nsub * 1e3 for k in ("sort", "clear", "p2g 1", "p2g 2", "update", "g2p")}
     dom = max(("clear", "p2g 1", "p2g 2", "g2p"), key=lambda k: per_phase_ms[k])
     achieved = ALG_BYTES[dom] * n_local / (per_phase_ms[dom] * 1e-3) / 1e9
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+    roofline = {"bound": "hbm", "kernel": f"{KERNEL_OF_PHASE[dom]} ({dom})", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(KERNEL_OF_PHASE[dom]),
+                "traffic_source": NCU_CAPTURE + " (single-GPU capture of the same kernel and per-GPU size)",
+                "peak_source": peak_src,
                 "alg_bytes_per_particle": ALG_BYTES[dom], "ms_per_launch": per_phase_ms[dom],
                 "step_frac": value * ALG_BYTES_STEP / 1e9 / (peak * world),
                 "per_phase_ms": per_phase_ms,
