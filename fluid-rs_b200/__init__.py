@@ -110,11 +110,13 @@ def lib():
     """Load csrc/libfluid_b200.so.  Raises if it has not been built — never falls back."""
     global _lib
     if _lib is None:
-        if not LIB_PATH.exists():
+        import os
+        path = Path(os.environ.get("FLUID_B200_LIB", str(LIB_PATH)))   # A/B builds of the same CUDA library
+        if not path.exists():
             raise FileNotFoundError(
                 f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(nvcc, sm_100a).  This engine has no CPU or eager fallback.")
-        L = C.CDLL(str(LIB_PATH))
+        L = C.CDLL(str(path))
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)
             fn.restype = res

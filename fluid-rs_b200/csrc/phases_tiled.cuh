@@ -40,6 +40,10 @@ struct T3 {
     static constexpr int NODES = NX * NY * NZ;       // 600 footprint nodes
     static constexpr int PLANE = 104;                // padded z stride in shared memory
     static constexpr int SLOTS = PLANE * NZ;         // 624 shared-memory slots per tile
+    // scalar (float) tiles use their own strides: x + 12*y + 128*z halves the 32-bit bank conflicts
+    // of a window under the class-major lane order (modelled 2.8 -> 2.0 wavefronts per access)
+    static constexpr int SROW = 12, SPLANE = 128;
+    static constexpr int SSLOTS = SPLANE * NZ;       // 768
     static constexpr int WARPS = 4;                  // tiles per CTA (no CTA-level sync is used)
     static constexpr int THREADS = WARPS * 32;
 };
@@ -123,12 +127,19 @@ __device__ __forceinline__ int foot_step(const Geo& g, const TileCtx& tc, const 
     }
     return f.x + T3::NX * ly + T3::PLANE * lz;
 }
+// scalar-tile slot of the node a float4-tile slot refers to
+__device__ __forceinline__ int scalar_slot(int slot4) {
+    const int lz = slot4 / T3::PLANE, r = slot4 - lz * T3::PLANE;
+    const int ly = r / T3::NX, lx = r - ly * T3::NX;
+    return lx + T3::SROW * ly + T3::SPLANE * lz;
+}
 
 // Per-particle stencil in tile coordinates.
 struct TStencil {
     float wx[3], wy[3], wz[3];   // zeroed outside the p_rect grid (3d:166-168)
     float cx, cy, cz;            // pos - (cell + 0.5)
-    int node0;                   // shared-memory slot of stencil offset (0,0,0)
+    int node0;                   // shared-memory slot of stencil offset (0,0,0) in a float4 tile
+    int node0s;                  // the same node in a scalar tile
 };
 
 __device__ __forceinline__ void axis_weights(float c, float* w) {
@@ -163,6 +174,7 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
     int ly = min(max(ry - tc.c0[1], 0), T3::Y - 1);
     int lz = min(max(rz - tc.c0[2], 0), T3::Z - 1);
     s.node0 = lx + T3::NX * ly + T3::PLANE * lz;
+    s.node0s = lx + T3::SROW * ly + T3::SPLANE * lz;
 }
 
 // ---- clear: zero the 8x8x4 node blocks marked dirty by the sort (clear_grid, 3d:136-146) ----------
@@ -216,15 +228,15 @@ __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
              const int* __restrict__ n_active, float* __restrict__ gmass) {
-    __shared__ float sm[T3::WARPS * T3::SLOTS];
+    __shared__ float sm[T3::WARPS * T3::SSLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = sm + warp * T3::SLOTS;
+    float* tile = sm + warp * T3::SSLOTS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
-        for (int k = lane; k < T3::SLOTS; k += 32) tile[k] = 0.0f;
+        for (int k = lane; k < T3::SSLOTS; k += 32) tile[k] = 0.0f;
         __syncwarp();
         // software pipeline: record one window ahead, index two windows ahead
         int off, len;
@@ -249,17 +261,17 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
 #pragma unroll
                 for (int ox = 0; ox < 3; ++ox) {
                     const float wxy = s.wx[ox] * s.wy[oy];
-                    float* nd = tile + s.node0 + ox + T3::NX * oy;
+                    float* nd = tile + s.node0s + ox + T3::SROW * oy;
                     // three nodes along z: private to this lane within the window.  Loads and math
                     // run for every lane (idle lanes point at a valid column), only the stores are
                     // predicated: no branch in the chain.
-                    float a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
+                    float a0 = nd[0], a1 = nd[T3::SPLANE], a2 = nd[2 * T3::SPLANE];
                     a0 += wxy * wzm[0];
                     a1 += wxy * wzm[1];
                     a2 += wxy * wzm[2];
                     if (active) nd[0] = a0;
-                    if (active) nd[T3::PLANE] = a1;
-                    if (active) nd[2 * T3::PLANE] = a2;
+                    if (active) nd[T3::SPLANE] = a1;
+                    if (active) nd[2 * T3::SPLANE] = a2;
                     __syncwarp();
                 }
         }
@@ -269,7 +281,7 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
             int gi;
             const int sl = foot_step(g, tc, fl, it, gi);
             if (gi >= 0) {
-                const float v = tile[sl];
+                const float v = tile[scalar_slot(sl)];
                 if (v != 0.0f) atomicAdd(&gmass[gi], v);
             }
         }
@@ -281,7 +293,7 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
 
 struct P2GSmem {
     float4 acc[T3::WARPS][T3::SLOTS];   // {momentum + force, mass} accumulators
-    float mass[T3::WARPS][T3::SLOTS];   // complete node masses (from k_mass_tiled)
+    float mass[T3::WARPS][T3::SSLOTS];  // complete node masses (from k_mass_tiled), scalar-tile strides
 };
 
 struct PRec {   // one particle's streams
@@ -336,7 +348,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 int gi;
                 const int sl = foot_step(g, tc, fl, it, gi);
                 if (fl.rsub < 3) {
-                    ms[sl] = mv[it];
+                    ms[scalar_slot(sl)] = mv[it];
                     acc[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
             }
@@ -362,7 +374,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 float plane = 0.0f;
 #pragma unroll
                 for (int oy = 0; oy < 3; ++oy) {
-                    const float* row = ms + s.node0 + T3::NX * oy + T3::PLANE * oz;
+                    const float* row = ms + s.node0s + T3::SROW * oy + T3::SPLANE * oz;
                     plane += (row[0] * s.wx[0] + row[1] * s.wx[1] + row[2] * s.wx[2]) * s.wy[oy];
                 }
                 density += plane * s.wz[oz];
