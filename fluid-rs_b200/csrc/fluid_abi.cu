@@ -88,7 +88,8 @@ struct fluid_sim {
     int* rank = nullptr;     // per particle: rank inside its bucket
     int* perm = nullptr;     // cell-sorted slot -> slot in the tile order
     int* src = nullptr;      // sorted slot -> storage index in buf[cur]
-    int* imm_list = nullptr; // particles that changed tile in the last g2p
+    int* imm_list = nullptr; // particles that changed tile in the last g2p (per-tile lists)
+    int* imm_cnt = nullptr;  // leavers per active-tile-list entry
     int4* tiles = nullptr;   // active tile list {tile, first slot, count, 0}, rebuilt by every sort
     int* scal = nullptr;     // device scalars: [0] active tiles, [1] immigrants
     int* cell_off = nullptr; // per bucket: first cell-sorted slot (cellStart)
@@ -334,6 +335,7 @@ SortTables sort_tables(fluid_sim* s) {
     t.count = s->count;
     t.tile_total = s->tile_total;
     t.imm_list = s->imm_list;
+    t.imm_cnt = s->imm_cnt;
     t.scal = s->scal;
     return t;
 }
@@ -390,7 +392,7 @@ fluid_status sort_cold(fluid_sim* s) {
 // steady state: g2p already counted the particles that stayed in their tile
 template <int DIM>
 fluid_status sort_steady(fluid_sim* s) {
-    k_immigrants<<<s->sm_count * 4, 256, 0, s->stream>>>(sort_tables(s));
+    k_immigrants<<<s->sm_count * 8, 256, 0, s->stream>>>(sort_tables(s), s->tiles, s->geo.n_tiles + N_PSEUDO);
     ++s->launches;
     return sort_finish<DIM>(s);
 }
@@ -744,6 +746,7 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->dirty[1]);
     cudaFree(s->cand);
     cudaFree(s->dirty_list);
+    cudaFree(s->imm_cnt);
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -855,7 +858,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     cudaFree(s->dirty[1]);
     cudaFree(s->cand);
     cudaFree(s->dirty_list);
-    s->cand = s->dirty_list = nullptr;
+    cudaFree(s->imm_cnt);
+    s->cand = s->dirty_list = s->imm_cnt = nullptr;
     s->dirty[0] = s->dirty[1] = nullptr;
     s->grid_clean = false;
     s->grid = nullptr;
@@ -871,6 +875,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
     CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + N_PSEUDO) * sizeof(int4)));
     CU_TRY(cudaMalloc(&s->cand, (n_pt + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->imm_cnt, (n_pt + 8) * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(s->imm_cnt, 0, (n_pt + 8) * sizeof(int), s->stream));
     CU_TRY(cudaMalloc(&s->dirty_list, (n_pt + 8) * sizeof(int)));
     for (int b = 0; b < 2; ++b) {
         CU_TRY(cudaMalloc(&s->dirty[b], g.n_tiles + 8));

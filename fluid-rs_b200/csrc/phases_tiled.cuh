@@ -236,6 +236,9 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
+        if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
+            continue;
+        }
         for (int k = lane; k < T3::SSLOTS; k += 32) tile[k] = 0.0f;
         __syncwarp();
         // software pipeline: record one window ahead, index two windows ahead
@@ -326,6 +329,9 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
+        if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
+            continue;
+        }
         int off, len;
         window_range(tc, 0, off, len);
         PRec nxt;
@@ -471,6 +477,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
+        if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
+            if (COUNT && lane == 0) st.imm_cnt[a] = 0;
+            continue;
+        }
         // q = state before this substep (storage order, read through src);
         // qn = state after it, written at the sorted slot.  g2p has no write conflicts, so it walks
         // the tile's slots 32 at a time regardless of the window structure.
@@ -478,6 +488,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
         if (lane < tc.count) p_next = __ldg(&q.P[i_cur]);
         int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
+        int n_leave = 0;
         if (COUNT) {
 #pragma unroll
             for (int j = 0; j < TILE_CELLS / 32; ++j) scnt[lane + 32 * j] = 0;
@@ -620,13 +631,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
                         }
                     }
                 }
+                // leavers are listed inside this tile's own slot range: no global counter
                 const unsigned lm = __ballot_sync(0xffffffffu, leaves);
-                if (lm) {
-                    int slot = 0;
-                    if (lane == 0) slot = atomicAdd(&st.scal[SCAL_N_IMM], __popc(lm));
-                    slot = __shfl_sync(0xffffffffu, slot, 0);
-                    if (leaves) st.imm_list[slot + __popc(lm & ((1u << lane) - 1u))] = d;
-                }
+                if (leaves) st.imm_list[tc.base + n_leave + __popc(lm & ((1u << lane) - 1u))] = d;
+                n_leave += __popc(lm);
             }
         }
         __syncwarp();
@@ -641,7 +649,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
                 total += c;
             }
             total = __reduce_add_sync(0xffffffffu, total);
-            if (lane == 0) st.tile_total[tc.tile] = total;
+            if (lane == 0) {
+                st.tile_total[tc.tile] = total;
+                st.imm_cnt[a] = n_leave;
+            }
         }
         __syncwarp();
     }

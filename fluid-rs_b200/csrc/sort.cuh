@@ -39,8 +39,9 @@ struct SortTables {
     int* rank;         // per particle: rank inside its bucket
     int* count;        // per bucket (n_cells_pad + 512)
     int* tile_total;   // per tile (+2 pseudo tiles)
-    int* imm_list;     // particles that changed tile in g2p
-    int* scal;         // [0] n_active tiles, [1] n_imm
+    int* imm_list;     // particles that changed tile in g2p: tile a's leavers sit at [first slot of a, +imm_cnt[a])
+    int* imm_cnt;      // per active-tile-list entry: number of leavers
+    int* scal;         // device scalars (SCAL_*)
 };
 
 constexpr int TILE_CELLS = 256;
@@ -107,21 +108,27 @@ k_classify_all(const __grid_constant__ Geo g, const float4* __restrict__ P, int 
     }
 }
 
-// Steady state: the particles g2p listed because they left their tile (or were dropped).
+// Steady state: the particles g2p listed because they left their tile (or were dropped).  g2p keeps
+// one list per tile inside the tile's own slot range (no global counter, no same-address atomics);
+// persistent warps walk the tile list of the sort that g2p ran on.
 __global__ void __launch_bounds__(256)
-k_immigrants(SortTables t) {
-    const int n_imm = t.scal[SCAL_N_IMM];
-    const int stride = gridDim.x * blockDim.x;
-    const int rounds = (n_imm + stride - 1) / stride;   // every lane takes part in the warp votes
-    for (int r = 0; r < rounds; ++r) {
-        const int j = r * stride + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool valid = j < n_imm;
-        int i = 0, bucket = 0;
-        if (valid) {
-            i = t.imm_list[j];
-            bucket = t.gcell[i];
+k_immigrants(SortTables t, const int4* __restrict__ tiles, int n_tiles_listed_max) {
+    const int n_list = min(t.scal[SCAL_N_ACTIVE], n_tiles_listed_max);
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_list; a += n_warps) {
+        const int n_imm = t.imm_cnt[a];
+        if (n_imm == 0) continue;
+        const int first = tiles[a].y;
+        for (int j0 = 0; j0 < n_imm; j0 += 32) {
+            const bool valid = j0 + lane < n_imm;
+            int i = 0, bucket = 0;
+            if (valid) {
+                i = t.imm_list[first + j0 + lane];
+                bucket = t.gcell[i];
+            }
+            count_global(t, i, bucket, valid);
         }
-        count_global(t, i, bucket, valid);
     }
 }
 
@@ -297,6 +304,7 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
     const int lane = threadIdx.x & 31;
     // persistent warps over the list of tiles that hold particles (k_scan_final)
     const int n_cand = scal[SCAL_N_CAND];
+    if (blockIdx.x == 0 && threadIdx.x == 0) scal[SCAL_N_ACTIVE] = n_cand;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_cand; a += n_warps) {
     const int t = cand[a];
@@ -307,6 +315,7 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         if (lane == 0) {
             cell_off[c_first] = base;
             count[c_first] = 0;
+            tiles[a] = make_int4(t, base, 0, 1);   // listed, but nothing for the tile kernels to do
         }
         for (int r = lane; r < n_t; r += 32) perm[base + r] = base + r;
         continue;
@@ -346,13 +355,13 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
         op[1] = make_int4(st[4], st[5], st[6], st[7]);
     }
     if (ORDER == ORDER_CELL) {
-        if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, (n_t + 31) / 32);
+        if (lane == 0) tiles[a] = make_int4(t, base, n_t, (n_t + 31) / 32);
         for (int r = 0; r < mine; ++r) perm[base + q_first + r] = base + q_first + r;
         continue;
     }
     const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
     const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
-    if (lane == 0) tiles[atomicAdd(&scal[SCAL_N_ACTIVE], 1)] = make_int4(t, base, n_t, w_count);
+    if (lane == 0) tiles[a] = make_int4(t, base, n_t, w_count);   // list slot = candidate index: no atomics
     const int per = n_t / w_count, extra = n_t - per * w_count;
 
     // class totals N_b (lanes 4b..4b+3 hold class b) and class starts S_b
