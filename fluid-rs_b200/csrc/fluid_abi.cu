@@ -99,6 +99,8 @@ struct fluid_sim {
     int* dirty_list = nullptr;   // node blocks to clear this substep
     unsigned char* dirty[2] = {nullptr, nullptr};   // node blocks touched by the current / previous sort
     int dirty_cur = 0;
+    int* gz = nullptr;           // per tile: substep number in which k_g2p_tiled zeroed its node-mass block
+    int epoch = 0;               // tiled substeps run so far (compared with gz)
     bool grid_clean = false;     // every node outside the dirty blocks is zero
     bool sorted_valid = false;   // arrays are in tile order for the current positions
     bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
@@ -465,12 +467,13 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                     s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY);
                 k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                                   static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-                    s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass);
+                    s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, true);
                 s->launches += 2;
             }
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
+            ++s->epoch;
             k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                  s->gmass);
+                                                                                  s->gmass, s->grid);
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
@@ -506,7 +509,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             sb.rec[1] = s->mig_rec[1];
             sb.cap = s->mig_cap;
             k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb);
+                s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch);
             // ignored (and, outside slab runs, dropped) particles sit behind the tiles: carried over
             // and counted here; a slab run ends dropped / migrated particles at this point
             const int* n_end = s->geo.slab_on ? s->tile_base + s->geo.n_tiles + 1 : nullptr;
@@ -747,6 +750,7 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->cand);
     cudaFree(s->dirty_list);
     cudaFree(s->imm_cnt);
+    cudaFree(s->gz);
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -859,7 +863,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     cudaFree(s->cand);
     cudaFree(s->dirty_list);
     cudaFree(s->imm_cnt);
-    s->cand = s->dirty_list = s->imm_cnt = nullptr;
+    cudaFree(s->gz);
+    s->cand = s->dirty_list = s->imm_cnt = s->gz = nullptr;
     s->dirty[0] = s->dirty[1] = nullptr;
     s->grid_clean = false;
     s->grid = nullptr;
@@ -878,6 +883,9 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaMalloc(&s->imm_cnt, (n_pt + 8) * sizeof(int)));
     CU_TRY(cudaMemsetAsync(s->imm_cnt, 0, (n_pt + 8) * sizeof(int), s->stream));
     CU_TRY(cudaMalloc(&s->dirty_list, (n_pt + 8) * sizeof(int)));
+    CU_TRY(cudaMalloc(&s->gz, (n_pt + 8) * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(s->gz, 0, (n_pt + 8) * sizeof(int), s->stream));
+    s->epoch = 0;
     for (int b = 0; b < 2; ++b) {
         CU_TRY(cudaMalloc(&s->dirty[b], g.n_tiles + 8));
         CU_TRY(cudaMemsetAsync(s->dirty[b], 0, g.n_tiles + 8, s->stream));
@@ -1319,7 +1327,8 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
                 s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY);
             k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                               static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-                s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass);
+                s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, 0, false);
+            ++s->epoch;   // no g2p ran: no stamp of an earlier substep may match the next clear
             s->dirty_cur ^= 1;
         }
         return FLUID_OK;

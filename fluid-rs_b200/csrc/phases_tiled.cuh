@@ -198,14 +198,21 @@ k_dirty_list(const __grid_constant__ Geo g, const unsigned char* __restrict__ di
     if (d) list[slot + __popc(m & ((1u << lane) - 1u))] = t;
 }
 
+// The tile kernels zero the blocks of the tiles they own on the way (k_mass_tiled: the node records of
+// the tiles active in this sort; k_g2p_tiled: the node masses of the tiles active in the previous one,
+// stamped in `gz`), so this kernel is left with the rim: dirty blocks whose own tile holds no particles.
 __global__ void __launch_bounds__(128)
 k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const int* __restrict__ n_list,
-              float4* __restrict__ grid, float* __restrict__ gmass) {
+              float4* __restrict__ grid, float* __restrict__ gmass, const int* __restrict__ tile_base,
+              const int* __restrict__ gz, int epoch_prev, bool fused) {
     const int lane = threadIdx.x & 31;
     const int n = *n_list;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n; a += n_warps) {
         const int t = list[a];
+        const bool do_grid = !fused || tile_base[t + 1] == tile_base[t];   // else k_mass_tiled zeroes it
+        const bool do_mass = !fused || gz[t] != epoch_prev;                // else k_g2p_tiled did
+        if (!do_grid && !do_mass) continue;
         const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
         // 256 nodes: lane -> x = lane & 7, y = (lane >> 3) + 4*(j & 1), z = j >> 1
 #pragma unroll
@@ -215,10 +222,22 @@ k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const
             const int z = tz * T3::Z + (j >> 1);
             if (x < g.size[0] && y < g.size[1] && z < g.size[2]) {
                 const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
-                grid[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
-                gmass[gi] = 0.0f;
+                if (do_grid) grid[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (do_mass) gmass[gi] = 0.0f;
             }
         }
+    }
+}
+
+// Zero the tile's own 8x8x4 node block of `arr` (the nodes with the tile's cell indices).
+template <typename T>
+__device__ __forceinline__ void zero_own_block(const Geo& g, const TileCtx& tc, int lane, T* __restrict__ arr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int x = tc.c0[0] + (lane & 7);
+        const int y = tc.c0[1] + (lane >> 3) + 4 * (j & 1);
+        const int z = tc.c0[2] + (j >> 1);
+        if (x < g.size[0] && y < g.size[1] && z < g.size[2]) arr[g.guard + x + (y + z * g.size[1]) * g.size[0]] = T{};
     }
 }
 
@@ -227,7 +246,7 @@ k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const
 __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
-             const int* __restrict__ n_active, float* __restrict__ gmass) {
+             const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid) {
     __shared__ float sm[T3::WARPS * T3::SSLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = sm + warp * T3::SSLOTS;
@@ -241,6 +260,9 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
         }
         for (int k = lane; k < T3::SSLOTS; k += 32) tile[k] = 0.0f;
         __syncwarp();
+        // clear_grid for the node records of this tile's own block (nothing touches `grid` in this
+        // kernel; "p2g 2" deposits into it next)
+        zero_own_block(g, tc, lane, grid);
         // software pipeline: record one window ahead, index two windows ahead
         int off, len;
         window_range(tc, 0, off, len);
@@ -466,7 +488,8 @@ template <bool COUNT>
 __global__ void __launch_bounds__(T3::THREADS, 4)
 k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
-            const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb) {
+            const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb,
+            float* __restrict__ gmass, int* __restrict__ gz, int epoch) {
     __shared__ float4 sm[T3::WARPS * T3::SLOTS];
     __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -493,6 +516,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
 #pragma unroll
             for (int j = 0; j < TILE_CELLS / 32; ++j) scnt[lane + 32 * j] = 0;
         }
+        // clear_grid for the node masses of this tile's own block, one substep ahead: nothing reads
+        // `gmass` between "p2g 2" and the next "p2g 1"; the stamp tells k_clear_tiles to skip the block
+        zero_own_block(g, tc, lane, gmass);
+        if (lane == 0) gz[tc.tile] = epoch;
         // node records of the footprint: cp.async (LDGSTS) straight into shared memory, all 19 per
         // lane in flight, zero-filled outside the p_rect grid; then update_grid in place
         const FootLane fl = foot_lane(lane);

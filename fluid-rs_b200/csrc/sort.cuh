@@ -16,9 +16,10 @@
 //            - cold start (after add_particles / set_rect, and the generic path): k_classify_all
 //              does it for every particle with global atomics;
 //   scan     exclusive scan over the TILE totals only (hand-written three-kernel scan, no CUB);
-//   perm     one warp per tile: cell offsets inside the tile (cellStart), the slot of every
-//            (cell, rank) in the chosen order, the active-tile list; resets count[] for reuse;
-//   reorder  all SoA streams move to the other buffer.
+//   tables   one warp per tile: cell offsets inside the tile (cellStart), the window tables of the
+//            chosen order, the active-tile list; resets count[] for reuse;
+//   src      one thread per particle: its slot in closed form from those tables -> src[slot];
+//   reorder  none: the tile kernels gather through src[] and g2p writes at the sorted slots.
 #pragma once
 
 #include "common.cuh"
@@ -294,123 +295,106 @@ __device__ __forceinline__ int small_div(int x, float inv_w) {
 
 constexpr int PERM_WARPS = 4;
 constexpr int PERM_MAX_W = 32;   // windows per tile covered by the in-window merge table
+constexpr int TAB_BYTES = PERM_MAX_W * 8;   // per listed tile: members of class b in window w, one byte each
 
+// What k_build_src needs to place a particle of a tile: {W (0 = plain cell order), tile-list entry}
+// W < 0: |W| windows but no class merge (more than PERM_MAX_W windows or >= 8192 particles).
+
+// One warp per tile that holds particles: cellStart of its 256 cells, the number of windows W, the
+// class-in-window table, the active-tile list entry and the dirty marks of the node blocks the tile's
+// particles can reach; count[] is reset for the next round.  The per-particle slots are computed by
+// k_build_src from these tables (closed form), so no per-slot permutation is stored.
 template <int ORDER>
 __global__ void __launch_bounds__(PERM_WARPS * 32)
-k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* __restrict__ tile_base,
-            int* __restrict__ cell_off, int* __restrict__ perm, int4* __restrict__ tiles,
-            int* __restrict__ scal, unsigned char* __restrict__ dirty, const int* __restrict__ cand) {
-    __shared__ __align__(16) int tab_all[PERM_WARPS][PERM_MAX_W * 8];
+k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int* __restrict__ tile_base,
+              int* __restrict__ cell_off, int2* __restrict__ tile_info, unsigned char* __restrict__ tab,
+              int4* __restrict__ tiles, int* __restrict__ scal, unsigned char* __restrict__ dirty,
+              const int* __restrict__ cand) {
     const int lane = threadIdx.x & 31;
     // persistent warps over the list of tiles that hold particles (k_scan_final)
     const int n_cand = scal[SCAL_N_CAND];
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[SCAL_N_ACTIVE] = n_cand;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_cand; a += n_warps) {
-    const int t = cand[a];
-    const int base = tile_base[t];
-    const int n_t = tile_base[t + 1] - base;
-    const int c_first = t * TILE_CELLS;
-    if (t >= g.n_tiles) {   // pseudo tiles: a single bucket, slots stay in rank order
+        const int t = cand[a];
+        const int base = tile_base[t];
+        const int n_t = tile_base[t + 1] - base;
+        const int c_first = t * TILE_CELLS;
+        if (t >= g.n_tiles) {   // pseudo tiles: a single bucket, slots stay in rank order
+            if (lane == 0) {
+                cell_off[c_first] = base;
+                count[c_first] = 0;
+                tiles[a] = make_int4(t, base, 0, 1);   // listed, but nothing for the tile kernels to do
+                tile_info[t] = make_int2(0, a);
+            }
+            continue;
+        }
+        if (dirty && lane < 27) {
+            // the particles of this tile deposit into the node blocks of its 3x3x3 tile neighbourhood:
+            // mark them for k_clear_tiles (clear_grid, 3d:136-146, only where something was written)
+            const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
+            const int nx = tx + lane % 3 - 1, ny = ty + (lane / 3) % 3 - 1, nz = tz + lane / 9 - 1;
+            if (nx >= 0 && ny >= 0 && nz >= 0 && nx < g.tdim[0] && ny < g.tdim[1] && nz < g.tdim[2])
+                dirty[(nz * g.tdim[1] + ny) * g.tdim[0] + nx] = 1;
+        }
+        // lane owns 8 consecutive cells (3D: two (x,y) columns of one bank class, 4 cells each)
+        int cnt[8];
+        {
+            int4* cp = reinterpret_cast<int4*>(count + c_first + lane * 8);
+            int4 a4 = cp[0], b4 = cp[1];
+            cnt[0] = a4.x; cnt[1] = a4.y; cnt[2] = a4.z; cnt[3] = a4.w;
+            cnt[4] = b4.x; cnt[5] = b4.y; cnt[6] = b4.z; cnt[7] = b4.w;
+            cp[0] = make_int4(0, 0, 0, 0);      // count[] is all zero again outside a sort
+            cp[1] = make_int4(0, 0, 0, 0);
+        }
+        int mine = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mine += cnt[j];
+        const int q_first = warp_inclusive_scan(mine) - mine;   // cell-sorted offset of my first cell
+        {
+            int ex = base + q_first;
+            int st[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                st[j] = ex;
+                ex += cnt[j];
+            }
+            int4* op = reinterpret_cast<int4*>(cell_off + c_first + lane * 8);   // cellStart
+            op[0] = make_int4(st[0], st[1], st[2], st[3]);
+            op[1] = make_int4(st[4], st[5], st[6], st[7]);
+        }
+        if (ORDER == ORDER_CELL) {
+            if (lane == 0) {
+                tiles[a] = make_int4(t, base, n_t, (n_t + 31) / 32);
+                tile_info[t] = make_int2(0, a);
+            }
+            continue;
+        }
+        const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
+        const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
+        const bool merge = w_count <= PERM_MAX_W && n_t < 8192;
         if (lane == 0) {
-            cell_off[c_first] = base;
-            count[c_first] = 0;
-            tiles[a] = make_int4(t, base, 0, 1);   // listed, but nothing for the tile kernels to do
+            tiles[a] = make_int4(t, base, n_t, w_count);   // list slot = candidate index: no atomics
+            tile_info[t] = make_int2(merge ? w_count : -w_count, a);
         }
-        for (int r = lane; r < n_t; r += 32) perm[base + r] = base + r;
-        continue;
-    }
-    if (dirty && lane < 27) {
-        // the particles of this tile deposit into the node blocks of its 3x3x3 tile neighbourhood:
-        // mark them for k_clear_tiles (clear_grid, 3d:136-146, only where something was written)
-        const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
-        const int nx = tx + lane % 3 - 1, ny = ty + (lane / 3) % 3 - 1, nz = tz + lane / 9 - 1;
-        if (nx >= 0 && ny >= 0 && nz >= 0 && nx < g.tdim[0] && ny < g.tdim[1] && nz < g.tdim[2])
-            dirty[(nz * g.tdim[1] + ny) * g.tdim[0] + nx] = 1;
-    }
-    // lane owns 8 consecutive cells (3D: two (x,y) columns of one bank class, 4 cells each)
-    int cnt[8];
-    {
-        int4* cp = reinterpret_cast<int4*>(count + c_first + lane * 8);
-        int4 a = cp[0], b = cp[1];
-        cnt[0] = a.x; cnt[1] = a.y; cnt[2] = a.z; cnt[3] = a.w;
-        cnt[4] = b.x; cnt[5] = b.y; cnt[6] = b.z; cnt[7] = b.w;
-        cp[0] = make_int4(0, 0, 0, 0);      // count[] is all zero again outside a sort
-        cp[1] = make_int4(0, 0, 0, 0);
-    }
-    int mine = 0;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) mine += cnt[j];
-    const int q_first = warp_inclusive_scan(mine) - mine;   // cell-sorted offset of my first cell
-    {
-        int ex = base + q_first;
-        int st[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            st[j] = ex;
-            ex += cnt[j];
-        }
-        int4* op = reinterpret_cast<int4*>(cell_off + c_first + lane * 8);   // cellStart
-        op[0] = make_int4(st[0], st[1], st[2], st[3]);
-        op[1] = make_int4(st[4], st[5], st[6], st[7]);
-    }
-    if (ORDER == ORDER_CELL) {
-        if (lane == 0) tiles[a] = make_int4(t, base, n_t, (n_t + 31) / 32);
-        for (int r = 0; r < mine; ++r) perm[base + q_first + r] = base + q_first + r;
-        continue;
-    }
-    const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
-    const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
-    if (lane == 0) tiles[a] = make_int4(t, base, n_t, w_count);   // list slot = candidate index: no atomics
-    const int per = n_t / w_count, extra = n_t - per * w_count;
-
-    // class totals N_b (lanes 4b..4b+3 hold class b) and class starts S_b
-    int n_cls = mine;
-    n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 1);
-    n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 2);
-    const int s_cls = __shfl_sync(0xffffffffu, q_first, lane & ~3);   // start of my class
-    int* tab = tab_all[(threadIdx.x >> 5)];
-    const bool merge = w_count <= PERM_MAX_W && n_t < 8192;
-    const float inv_w = 1.0f / static_cast<float>(w_count);
-    if (merge) {
+        if (!merge) continue;
+        // class totals N_b (lanes 4b..4b+3 hold class b) and class starts S_b
+        int n_cls = mine;
+        n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 1);
+        n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 2);
+        const int s_cls = __shfl_sync(0xffffffffu, q_first, lane & ~3);   // start of my class
+        const float inv_w = 1.0f / static_cast<float>(w_count);
         // tab[w*8 + b] = members of class b in window w: those q in [S_b, S_b + N_b) with q = w (mod W)
         const int b = lane & 7;
         const int nb = __shfl_sync(0xffffffffu, n_cls, 4 * b);
         const int sb = __shfl_sync(0xffffffffu, s_cls, 4 * b);
         const int sb_mod = sb - small_div(sb, inv_w) * w_count;
+        unsigned char* my_tab = tab + static_cast<size_t>(a) * TAB_BYTES;
         for (int w = lane >> 3; w < w_count; w += 4) {
             int off = w - sb_mod;
             if (off < 0) off += w_count;
-            tab[w * 8 + b] = off < nb ? small_div(nb - off + w_count - 1, inv_w) : 0;
+            my_tab[w * 8 + b] = static_cast<unsigned char>(off < nb ? small_div(nb - off + w_count - 1, inv_w) : 0);
         }
-    }
-    __syncwarp();
-    const int my_cls = lane >> 2;
-    const int s_mod = merge ? s_cls - small_div(s_cls, inv_w) * w_count : 0;
-    int w = merge ? q_first - small_div(q_first, inv_w) * w_count : q_first % w_count;
-    for (int r = 0; r < mine; ++r) {
-        const int q = q_first + r;              // position in the class-major sequence
-        int pos;
-        if (merge) {
-            int off = w - s_mod;
-            if (off < 0) off += w_count;
-            const int k = small_div(q - (s_cls + off), inv_w);   // my index among my class in window w
-            const int4 ta = *reinterpret_cast<const int4*>(tab + w * 8);
-            const int4 tb = *reinterpret_cast<const int4*>(tab + w * 8 + 4);
-            const int n[8] = {ta.x, ta.y, ta.z, ta.w, tb.x, tb.y, tb.z, tb.w};
-            pos = 0;
-#pragma unroll
-            for (int b2 = 0; b2 < 8; ++b2) {
-                pos += min(n[b2], k);
-                if (b2 < my_cls && n[b2] > k) ++pos;
-            }
-        } else {
-            pos = q / w_count;
-        }
-        perm[base + q] = base + w * per + min(w, extra) + pos;
-        if (++w == w_count) w = 0;
-    }
-    __syncwarp();   // tab is reused by the next tile
     }
 }
 
@@ -418,12 +402,57 @@ k_tile_perm(const __grid_constant__ Geo g, int* __restrict__ count, const int* _
 // the tile kernels gather through src[], and g2p writes the advanced particles straight into
 // their sorted slots of the other buffer, so storage order is always last substep's sorted
 // order and the gathers stay nearly coalesced.
+//
+// Slot of a particle with (bucket, rank): q = cellStart[bucket] - first slot of the tile + rank is its
+// position in the tile's class-major cell order; window w = q mod W; inside the window the classes are
+// merged round robin (ORDER_CLASS_RR above): with k = my index among my class's members of the window,
+//     pos = sum_b min(n_b, k) + #{b < my class : n_b > k},   n_b = tab[w][b].
 __global__ void __launch_bounds__(256)
 k_build_src(int n, const int* __restrict__ gcell, const int* __restrict__ rank,
-            const int* __restrict__ cell_off, const int* __restrict__ perm, int* __restrict__ src) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+            const int* __restrict__ cell_off, const int* __restrict__ tile_base,
+            const int2* __restrict__ tile_info, const unsigned char* __restrict__ tab, int* __restrict__ src) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    src[perm[cell_off[gcell[i]] + rank[i]]] = i;
+    const int bucket = gcell[i];
+    const int t = bucket >> 8;
+    const int q_abs = cell_off[bucket] + rank[i];
+    const int2 info = __ldg(&tile_info[t]);
+    if (info.x == 0) {   // plain cell order (2D, pseudo tiles)
+        src[q_abs] = i;
+        return;
+    }
+    const int base = __ldg(&tile_base[t]);
+    const int n_t = __ldg(&tile_base[t + 1]) - base;
+    const int q = q_abs - base;
+    int slot;
+    if (info.x < 0) {    // too many windows for the merge table: round robin only
+        const int w_count = -info.x;
+        const int per = n_t / w_count, extra = n_t - per * w_count;
+        const int pos = q / w_count, w = q - pos * w_count;
+        slot = base + w * per + min(w, extra) + pos;
+    } else {
+        const int w_count = info.x;
+        const float inv_w = 1.0f / static_cast<float>(w_count);
+        const int per = small_div(n_t, inv_w), extra = n_t - per * w_count;
+        const int w = q - small_div(q, inv_w) * w_count;
+        const int cls = (bucket & (TILE_CELLS - 1)) >> 5;
+        const int s_cls = __ldg(&cell_off[(t << 8) + (cls << 5)]) - base;
+        const int s_mod = s_cls - small_div(s_cls, inv_w) * w_count;
+        int off = w - s_mod;
+        if (off < 0) off += w_count;
+        const int k = small_div(q - (s_cls + off), inv_w);   // my index among my class in window w
+        const uint2 row = __ldg(reinterpret_cast<const uint2*>(tab + static_cast<size_t>(info.y) * TAB_BYTES + w * 8));
+        const unsigned kk = static_cast<unsigned>(min(k, 255)) * 0x01010101u;
+        // sum_b min(n_b, k): per-byte minimum, then the byte sum
+        int pos = __vsadu4(__vminu4(row.x, kk), 0u) + __vsadu4(__vminu4(row.y, kk), 0u);
+        // #{b < cls : n_b > k}
+        const unsigned gx = __vcmpgtu4(row.x, kk), gy = __vcmpgtu4(row.y, kk);   // 0xff per byte where n_b > k
+        const unsigned long long gt = (static_cast<unsigned long long>(gy) << 32) | gx;
+        const unsigned long long below = cls == 0 ? 0ull : (~0ull >> (64 - 8 * cls));
+        pos += __popcll(gt & below) >> 3;
+        slot = base + w * per + min(w, extra) + pos;
+    }
+    src[slot] = i;
 }
 
 // Physical gather (only used to compact dropped particles away and for the steady-state tail).
