@@ -86,7 +86,6 @@ struct fluid_sim {
     // neighbour search (sort.cuh)
     int* gcell = nullptr;    // per particle: bucket (tile * 256 + cell in tile)
     int* rank = nullptr;     // per particle: rank inside its bucket
-    int* perm = nullptr;     // cell-sorted slot -> slot in the tile order
     int* src = nullptr;      // sorted slot -> storage index in buf[cur]
     int* imm_list = nullptr; // particles that changed tile in the last g2p (per-tile lists)
     int* imm_cnt = nullptr;  // leavers per active-tile-list entry
@@ -99,6 +98,8 @@ struct fluid_sim {
     int* dirty_list = nullptr;   // node blocks to clear this substep
     unsigned char* dirty[2] = {nullptr, nullptr};   // node blocks touched by the current / previous sort
     int dirty_cur = 0;
+    int2* tile_info = nullptr;   // per tile: {windows W (0 = plain cell order, < 0 = no class merge), tile-list entry}
+    unsigned char* tab = nullptr;   // per tile-list entry: TAB_BYTES of class-in-window counts (k_tile_tables)
     int* gz = nullptr;           // per tile: substep number in which k_g2p_tiled zeroed its node-mass block
     int epoch = 0;               // tiled substeps run so far (compared with gz)
     bool grid_clean = false;     // every node outside the dirty blocks is zero
@@ -187,17 +188,15 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->gcell);
     cudaFree(s->rank);
-    cudaFree(s->perm);
     cudaFree(s->imm_list);
     cudaFree(s->src);
-    s->gcell = s->rank = s->perm = s->imm_list = s->src = nullptr;
+    s->gcell = s->rank = s->imm_list = s->src = nullptr;
     s->sorted_valid = s->counts_pending = false;
     s->buf[0] = nb[0];
     s->buf[1] = nb[1];
     s->cur = 0;
     CU_TRY(cudaMalloc(&s->gcell, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->rank, cap * sizeof(int)));
-    CU_TRY(cudaMalloc(&s->perm, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->imm_list, cap * sizeof(int)));
     CU_TRY(cudaMalloc(&s->src, cap * sizeof(int)));
     s->cap = cap;
@@ -358,15 +357,15 @@ fluid_status sort_finish(fluid_sim* s) {
                                            static_cast<unsigned>(s->sm_count * 16));
     if (DIM == 3) {
         s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
-        k_tile_perm<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal,
-                                                                          s->dirty[s->dirty_cur], s->cand);
+        k_tile_tables<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
+                                                                            s->tiles, s->scal, s->dirty[s->dirty_cur], s->cand);
     } else {
-        k_tile_perm<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->perm, s->tiles, s->scal,
-                                                                      nullptr, s->cand);
+        k_tile_tables<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
+                                                                        s->tiles, s->scal, nullptr, s->cand);
     }
     s->launches += 4;
     if (n > 0) {
-        k_build_src<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->gcell, s->rank, s->cell_off, s->perm, s->src);
+        k_build_src<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->gcell, s->rank, s->cell_off, s->tile_base, s->tile_info, s->tab, s->src);
         ++s->launches;
     }
     CU_TRY(cudaGetLastError());
@@ -734,7 +733,6 @@ fluid_status fluid_destroy(fluid_sim* s) {
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->gcell);
     cudaFree(s->rank);
-    cudaFree(s->perm);
     cudaFree(s->imm_list);
     cudaFree(s->src);
     cudaFree(s->gmass);
@@ -751,6 +749,8 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->dirty_list);
     cudaFree(s->imm_cnt);
     cudaFree(s->gz);
+    cudaFree(s->tile_info);
+    cudaFree(s->tab);
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -864,7 +864,11 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     cudaFree(s->dirty_list);
     cudaFree(s->imm_cnt);
     cudaFree(s->gz);
+    cudaFree(s->tile_info);
+    cudaFree(s->tab);
     s->cand = s->dirty_list = s->imm_cnt = s->gz = nullptr;
+    s->tile_info = nullptr;
+    s->tab = nullptr;
     s->dirty[0] = s->dirty[1] = nullptr;
     s->grid_clean = false;
     s->grid = nullptr;
@@ -886,6 +890,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaMalloc(&s->gz, (n_pt + 8) * sizeof(int)));
     CU_TRY(cudaMemsetAsync(s->gz, 0, (n_pt + 8) * sizeof(int), s->stream));
     s->epoch = 0;
+    CU_TRY(cudaMalloc(&s->tile_info, (n_pt + 8) * sizeof(int2)));
+    CU_TRY(cudaMalloc(&s->tab, (n_pt + 8) * TAB_BYTES));
     for (int b = 0; b < 2; ++b) {
         CU_TRY(cudaMalloc(&s->dirty[b], g.n_tiles + 8));
         CU_TRY(cudaMemsetAsync(s->dirty[b], 0, g.n_tiles + 8, s->stream));
