@@ -315,10 +315,34 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
     const int n_cand = scal[SCAL_N_CAND];
     if (blockIdx.x == 0 && threadIdx.x == 0) scal[SCAL_N_ACTIVE] = n_cand;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
-    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n_cand; a += n_warps) {
-        const int t = cand[a];
-        const int base = tile_base[t];
-        const int n_t = tile_base[t + 1] - base;
+    // Software pipeline over this warp's tiles: the three dependent loads (list entry -> tile_base ->
+    // counts) of the next tile are in flight while the current one is processed.
+    const int a0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int t_nx = a0 < n_cand ? cand[a0] : 0;
+    int t_nn = a0 + n_warps < n_cand ? cand[a0 + n_warps] : 0;
+    int base_nx = 0, end_nx = 0;
+    int4 ca_nx = make_int4(0, 0, 0, 0), cb_nx = ca_nx;
+    if (a0 < n_cand) {
+        base_nx = tile_base[t_nx];
+        end_nx = tile_base[t_nx + 1];
+        const int4* cp = reinterpret_cast<const int4*>(count + t_nx * TILE_CELLS + lane * 8);
+        ca_nx = cp[0];
+        cb_nx = cp[1];
+    }
+    for (int a = a0; a < n_cand; a += n_warps) {
+        const int t = t_nx;
+        const int base = base_nx;
+        const int n_t = end_nx - base_nx;
+        const int4 a4 = ca_nx, b4 = cb_nx;
+        t_nx = t_nn;
+        if (a + n_warps < n_cand) {
+            base_nx = tile_base[t_nx];
+            end_nx = tile_base[t_nx + 1];
+            const int4* cp = reinterpret_cast<const int4*>(count + t_nx * TILE_CELLS + lane * 8);
+            ca_nx = cp[0];
+            cb_nx = cp[1];
+        }
+        if (a + 2 * n_warps < n_cand) t_nn = cand[a + 2 * n_warps];
         const int c_first = t * TILE_CELLS;
         if (t >= g.n_tiles) {   // pseudo tiles: a single bucket, slots stay in rank order
             if (lane == 0) {
@@ -341,7 +365,6 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
         int cnt[8];
         {
             int4* cp = reinterpret_cast<int4*>(count + c_first + lane * 8);
-            int4 a4 = cp[0], b4 = cp[1];
             cnt[0] = a4.x; cnt[1] = a4.y; cnt[2] = a4.z; cnt[3] = a4.w;
             cnt[4] = b4.x; cnt[5] = b4.y; cnt[6] = b4.z; cnt[7] = b4.w;
             cp[0] = make_int4(0, 0, 0, 0);      // count[] is all zero again outside a sort

@@ -1,0 +1,21 @@
+"""Top stall lines of one kernel from an ncu report's source page (run where ncu is installed).
+usage: python tools/ncu_hot.py report.ncu-rep kernel_regex [min_percent]"""
+import csv, subprocess, sys, io
+rep, kern = sys.argv[1], sys.argv[2]
+thr = float(sys.argv[3]) if len(sys.argv) > 3 else 1.5
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kern],
+                     capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(out)))
+hi = [k for k, r in enumerate(rows) if r and r[0] == "Address"]
+start = hi[0]
+end = hi[1] - 1 if len(hi) > 1 else len(rows)     # first launch only
+h = rows[start]
+c = h.index("Warp Stall Sampling (All Samples)")
+e = h.index("Instructions Executed")
+body = [r for r in rows[start + 1:end] if len(r) > c and r[0].startswith("0x")]
+tot = sum(float(r[c] or 0) for r in body)
+print("instructions", len(body), "samples", tot)
+for k, r in enumerate(body):
+    f = float(r[c] or 0)
+    if f / tot * 100 >= thr:
+        print(f"{k:5d} {f / tot * 100:5.1f}%  exec {r[e]:>9}  {r[1].strip()[:100]}")
