@@ -287,10 +287,9 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                 for (int ox = 0; ox < 3; ++ox) {
                     const float wxy = s.wx[ox] * s.wy[oy];
                     float* nd = tile + s.node0s + ox + T3::SROW * oy;
-                    // three nodes along z: private to this lane within the window.  Loads and math
-                    // run for every lane (idle lanes point at a valid column), only the stores are
-                    // predicated: no branch in the chain.
-                    float a0 = nd[0], a1 = nd[T3::SPLANE], a2 = nd[2 * T3::SPLANE];
+                    // three nodes along z: private to this lane within the window.  Loads and stores
+                    // are predicated (an idle lane's stale address would only add bank conflicts).
+                    float a0 = active ? nd[0] : 0.0f, a1 = active ? nd[T3::SPLANE] : 0.0f, a2 = active ? nd[2 * T3::SPLANE] : 0.0f;
                     a0 += wxy * wzm[0];
                     a1 += wxy * wzm[1];
                     a2 += wxy * wzm[2];
@@ -445,9 +444,10 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                     const float G0 = wxy * M[6], G1 = wxy * M[7], G2 = wxy * M[8];
                     const float mw = wxy * m;
                     float4* nd = acc + s.node0 + ox + T3::NX * oy;
-                    // three nodes along z: private to this lane within the window; loads and math are
-                    // unconditional (idle lanes point at a valid column), only the stores are predicated
-                    float4 a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
+                    // three nodes along z: private to this lane within the window; loads and stores are
+                    // predicated (an idle lane's stale address would only add bank conflicts), the math is not
+                    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float4 a0 = active ? nd[0] : zero4, a1 = active ? nd[T3::PLANE] : zero4, a2 = active ? nd[2 * T3::PLANE] : zero4;
                     a0.x += s.wz[0] * A0;  a0.y += s.wz[0] * A1;  a0.z += s.wz[0] * A2;  a0.w += s.wz[0] * mw;
                     a1.x += s.wz[1] * A0 + q1 * G0;  a1.y += s.wz[1] * A1 + q1 * G1;
                     a1.z += s.wz[1] * A2 + q1 * G2;  a1.w += s.wz[1] * mw;
@@ -509,7 +509,11 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         // the tile's slots 32 at a time regardless of the window structure.
         int i_cur = lane < tc.count ? __ldg(&src[tc.base + lane]) : 0;
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < tc.count) p_next = __ldg(&q.P[i_cur]);
+        float id_next = 0.0f;            // the particle id travels in V.w: fetched with the position, a window ahead
+        if (lane < tc.count) {
+            p_next = __ldg(&q.P[i_cur]);
+            id_next = __ldg(&q.V[i_cur].w);
+        }
         int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
         int n_leave = 0;
         if (COUNT) {
@@ -558,8 +562,12 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             const int d = tc.base + it + lane;   // sorted slot = index in the new buffer
             const int i = i_cur;                 // storage index in the old buffer
             const float4 p = p_next;
+            const float idw = id_next;
             i_cur = i_next;
-            if (it + 32 + lane < tc.count) p_next = __ldg(&q.P[i_next]);   // prefetch the next window
+            if (it + 32 + lane < tc.count) {   // prefetch the next window
+                p_next = __ldg(&q.P[i_next]);
+                id_next = __ldg(&q.V[i_next].w);
+            }
             if (it + 64 + lane < tc.count) i_next = __ldg(&src[d + 64]);
             float pos[3] = {p.x, p.y, p.z};
             const bool advance = active && classify_pos<3>(g, pos) == CLS_ACTIVE;   // g2p walks a_rect blocks only
@@ -608,7 +616,6 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
                 }
                 integrate_particle<3>(g, pos, vel, mouse);
                 if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
-                const float idw = __ldg(&q.V[i].w);
                 qn.P[d] = make_float4(pos[0], pos[1], pos[2], p.w);
                 qn.V[d] = make_float4(vel[0], vel[1], vel[2], idw);
                 qn.CA[d] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);

@@ -15,7 +15,10 @@ e = h.index("Instructions Executed")
 body = [r for r in rows[start + 1:end] if len(r) > c and r[0].startswith("0x")]
 tot = sum(float(r[c] or 0) for r in body)
 print("instructions", len(body), "samples", tot)
+stall_cols = [(i, x) for i, x in enumerate(h) if x.startswith("stall_") and not x.endswith("_not_issued")]
 for k, r in enumerate(body):
     f = float(r[c] or 0)
     if f / tot * 100 >= thr:
-        print(f"{k:5d} {f / tot * 100:5.1f}%  exec {r[e]:>9}  {r[1].strip()[:100]}")
+        why = sorted(((float(r[i] or 0), x) for i, x in stall_cols), reverse=True)[:3]
+        why = " ".join(f"{x[6:]}={v:.0f}" for v, x in why if v > 0)
+        print(f"{k:5d} {f / tot * 100:5.1f}%  exec {r[e]:>9}  {r[1].strip()[:80]:80s} {why}")
