@@ -281,15 +281,19 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
             TStencil s;
             tile_stencil(g, tc, p.x, p.y, p.z, s);
             const float wzm[3] = {s.wz[0] * p.w, s.wz[1] * p.w, s.wz[2] * p.w};
+            // an idle lane reads where lane 0 reads (same word: no extra wavefront; its own stale address
+            // could sit in a bank an active lane uses)
+            const int n0s_lane0 = __shfl_sync(0xffffffffu, s.node0s, 0);   // every lane takes part in the shuffle
+            const int n0s = active ? s.node0s : n0s_lane0;
 #pragma unroll
             for (int oy = 0; oy < 3; ++oy)
 #pragma unroll
                 for (int ox = 0; ox < 3; ++ox) {
                     const float wxy = s.wx[ox] * s.wy[oy];
-                    float* nd = tile + s.node0s + ox + T3::SROW * oy;
-                    // three nodes along z: private to this lane within the window.  Loads and stores
-                    // are predicated (an idle lane's stale address would only add bank conflicts).
-                    float a0 = active ? nd[0] : 0.0f, a1 = active ? nd[T3::SPLANE] : 0.0f, a2 = active ? nd[2 * T3::SPLANE] : 0.0f;
+                    float* nd = tile + n0s + ox + T3::SROW * oy;
+                    // three nodes along z: private to this lane within the window.  Loads and math run
+                    // for every lane, only the stores are predicated: no branch in the chain.
+                    float a0 = nd[0], a1 = nd[T3::SPLANE], a2 = nd[2 * T3::SPLANE];
                     a0 += wxy * wzm[0];
                     a1 += wxy * wzm[1];
                     a2 += wxy * wzm[2];
@@ -385,6 +389,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         for (int w = 0; w < tc.windows; ++w) {
             window_range(tc, w, off, len);
             const bool active = lane < len;
+            const int len_w = len;
             const int d = tc.base + off + lane;   // sorted slot
             const PRec cur = nxt;
             window_range(tc, w + 1, off, len);
@@ -393,6 +398,14 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             if (lane < len) i_next = __ldg(&src[tc.base + off + lane]);
             TStencil s;
             tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
+            // idle lanes read where the first lane of their quarter warp reads (128-bit accesses are served
+            // per quarter warp; same address = no extra wavefront), or lane 0 if the whole quarter is idle;
+            // their own stale address could sit in a bank an active lane uses
+            const int q_lane = lane & ~7;
+            const int n0_q = __shfl_sync(0xffffffffu, s.node0, q_lane < len_w ? q_lane : 0);   // every lane takes part
+            const int n0s_lane0 = __shfl_sync(0xffffffffu, s.node0s, 0);
+            const int n0 = active ? s.node0 : n0_q;
+            const int n0s = active ? s.node0s : n0s_lane0;
 
             // density = sum_i m_i w_ip (3d:198-215), summed x -> y -> z
             float density = 0.0f;
@@ -401,7 +414,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 float plane = 0.0f;
 #pragma unroll
                 for (int oy = 0; oy < 3; ++oy) {
-                    const float* row = ms + s.node0s + T3::SROW * oy + T3::SPLANE * oz;
+                    const float* row = ms + n0s + T3::SROW * oy + T3::SPLANE * oz;
                     plane += (row[0] * s.wx[0] + row[1] * s.wx[1] + row[2] * s.wx[2]) * s.wy[oy];
                 }
                 density += plane * s.wz[oz];
@@ -443,11 +456,10 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                     const float A0 = wxy * (r0 + ox * M[0]), A1 = wxy * (r1 + ox * M[1]), A2 = wxy * (r2 + ox * M[2]);
                     const float G0 = wxy * M[6], G1 = wxy * M[7], G2 = wxy * M[8];
                     const float mw = wxy * m;
-                    float4* nd = acc + s.node0 + ox + T3::NX * oy;
-                    // three nodes along z: private to this lane within the window; loads and stores are
-                    // predicated (an idle lane's stale address would only add bank conflicts), the math is not
-                    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float4 a0 = active ? nd[0] : zero4, a1 = active ? nd[T3::PLANE] : zero4, a2 = active ? nd[2 * T3::PLANE] : zero4;
+                    float4* nd = acc + n0 + ox + T3::NX * oy;
+                    // three nodes along z: private to this lane within the window; loads and math are
+                    // unconditional, only the stores are predicated
+                    float4 a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
                     a0.x += s.wz[0] * A0;  a0.y += s.wz[0] * A1;  a0.z += s.wz[0] * A2;  a0.w += s.wz[0] * mw;
                     a1.x += s.wz[1] * A0 + q1 * G0;  a1.y += s.wz[1] * A1 + q1 * G1;
                     a1.z += s.wz[1] * A2 + q1 * G2;  a1.w += s.wz[1] * mw;
