@@ -40,10 +40,13 @@ struct T3 {
     static constexpr int NODES = NX * NY * NZ;       // 600 footprint nodes
     static constexpr int PLANE = 104;                // padded z stride in shared memory
     static constexpr int SLOTS = PLANE * NZ;         // 624 shared-memory slots per tile
-    // scalar (float) tiles use their own strides: x + 12*y + 128*z halves the 32-bit bank conflicts
-    // of a window under the class-major lane order (modelled 2.8 -> 2.0 wavefronts per access)
-    static constexpr int SROW = 12, SPLANE = 128;
-    static constexpr int SSLOTS = SPLANE * NZ;       // 768
+    // Node-MASS tiles pack the z axis: column (x,y) holds two overlapping quads of nodes along z,
+    // Q0 = z 0..3 and Q1 = z 2..5, one float4 each at x + 10*y + 104*Q (the float4 tile's indexing with Q
+    // as the plane, so the same bank-group rule holds).  A particle in cell layer lz touches nodes
+    // lz..lz+2: all inside quad lz >> 1, so one 128-bit access per stencil column replaces three 32-bit
+    // ones (which ran at 2.0 wavefronts each under the class-major lane order).  Nodes z = 2,3 live in
+    // both quads: a deposit goes to one of them and the flush adds the two.
+    static constexpr int QSLOTS = PLANE * 2;         // 208 float4 per mass tile
     static constexpr int WARPS = 4;                  // tiles per CTA (no CTA-level sync is used)
     static constexpr int THREADS = WARPS * 32;
 };
@@ -127,19 +130,13 @@ __device__ __forceinline__ int foot_step(const Geo& g, const TileCtx& tc, const 
     }
     return f.x + T3::NX * ly + T3::PLANE * lz;
 }
-// scalar-tile slot of the node a float4-tile slot refers to
-__device__ __forceinline__ int scalar_slot(int slot4) {
-    const int lz = slot4 / T3::PLANE, r = slot4 - lz * T3::PLANE;
-    const int ly = r / T3::NX, lx = r - ly * T3::NX;
-    return lx + T3::SROW * ly + T3::SPLANE * lz;
-}
-
 // Per-particle stencil in tile coordinates.
 struct TStencil {
     float wx[3], wy[3], wz[3];   // zeroed outside the p_rect grid (3d:166-168)
     float cx, cy, cz;            // pos - (cell + 0.5)
     int node0;                   // shared-memory slot of stencil offset (0,0,0) in a float4 tile
-    int node0s;                  // the same node in a scalar tile
+    int node0q;                  // stencil column (0,0) in a mass tile: x + 10*y + 104*(lz >> 1)
+    float wq[4];                 // z weights laid over the quad: nodes (lz & 1) .. (lz & 1) + 2
 };
 
 __device__ __forceinline__ void axis_weights(float c, float* w) {
@@ -174,7 +171,12 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
     int ly = min(max(ry - tc.c0[1], 0), T3::Y - 1);
     int lz = min(max(rz - tc.c0[2], 0), T3::Z - 1);
     s.node0 = lx + T3::NX * ly + T3::PLANE * lz;
-    s.node0s = lx + T3::SROW * ly + T3::SPLANE * lz;
+    s.node0q = lx + T3::NX * ly + T3::PLANE * (lz >> 1);
+    const bool hi = (lz & 1) != 0;
+    s.wq[0] = hi ? 0.0f : s.wz[0];
+    s.wq[1] = hi ? s.wz[0] : s.wz[1];
+    s.wq[2] = hi ? s.wz[1] : s.wz[2];
+    s.wq[3] = hi ? s.wz[2] : 0.0f;
 }
 
 // ---- clear: zero the 8x8x4 node blocks marked dirty by the sort (clear_grid, 3d:136-146) ----------
@@ -247,9 +249,9 @@ __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
              const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid) {
-    __shared__ float sm[T3::WARPS * T3::SSLOTS];
+    __shared__ float4 sm[T3::WARPS * T3::QSLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = sm + warp * T3::SSLOTS;
+    float4* tile = sm + warp * T3::QSLOTS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
@@ -258,7 +260,7 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
         if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
             continue;
         }
-        for (int k = lane; k < T3::SSLOTS; k += 32) tile[k] = 0.0f;
+        for (int k = lane; k < T3::QSLOTS; k += 32) tile[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         __syncwarp();
         // clear_grid for the node records of this tile's own block (nothing touches `grid` in this
         // kernel; "p2g 2" deposits into it next)
@@ -273,6 +275,7 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
         for (int w = 0; w < tc.windows; ++w) {
             window_range(tc, w, off, len);
             const bool active = lane < len;
+            const int len_w = len;
             const float4 p = p_next;
             window_range(tc, w + 1, off, len);
             if (lane < len) p_next = __ldg(&P[i_next]);
@@ -280,37 +283,47 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
             if (lane < len) i_next = __ldg(&src[tc.base + off + lane]);
             TStencil s;
             tile_stencil(g, tc, p.x, p.y, p.z, s);
-            const float wzm[3] = {s.wz[0] * p.w, s.wz[1] * p.w, s.wz[2] * p.w};
-            // an idle lane reads where lane 0 reads (same word: no extra wavefront; its own stale address
-            // could sit in a bank an active lane uses)
-            const int n0s_lane0 = __shfl_sync(0xffffffffu, s.node0s, 0);   // every lane takes part in the shuffle
-            const int n0s = active ? s.node0s : n0s_lane0;
+            const float wqm[4] = {s.wq[0] * p.w, s.wq[1] * p.w, s.wq[2] * p.w, s.wq[3] * p.w};
+            // an idle lane reads where the first lane of its quarter warp reads (128-bit accesses are
+            // served per quarter warp; same address = no extra wavefront), or lane 0 if the whole quarter
+            // is idle; its own stale address could sit in a bank group an active lane uses
+            const int q_lane = lane & ~7;
+            const int n0_q = __shfl_sync(0xffffffffu, s.node0q, q_lane < len_w ? q_lane : 0);   // every lane takes part
+            const int n0 = active ? s.node0q : n0_q;
 #pragma unroll
             for (int oy = 0; oy < 3; ++oy)
 #pragma unroll
                 for (int ox = 0; ox < 3; ++ox) {
                     const float wxy = s.wx[ox] * s.wy[oy];
-                    float* nd = tile + n0s + ox + T3::SROW * oy;
-                    // three nodes along z: private to this lane within the window.  Loads and math run
-                    // for every lane, only the stores are predicated: no branch in the chain.
-                    float a0 = nd[0], a1 = nd[T3::SPLANE], a2 = nd[2 * T3::SPLANE];
-                    a0 += wxy * wzm[0];
-                    a1 += wxy * wzm[1];
-                    a2 += wxy * wzm[2];
-                    if (active) nd[0] = a0;
-                    if (active) nd[T3::SPLANE] = a1;
-                    if (active) nd[2 * T3::SPLANE] = a2;
+                    float4* nd = tile + n0 + ox + T3::NX * oy;
+                    // the quad of this column: private to this lane within the window.  The load and
+                    // the math run for every lane, only the store is predicated: no branch in the chain.
+                    float4 q4 = *nd;
+                    q4.x += wxy * wqm[0];
+                    q4.y += wxy * wqm[1];
+                    q4.z += wxy * wqm[2];
+                    q4.w += wxy * wqm[3];
+                    if (active) *nd = q4;
                     __syncwarp();
                 }
         }
-        const FootLane fl = foot_lane(lane);
-#pragma unroll 4
-        for (int it = 0; it < FOOT_STEPS; ++it) {
-            int gi;
-            const int sl = foot_step(g, tc, fl, it, gi);
-            if (gi >= 0) {
-                const float v = tile[scalar_slot(sl)];
-                if (v != 0.0f) atomicAdd(&gmass[gi], v);
+        // flush: lane -> footprint column c = lane + 32*it (100 columns), six nodes along z
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+            const int c = lane + 32 * it;
+            if (c < T3::NX * T3::NY) {
+                const int ly = c / T3::NX, lx = c - ly * T3::NX;
+                const int x = tc.c0[0] - 1 + lx, y = tc.c0[1] - 1 + ly;
+                const float4 q0 = tile[c], q1 = tile[c + T3::PLANE];
+                const float m6[6] = {q0.x, q0.y, q0.z + q1.x, q0.w + q1.y, q1.z, q1.w};
+                if (!tc.edge || (x >= 0 && y >= 0 && x < g.size[0] && y < g.size[1])) {
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) {
+                        const int z = tc.c0[2] - 1 + k;
+                        if (m6[k] != 0.0f && (!tc.edge || (z >= 0 && z < g.size[2])))
+                            atomicAdd(&gmass[g.guard + x + (y + z * g.size[1]) * g.size[0]], m6[k]);
+                    }
+                }
             }
         }
         __syncwarp();
@@ -321,7 +334,7 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
 
 struct P2GSmem {
     float4 acc[T3::WARPS][T3::SLOTS];   // {momentum + force, mass} accumulators
-    float mass[T3::WARPS][T3::SSLOTS];  // complete node masses (from k_mass_tiled), scalar-tile strides
+    float4 mass[T3::WARPS][T3::QSLOTS]; // complete node masses (from k_mass_tiled) as z quads
 };
 
 struct PRec {   // one particle's streams
@@ -348,7 +361,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* acc = sm.acc[warp];
-    float* ms = sm.mass[warp];
+    float4* ms = sm.mass[warp];
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
@@ -366,23 +379,31 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         window_range(tc, 1, off, len);
         int i_next = lane < len ? __ldg(&src[tc.base + off + lane]) : 0;
         const FootLane fl = foot_lane(lane);
-        {   // node masses of the footprint: all loads in flight before the first store
-            float mv[FOOT_STEPS];
+        {   // node masses of the footprint, column by column (six nodes along z -> two quads): all loads
+            // in flight before the first store
+            float mv[4][6];
 #pragma unroll
-            for (int it = 0; it < FOOT_STEPS; ++it) {
-                int gi;
-                (void)foot_step(g, tc, fl, it, gi);
-                mv[it] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
-            }
+            for (int it = 0; it < 4; ++it) {
+                const int c = lane + 32 * it;
+                const int ly = c / T3::NX, lx = c - ly * T3::NX;
+                const int x = tc.c0[0] - 1 + lx, y = tc.c0[1] - 1 + ly;
+                const bool col_ok = c < T3::NX * T3::NY && (!tc.edge || (x >= 0 && y >= 0 && x < g.size[0] && y < g.size[1]));
 #pragma unroll
-            for (int it = 0; it < FOOT_STEPS; ++it) {
-                int gi;
-                const int sl = foot_step(g, tc, fl, it, gi);
-                if (fl.rsub < 3) {
-                    ms[scalar_slot(sl)] = mv[it];
-                    acc[sl] = make_float4(0.f, 0.f, 0.f, 0.f);
+                for (int k = 0; k < 6; ++k) {
+                    const int z = tc.c0[2] - 1 + k;
+                    const bool ok = col_ok && (!tc.edge || (z >= 0 && z < g.size[2]));
+                    mv[it][k] = ok ? __ldg(&gmass[g.guard + x + (y + z * g.size[1]) * g.size[0]]) : 0.0f;
                 }
             }
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int c = lane + 32 * it;
+                if (c < T3::NX * T3::NY) {
+                    ms[c] = make_float4(mv[it][0], mv[it][1], mv[it][2], mv[it][3]);
+                    ms[c + T3::PLANE] = make_float4(mv[it][2], mv[it][3], mv[it][4], mv[it][5]);
+                }
+            }
+            for (int k = lane; k < T3::SLOTS; k += 32) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         __syncwarp();
 
@@ -403,21 +424,23 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             // their own stale address could sit in a bank an active lane uses
             const int q_lane = lane & ~7;
             const int n0_q = __shfl_sync(0xffffffffu, s.node0, q_lane < len_w ? q_lane : 0);   // every lane takes part
-            const int n0s_lane0 = __shfl_sync(0xffffffffu, s.node0s, 0);
+            const int n0q_q = __shfl_sync(0xffffffffu, s.node0q, q_lane < len_w ? q_lane : 0);
             const int n0 = active ? s.node0 : n0_q;
-            const int n0s = active ? s.node0s : n0s_lane0;
+            const int n0q = active ? s.node0q : n0q_q;
 
-            // density = sum_i m_i w_ip (3d:198-215), summed x -> y -> z
+            // density = sum_i m_i w_ip (3d:198-215): one quad of node masses per stencil column,
+            // summed z -> x -> y
             float density = 0.0f;
 #pragma unroll
-            for (int oz = 0; oz < 3; ++oz) {
-                float plane = 0.0f;
+            for (int oy = 0; oy < 3; ++oy) {
+                const float4* row = ms + n0q + T3::NX * oy;
+                float rs = 0.0f;
 #pragma unroll
-                for (int oy = 0; oy < 3; ++oy) {
-                    const float* row = ms + n0s + T3::SROW * oy + T3::SPLANE * oz;
-                    plane += (row[0] * s.wx[0] + row[1] * s.wx[1] + row[2] * s.wx[2]) * s.wy[oy];
+                for (int ox = 0; ox < 3; ++ox) {
+                    const float4 q4 = row[ox];
+                    rs += (q4.x * s.wq[0] + q4.y * s.wq[1] + q4.z * s.wq[2] + q4.w * s.wq[3]) * s.wx[ox];
                 }
-                density += plane * s.wz[oz];
+                density += rs * s.wy[oy];
             }
             const float m = cur.p.w;
             float volume = 0.0f, pressure = 0.0f;
