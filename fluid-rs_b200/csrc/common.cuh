@@ -112,7 +112,7 @@ __device__ __forceinline__ int classify_pos(const Geo& g, const float* pos) {
 // Cell index inside an 8x8x4 tile: class-major.  The bank class of a cell is the 16-byte bank
 // group (x + 2y) mod 8 of its node column in the shared-memory tile (index x + 10y + 104z); cells
 // are numbered class, then y (which fixes the column inside the class), then z: 32 cells per class,
-// 4 per column.  k_tile_perm builds windows that hold each class evenly (sort.cuh).
+// 4 per column.  k_tile_tables and k_build_src build windows that hold each class evenly (sort.cuh).
 __device__ __forceinline__ int local_cell_3d(int lx, int ly, int lz) {
     const int cls = (lx + 2 * ly) & 7;
     return lz + 4 * (ly + 8 * cls);

@@ -94,7 +94,7 @@ struct fluid_sim {
     int* cell_off = nullptr; // per bucket: first cell-sorted slot (cellStart)
     int* tile_total = nullptr;
     int* tile_base = nullptr;    // exclusive scan of tile_total; [n_tiles] = number of p_rect particles
-    int* cand = nullptr;         // tiles that hold particles (from the scan), input list of k_tile_perm
+    int* cand = nullptr;         // tiles that hold particles (from the scan), input list of k_tile_tables
     int* dirty_list = nullptr;   // node blocks to clear this substep
     unsigned char* dirty[2] = {nullptr, nullptr};   // node blocks touched by the current / previous sort
     int dirty_cur = 0;

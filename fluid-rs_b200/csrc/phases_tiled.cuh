@@ -64,7 +64,7 @@ struct TileCtx {
     bool edge;     // the footprint sticks out of the p_rect grid
 };
 
-// Active tiles, listed by k_tile_perm: {tile id, first slot, count, windows}.  The tile kernels
+// Active tiles, listed by k_tile_tables: {tile id, first slot, count, windows}.  The tile kernels
 // run persistent warps that stride over this list, so empty tiles cost nothing.
 __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileCtx& tc) {
     const int t = e.x;

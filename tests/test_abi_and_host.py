@@ -40,7 +40,7 @@ def test_library_is_sm100a_and_has_our_kernels(pkg):
     out = subprocess.run(["cuobjdump", "-lelf", str(pkg.LIB_PATH)], capture_output=True, text=True)
     assert "sm_100a" in out.stdout
     syms = subprocess.run(["cuobjdump", "-sass", str(pkg.LIB_PATH)], capture_output=True, text=True).stdout
-    for k in ("k_classify_all", "k_tile_perm", "k_scan_final", "k_mass_tiled", "k_p2g_tiled", "k_g2p_tiled"):
+    for k in ("k_classify_all", "k_tile_tables", "k_build_src", "k_scan_final", "k_mass_tiled", "k_p2g_tiled", "k_g2p_tiled"):
         assert k in syms
 
 
