@@ -100,6 +100,9 @@ struct fluid_sim {
     int dirty_cur = 0;
     int2* tile_info = nullptr;   // per tile: {windows W (0 = plain cell order, < 0 = no class merge), tile-list entry}
     unsigned char* tab = nullptr;   // per tile-list entry: TAB_BYTES of class-in-window counts (k_tile_tables)
+    PeerHalo peer{};             // neighbours' grids mapped through CUDA IPC (peer-memory halo), or all null
+    void* peer_base[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // opened IPC mappings
+    bool p2p = false;            // deposits into the shared node planes go to the neighbour directly
     int* gz = nullptr;           // per tile: substep number in which k_g2p_tiled zeroed its node-mass block
     int epoch = 0;               // tiled substeps run so far (compared with gz)
     bool grid_clean = false;     // every node outside the dirty blocks is zero
@@ -358,10 +361,10 @@ fluid_status sort_finish(fluid_sim* s) {
     if (DIM == 3) {
         s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
         k_tile_tables<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
-                                                                            s->tiles, s->scal, s->dirty[s->dirty_cur], s->cand);
+                                                                            s->tiles, s->scal, s->dirty[s->dirty_cur], s->cand, s->peer);
     } else {
         k_tile_tables<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
-                                                                        s->tiles, s->scal, nullptr, s->cand);
+                                                                        s->tiles, s->scal, nullptr, s->cand, PeerHalo{});
     }
     s->launches += 4;
     if (n > 0) {
@@ -419,6 +422,23 @@ fluid_status profile_drain(fluid_sim* s) {
     return FLUID_OK;
 }
 
+// Peer-halo slab runs: the neighbour's "p2g 1" adds into this rank's node masses right after its own sort,
+// possibly before this rank's next clear.  So the node masses of the rim blocks are zeroed here, at the end
+// of the substep (after g2p, before the migrant exchange both ranks wait on); the blocks of the active
+// tiles were zeroed by k_g2p_tiled itself (stamp gz == epoch).  The list is the union of both dirty flag
+// arrays (this substep's sort, the neighbour's marks, which go into both); nothing is reset (the next clear
+// of the node records needs them).
+fluid_status clear_mass_rim(fluid_sim* s, bool fused) {
+    k_dirty_list<<<blocks_for(s->geo.n_tiles, 256), 256, 0, s->stream>>>(s->geo, s->dirty[0], s->dirty[1], s->dirty_list,
+                                                                        s->scal + SCAL_N_DIRTY2, false);
+    k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
+                                      static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
+        s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY2, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, fused, 2);
+    s->launches += 2;
+    CU_TRY(cudaGetLastError());
+    return FLUID_OK;
+}
+
 // One substep = clear -> p2g 1 -> p2g 2 -> update -> g2p (3d:111-133).  `phases` selects the parts
 // (slab runs exchange halo planes between them): 1 = sort + clear + p2g 1, 2 = p2g 2, 4 = update + g2p.
 template <int DIM>
@@ -463,16 +483,17 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             } else {
                 // only the node blocks the previous or the coming deposits can touch
                 k_dirty_list<<<blocks_for(s->geo.n_tiles, 256), 256, 0, s->stream>>>(
-                    s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY);
+                    s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY, true);
                 k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                                   static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-                    s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, true);
+                    s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, true,
+                    s->p2p ? 1 : 3);   // peer-halo runs clear the node masses at the end of the substep instead
                 s->launches += 2;
             }
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
             ++s->epoch;
             k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                  s->gmass, s->grid);
+                                                                                  s->gmass, s->grid, s->peer);
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
@@ -489,7 +510,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
         if (tiled)
             k_p2g_tiled<<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
                 s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
-                dbg ? dbg->pressure : nullptr);
+                dbg ? dbg->pressure : nullptr, s->peer);
         else
             k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid,
                                                                           dbg ? dbg->density : nullptr,
@@ -514,6 +535,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             const int* n_end = s->geo.slab_on ? s->tile_base + s->geo.n_tiles + 1 : nullptr;
             k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, q, qn, s->src, n_dep, n_end, n, sort_tables(s));
             s->launches += 2;
+            if (s->p2p) ST_TRY(clear_mass_rim(s, true));
             s->cur ^= 1;
             s->counts_pending = true;
         } else {
@@ -726,7 +748,23 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     return FLUID_OK;
 }
 
+// unmap a neighbour's arrays (peer-memory halo)
+static void close_peer(fluid_sim* s, int side) {
+    for (int k = 0; k < 4; ++k) {
+        if (s->peer_base[side][k]) cudaIpcCloseMemHandle(s->peer_base[side][k]);
+        s->peer_base[side][k] = nullptr;
+    }
+    s->peer.grid[side] = nullptr;
+    s->peer.gmass[side] = nullptr;
+    s->peer.dirty[side][0] = s->peer.dirty[side][1] = nullptr;
+    s->p2p = s->peer.grid[0] || s->peer.grid[1];
+}
+
 fluid_status fluid_destroy(fluid_sim* s) {
+    if (s) {
+        close_peer(s, 0);
+        close_peer(s, 1);
+    }
     if (!s) return FLUID_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
@@ -824,7 +862,9 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     g.n_tiles = static_cast<int>(tiles);
     g.n_cells_pad = static_cast<int>(tiles * 256);
     g.guard = 1 + g.size[0] + (D == 3 ? g.size[0] * g.size[1] : 0);
-    g.slab_on = 0;   // set_rect resets the decomposition: call fluid_slab_set again
+    g.slab_on = 0;   // set_rect resets the decomposition: call fluid_slab_set (and the IPC import) again
+    close_peer(s, 0);
+    close_peer(s, 1);
     g.slab_lo = 0;
     g.slab_hi = 0;
     g.res_f = res;
@@ -1330,12 +1370,15 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
         } else if (phase == 0) {
             CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
             k_dirty_list<<<blocks_for(s->geo.n_tiles, 256), 256, 0, s->stream>>>(
-                s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY);
+                s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY, true);
             k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                               static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-                s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, 0, false);
+                s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, 0, false,
+                s->p2p ? 1 : 3);
             ++s->epoch;   // no g2p ran: no stamp of an earlier substep may match the next clear
             s->dirty_cur ^= 1;
+        } else if (phase == 2 && s->p2p) {
+            ST_TRY(clear_mass_rim(s, false));   // the neighbours' "p2g 1" deposits of this substep
         }
         return FLUID_OK;
     }
@@ -1357,6 +1400,56 @@ fluid_status fluid_slab_accumulate(fluid_sim* s, int32_t side, int32_t kind) {
         k_accumulate_planes<float4><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid + first, s->halo_node_recv[side], n, zb - 1, dirty);
     ++s->launches;
     CU_TRY(cudaGetLastError());
+    return FLUID_OK;
+}
+
+// ---- peer-memory halo (NVLink P2P through CUDA IPC) ---------------------------------------------
+
+fluid_status fluid_slab_ipc_export(fluid_sim* s, void* handles) {
+    if (!s || !handles) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_ipc_export: null argument");
+    if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_ipc_export: fluid_slab_set has not been called");
+    CU_TRY(cudaSetDevice(s->device));
+    static_assert(FLUID_IPC_BYTES == 4 * sizeof(cudaIpcMemHandle_t), "FLUID_IPC_BYTES");
+    cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(handles);
+    CU_TRY(cudaIpcGetMemHandle(&h[0], s->grid));
+    CU_TRY(cudaIpcGetMemHandle(&h[1], s->gmass));
+    CU_TRY(cudaIpcGetMemHandle(&h[2], s->dirty[0]));
+    CU_TRY(cudaIpcGetMemHandle(&h[3], s->dirty[1]));
+    // The neighbours may deposit into this rank's planes before its own first substep gets to wipe the
+    // arrays: wipe now (the caller puts a barrier between the imports and the first substep).
+    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+    CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
+    CU_TRY(cudaMemsetAsync(s->dirty[0], 0, s->geo.n_tiles, s->stream));
+    CU_TRY(cudaMemsetAsync(s->dirty[1], 0, s->geo.n_tiles, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->grid_clean = true;
+    return FLUID_OK;
+}
+
+fluid_status fluid_slab_ipc_import(fluid_sim* s, int32_t side, const void* handles) {
+    if (!s || side < 0 || side > 1) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_ipc_import: bad argument");
+    if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_ipc_import: fluid_slab_set has not been called");
+    CU_TRY(cudaSetDevice(s->device));
+    close_peer(s, side);
+    if (!handles) {   // back to plane exchanges on this side
+        s->p2p = s->peer.grid[0] || s->peer.grid[1];
+        return FLUID_OK;
+    }
+    if (!s->has_nb[side]) return fail(FLUID_ERR_STATE, "fluid_slab_ipc_import: no neighbour on that side");
+    const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
+    for (int k = 0; k < 4; ++k) {
+        cudaError_t e = cudaIpcOpenMemHandle(&s->peer_base[side][k], h[k], cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            close_peer(s, side);
+            return fail(FLUID_ERR_CUDA, cudaGetErrorString(e));
+        }
+    }
+    s->peer.grid[side] = static_cast<float4*>(s->peer_base[side][0]);
+    s->peer.gmass[side] = static_cast<float*>(s->peer_base[side][1]);
+    s->peer.dirty[side][0] = static_cast<unsigned char*>(s->peer_base[side][2]);
+    s->peer.dirty[side][1] = static_cast<unsigned char*>(s->peer_base[side][3]);
+    s->p2p = true;
     return FLUID_OK;
 }
 

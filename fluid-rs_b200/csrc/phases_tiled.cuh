@@ -184,13 +184,13 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
 // previous substep (flags of two consecutive sorts are kept: `dirty_prev | dirty_now`).
 __global__ void __launch_bounds__(256)
 k_dirty_list(const __grid_constant__ Geo g, const unsigned char* __restrict__ dirty_now,
-             unsigned char* __restrict__ dirty_prev, int* __restrict__ list, int* __restrict__ n_list) {
+             unsigned char* __restrict__ dirty_prev, int* __restrict__ list, int* __restrict__ n_list, bool reset) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     bool d = false;
     if (t < g.n_tiles) {
         const bool was = dirty_prev[t] != 0;
         d = was || dirty_now[t] != 0;
-        if (was) dirty_prev[t] = 0;   // dirty_prev becomes the next sort's dirty_now
+        if (was && reset) dirty_prev[t] = 0;   // dirty_prev becomes the next sort's dirty_now
     }
     const unsigned m = __ballot_sync(0xffffffffu, d);
     const int lane = threadIdx.x & 31;
@@ -206,14 +206,15 @@ k_dirty_list(const __grid_constant__ Geo g, const unsigned char* __restrict__ di
 __global__ void __launch_bounds__(128)
 k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const int* __restrict__ n_list,
               float4* __restrict__ grid, float* __restrict__ gmass, const int* __restrict__ tile_base,
-              const int* __restrict__ gz, int epoch_prev, bool fused) {
+              const int* __restrict__ gz, int epoch_prev, bool fused, int what) {
     const int lane = threadIdx.x & 31;
     const int n = *n_list;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
     for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < n; a += n_warps) {
         const int t = list[a];
-        const bool do_grid = !fused || tile_base[t + 1] == tile_base[t];   // else k_mass_tiled zeroes it
-        const bool do_mass = !fused || gz[t] != epoch_prev;                // else k_g2p_tiled did
+        // what: 1 = node records, 2 = node masses, 3 = both (peer-halo slab runs clear them at different times)
+        const bool do_grid = (what & 1) && (!fused || tile_base[t + 1] == tile_base[t]);   // else k_mass_tiled zeroes it
+        const bool do_mass = (what & 2) && (!fused || gz[t] != epoch_prev);                // else k_g2p_tiled did
         if (!do_grid && !do_mass) continue;
         const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
         // 256 nodes: lane -> x = lane & 7, y = (lane >> 3) + 4*(j & 1), z = j >> 1
@@ -248,7 +249,7 @@ __device__ __forceinline__ void zero_own_block(const Geo& g, const TileCtx& tc, 
 __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
-             const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid) {
+             const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid, PeerHalo ph) {
     __shared__ float4 sm[T3::WARPS * T3::QSLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* tile = sm + warp * T3::QSLOTS;
@@ -308,6 +309,8 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                 }
         }
         // flush: lane -> footprint column c = lane + 32*it (100 columns), six nodes along z
+        float* peer_lo = (g.slab_on && tc.c0[2] == g.slab_lo) ? ph.gmass[0] : nullptr;              // warp-uniform
+        float* peer_hi = (g.slab_on && tc.c0[2] + T3::Z == g.slab_hi) ? ph.gmass[1] : nullptr;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int c = lane + 32 * it;
@@ -320,12 +323,18 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
 #pragma unroll
                     for (int k = 0; k < 6; ++k) {
                         const int z = tc.c0[2] - 1 + k;
-                        if (m6[k] != 0.0f && (!tc.edge || (z >= 0 && z < g.size[2])))
-                            atomicAdd(&gmass[g.guard + x + (y + z * g.size[1]) * g.size[0]], m6[k]);
+                        if (m6[k] != 0.0f && (!tc.edge || (z >= 0 && z < g.size[2]))) {
+                            const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
+                            atomicAdd(&gmass[gi], m6[k]);
+                            // the two node planes a slab face shares: the neighbour's copy as well (NVLink)
+                            if (k < 2 && peer_lo) atomicAdd(&peer_lo[gi], m6[k]);
+                            if (k >= 4 && peer_hi) atomicAdd(&peer_hi[gi], m6[k]);
+                        }
                     }
                 }
             }
         }
+        if (peer_lo || peer_hi) __threadfence_system();
         __syncwarp();
     }
 }
@@ -356,7 +365,7 @@ __global__ void __launch_bounds__(T3::THREADS, 4)
 k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float* __restrict__ gmass, float4* __restrict__ grid,
-            float* __restrict__ dbg_density, float* __restrict__ dbg_pressure) {
+            float* __restrict__ dbg_density, float* __restrict__ dbg_pressure, PeerHalo ph) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -495,15 +504,23 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 }
             }
         }
+        float4* peer_lo = (g.slab_on && tc.c0[2] == g.slab_lo) ? ph.grid[0] : nullptr;              // warp-uniform
+        float4* peer_hi = (g.slab_on && tc.c0[2] + T3::Z == g.slab_hi) ? ph.grid[1] : nullptr;
 #pragma unroll 4
         for (int it = 0; it < FOOT_STEPS; ++it) {
             int gi;
             const int sl = foot_step(g, tc, fl, it, gi);
             if (gi >= 0) {
                 const float4 v = acc[sl];
-                if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) atomicAdd(&grid[gi], v);
+                if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
+                    atomicAdd(&grid[gi], v);
+                    // the two node planes a slab face shares: the neighbour's copy as well (NVLink)
+                    if (sl < 2 * T3::PLANE && peer_lo) atomicAdd(&peer_lo[gi], v);
+                    if (sl >= 4 * T3::PLANE && peer_hi) atomicAdd(&peer_hi[gi], v);
+                }
             }
         }
+        if (peer_lo || peer_hi) __threadfence_system();
         __syncwarp();
     }
 }

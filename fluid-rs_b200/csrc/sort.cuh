@@ -45,10 +45,19 @@ struct SortTables {
     int* scal;         // device scalars (SCAL_*)
 };
 
+// Peer-memory halo of a slab run (NVLink P2P, mapped through CUDA IPC): side 0 = the rank below, 1 = above.
+// The tile kernels add every deposit that falls into the two node planes an interface shares into the
+// neighbour's arrays as well, so both ranks hold complete sums with no plane exchange.
+struct PeerHalo {
+    float4* grid[2];            // neighbour's node records (same geometry, same indexing) or nullptr
+    float* gmass[2];            // neighbour's node masses
+    unsigned char* dirty[2][2]; // neighbour's two dirty-block flag arrays
+};
+
 constexpr int TILE_CELLS = 256;
 constexpr int N_PSEUDO = 3;   // pseudo tiles behind the real ones: ignored, dropped, migrated away
 constexpr int SCAL_N_ACTIVE = 0, SCAL_N_IMM = 1, SCAL_MIG_LO = 2, SCAL_MIG_HI = 3, SCAL_MIG_OVERFLOW = 4;
-constexpr int SCAL_N_CAND = 5, SCAL_N_DIRTY = 6;
+constexpr int SCAL_N_CAND = 5, SCAL_N_DIRTY = 6, SCAL_N_DIRTY2 = 7;
 constexpr int MIG_WORDS = 17;   // packed migrant record: 16 f32 + id
 
 __device__ __forceinline__ bool is_tombstone(float x) { return isinf(x) && x > 0.0f; }
@@ -309,7 +318,7 @@ __global__ void __launch_bounds__(PERM_WARPS * 32)
 k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int* __restrict__ tile_base,
               int* __restrict__ cell_off, int2* __restrict__ tile_info, unsigned char* __restrict__ tab,
               int4* __restrict__ tiles, int* __restrict__ scal, unsigned char* __restrict__ dirty,
-              const int* __restrict__ cand) {
+              const int* __restrict__ cand, PeerHalo ph) {
     const int lane = threadIdx.x & 31;
     // persistent warps over the list of tiles that hold particles (k_scan_final)
     const int n_cand = scal[SCAL_N_CAND];
@@ -358,8 +367,20 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
             // mark them for k_clear_tiles (clear_grid, 3d:136-146, only where something was written)
             const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
             const int nx = tx + lane % 3 - 1, ny = ty + (lane / 3) % 3 - 1, nz = tz + lane / 9 - 1;
-            if (nx >= 0 && ny >= 0 && nz >= 0 && nx < g.tdim[0] && ny < g.tdim[1] && nz < g.tdim[2])
-                dirty[(nz * g.tdim[1] + ny) * g.tdim[0] + nx] = 1;
+            if (nx >= 0 && ny >= 0 && nz >= 0 && nx < g.tdim[0] && ny < g.tdim[1] && nz < g.tdim[2]) {
+                const int blk = (nz * g.tdim[1] + ny) * g.tdim[0] + nx;
+                dirty[blk] = 1;
+                // a tile on a slab face also deposits into the neighbour's copy of the two shared node
+                // planes (block layers tz-1, tz below / tz, tz+1 above): the neighbour has to clear them
+                if (ph.dirty[0][0] && tz * Tile<3>::Z == g.slab_lo && nz <= tz) {
+                    ph.dirty[0][0][blk] = 1;
+                    ph.dirty[0][1][blk] = 1;
+                }
+                if (ph.dirty[1][0] && (tz + 1) * Tile<3>::Z == g.slab_hi && nz >= tz) {
+                    ph.dirty[1][0][blk] = 1;
+                    ph.dirty[1][1][blk] = 1;
+                }
+            }
         }
         // lane owns 8 consecutive cells (3D: two (x,y) columns of one bank class, 4 cells each)
         int cnt[8];

@@ -3,9 +3,17 @@
 One process per GPU (torch.distributed, NCCL over NVLink).  Every rank holds the same dense node
 grid geometry and owns the particles whose cell floor(pos.z) lies in its slab.  Per substep:
 
-    phase 0  sort + clear + p2g 1     -> exchange the two MASS planes of each interface, add
-    phase 1  p2g 2                    -> exchange the two NODE planes of each interface, add
+    phase 0  sort + clear + p2g 1     -> the two MASS planes of each interface become complete
+    phase 1  p2g 2                    -> the two NODE planes of each interface become complete
     phase 2  update + g2p             -> particles that left the slab go to the neighbour
+
+How the shared planes become complete:
+  * peer-memory halo (default on GPUs): every rank maps its neighbours' grids through CUDA IPC and the tile
+    kernels add the deposits that fall into the shared planes into the neighbour's copy as well
+    (red.global.add over NVLink inside the kernels' flush) — no plane exchange, no accumulate pass, only a
+    neighbour barrier after the phase;
+  * plane exchange (FLUID_B200_SLAB_P2P=0, and the CPU protocol test): both ranks swap their partial
+    planes over the process group and add.
 
 The reference's own analogue is the +-1 block halo ring (`p_rect` vs `a_rect`, 3d:84-86) in which
 particles deposit but are not advanced, and the per-block mailboxes `swap_mul` (3d:327-358).
@@ -42,7 +50,7 @@ def plan_slabs(fill_lo: float, fill_hi: float, origin_z: int, size_z: int, world
 class SlabDriver:
     """The per-substep exchange protocol, independent of device and backend."""
 
-    def __init__(self, engine, rank: int, world: int, dist=None, device="cpu"):
+    def __init__(self, engine, rank: int, world: int, dist=None, device="cpu", p2p: bool = False):
         self.e = engine
         self.rank, self.world = rank, world
         self.dist = dist
@@ -50,6 +58,26 @@ class SlabDriver:
         self.nb = [rank - 1 if rank > 0 else None, rank + 1 if rank < world - 1 else None]
         self.migrated_out = 0
         self.migrated_in = 0
+        self.p2p = p2p          # peer-memory halo: the kernels deposit into the neighbours' planes themselves
+        self._token = None
+
+    # -- neighbour barrier (peer-memory halo) ---------------------------------------------------
+    def neighbour_barrier(self):
+        """A token each way with every neighbour: when it completes on this rank's stream, the neighbour's
+        phase kernel — and with it its deposits into this rank's planes — has finished."""
+        import torch
+        dist = self.dist
+        if self._token is None:
+            self._token = [torch.zeros(1, dtype=torch.float32, device=self.device) for _ in range(4)]
+        ops = []
+        for side in (0, 1):
+            if self.nb[side] is None:
+                continue
+            ops.append(dist.P2POp(dist.isend, self._token[2 * side], self.nb[side]))
+            ops.append(dist.P2POp(dist.irecv, self._token[2 * side + 1], self.nb[side]))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
 
     # -- halo planes -----------------------------------------------------------------------------
     def exchange_planes(self, kind: int):
@@ -109,11 +137,17 @@ class SlabDriver:
 
     def substep(self, mouse=None):
         self.e.phase(0, None)
-        self.exchange_planes(0)
+        if self.p2p:
+            self.neighbour_barrier()
+        else:
+            self.exchange_planes(0)
         self.e.phase(1, None)
-        self.exchange_planes(1)
+        if self.p2p:
+            self.neighbour_barrier()
+        else:
+            self.exchange_planes(1)
         self.e.phase(2, mouse)
-        self.migrate()
+        self.migrate()      # always a send/recv pair with each neighbour: it also orders the next substep
 
 
 class _DevArray:
@@ -199,8 +233,35 @@ class SlabSimulation:
         st = L.fluid_slab_set(self.sim._h, self.z_lo, self.z_hi, int(rank > 0), int(rank < world - 1))
         if st != 0:
             raise pkg.FluidError(st, L.fluid_last_error().decode())
-        self.driver = SlabDriver(CudaSlabEngine(pkg, self.sim), rank, world, dist, device=f"cuda:{device}")
+        import os
+        p2p = world > 1 and os.environ.get("FLUID_B200_SLAB_P2P", "1") != "0"
+        if p2p:
+            p2p = self._map_neighbours(L, dist, rank, world, device)
+        self.p2p = p2p
+        self.driver = SlabDriver(CudaSlabEngine(pkg, self.sim), rank, world, dist, device=f"cuda:{device}", p2p=p2p)
         self.iterations = int(self.sim.config.iterations)
+
+    def _map_neighbours(self, L, dist, rank, world, device) -> bool:
+        """Peer-memory halo set-up: all-gather the CUDA IPC handles of every rank's arrays and map the two
+        neighbours'.  Falls back to plane exchanges (on every rank) if any mapping fails."""
+        import torch
+        IPC_BYTES = 256
+        mine = (C.c_ubyte * IPC_BYTES)()
+        ok = L.fluid_slab_ipc_export(self.sim._h, C.cast(mine, C.c_void_p)) == 0
+        t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=f"cuda:{device}")
+        allh = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allh, t)
+        for side, nb in ((0, rank - 1), (1, rank + 1)):
+            if ok and 0 <= nb < world:
+                buf = (C.c_ubyte * IPC_BYTES)(*allh[nb].cpu().tolist())
+                ok = L.fluid_slab_ipc_import(self.sim._h, side, C.cast(buf, C.c_void_p)) == 0
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=f"cuda:{device}")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)      # also the barrier between the wipes and the first substep
+        if int(flag.item()) == 0:
+            for side in (0, 1):
+                L.fluid_slab_ipc_import(self.sim._h, side, None)
+            return False
+        return True
 
     def owns(self, records: np.ndarray) -> np.ndarray:
         cz = np.floor(records[:, 2]).astype(np.int64)

@@ -202,6 +202,19 @@ fluid_status fluid_slab_phase(fluid_sim* sim, int32_t phase, const float* mouse_
 fluid_status fluid_slab_accumulate(fluid_sim* sim, int32_t side, int32_t kind);
 /* After phase 2: device pointers to the packed records (17 words: 16 f32 + id) of the particles that
  * left through the lower / upper face and their counts.  Synchronises the stream. */
+/* Peer-memory halo (NVLink P2P; one process per GPU, arrays mapped through CUDA IPC).  With the
+ * neighbours' arrays imported, "p2g 1" and "p2g 2" add every deposit that falls into the two node planes
+ * an interface shares into the neighbour's copy as well (red.global.add over NVLink, inside the tile
+ * kernels' flush), so both ranks hold complete sums when the kernels end: fluid_slab_planes /
+ * fluid_slab_accumulate are not used and the caller only puts a neighbour barrier after phase 0 and after
+ * phase 1 (and keeps the migrant exchange after phase 2, which orders the next substep).
+ *   fluid_slab_ipc_export  FLUID_IPC_BYTES of handles for this rank's arrays; wipes them (call before the
+ *                          neighbours may deposit, i.e. before the barrier that ends the set-up)
+ *   fluid_slab_ipc_import  map the arrays of the neighbour on `side` (0 = lower, 1 = upper); NULL unmaps.
+ * fluid_set_rect reallocates the arrays: export / import again after it. */
+#define FLUID_IPC_BYTES 256
+fluid_status fluid_slab_ipc_export(fluid_sim* sim, void* handles);
+fluid_status fluid_slab_ipc_import(fluid_sim* sim, int32_t side, const void* handles);
 fluid_status fluid_slab_migrants(fluid_sim* sim, void** d_lower, int64_t* n_lower, void** d_upper,
                                  int64_t* n_upper);
 /* Append n packed 17-word records that are resident in device memory. */

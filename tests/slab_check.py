@@ -53,6 +53,7 @@ def main():
         o = np.argsort(allid, kind="stable")
         allrec, allid = allrec[o], allid[o]
         moved = sum(g[4] for g in gathered)
+        print("halo:", "peer memory (P2P deposits)" if sim.p2p else "plane exchange")
         print("slabs", [g[6] for g in gathered], "start", [g[2] for g in gathered],
               "end", [len(g[1]) for g in gathered], "migrated out/in", moved, sum(g[5] for g in gathered))
         ok &= np.array_equal(allid, rid)
