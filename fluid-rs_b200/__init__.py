@@ -103,6 +103,8 @@ SIGNATURES = {
     "fluid_slab_accumulate": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32]),
     "fluid_slab_migrants": (C.c_int, [C.c_void_p, _vpp, _i64p, _vpp, _i64p]),
     "fluid_slab_append": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64]),
+    "fluid_slab_migrants_begin": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
+    "fluid_slab_migrants_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fluid_slab_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
     "fluid_slab_ipc_import": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
 }

@@ -135,7 +135,9 @@ struct fluid_sim {
     cudaEvent_t* cur_ev = nullptr;     // event set of the substep in progress (split substeps)
     bool cur_timed = false;
     // z-slab decomposition
-    float* mig_rec[2] = {nullptr, nullptr};   // packed records of the particles leaving through z_lo / z_hi
+    float* mig_rec[2] = {nullptr, nullptr};   // a one-record header {count}, then the packed records of the particles leaving through z_lo / z_hi
+    int* d_status = nullptr;                  // device: scal[0..7], tile_base[n_tiles .. n_tiles + 3] gathered for one read-back
+    int* h_status = nullptr;                  // pinned host copy: + the headers of the two received buffers
     int mig_cap = 0;
     bool has_nb[2] = {false, false};
     float* halo_mass_recv[2] = {nullptr, nullptr};
@@ -525,8 +527,8 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             // state at the sorted slots of the other buffer (no reorder pass)
             Particles qn = s->buf[s->cur ^ 1];
             SlabBufs sb{};
-            sb.rec[0] = s->mig_rec[0];
-            sb.rec[1] = s->mig_rec[1];
+            sb.rec[0] = s->mig_rec[0] ? s->mig_rec[0] + MIG_WORDS : nullptr;   // behind the header record
+            sb.rec[1] = s->mig_rec[1] ? s->mig_rec[1] + MIG_WORDS : nullptr;
             sb.cap = s->mig_cap;
             k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
                 s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch);
@@ -789,6 +791,8 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->gz);
     cudaFree(s->tile_info);
     cudaFree(s->tab);
+    cudaFree(s->d_status);
+    if (s->h_status) cudaFreeHost(s->h_status);
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -1318,6 +1322,8 @@ fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t ha
     s->has_nb[1] = has_upper != 0;
     const int64_t plane2 = 2LL * s->geo.size[0] * s->geo.size[1];
     if (s->mig_cap == 0) s->mig_cap = 1 << 18;
+    if (!s->d_status) CU_TRY(cudaMalloc(&s->d_status, 16 * sizeof(int)));
+    if (!s->h_status) CU_TRY(cudaMallocHost(&s->h_status, 16 * sizeof(int)));
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -1326,7 +1332,7 @@ fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t ha
         s->halo_mass_recv[sd] = nullptr;
         s->halo_node_recv[sd] = nullptr;
         if (!s->has_nb[sd]) continue;
-        CU_TRY(cudaMalloc(&s->mig_rec[sd], static_cast<int64_t>(s->mig_cap) * MIG_WORDS * sizeof(float)));
+        CU_TRY(cudaMalloc(&s->mig_rec[sd], (static_cast<int64_t>(s->mig_cap) + 1) * MIG_WORDS * sizeof(float)));
         CU_TRY(cudaMalloc(&s->halo_mass_recv[sd], plane2 * sizeof(float)));
         CU_TRY(cudaMalloc(&s->halo_node_recv[sd], plane2 * sizeof(float4)));
     }
@@ -1403,6 +1409,56 @@ fluid_status fluid_slab_accumulate(fluid_sim* s, int32_t side, int32_t kind) {
     return FLUID_OK;
 }
 
+// ---- migration with one synchronisation per substep ---------------------------------------------
+
+namespace {
+// headers of the two send buffers (word 0 = number of records behind it) and this rank's counters in one block
+__global__ void k_pack_status(const int* __restrict__ scal, const int* __restrict__ tile_tail, float* __restrict__ rec_lo,
+                              float* __restrict__ rec_hi, int* __restrict__ status) {
+    const int i = threadIdx.x;
+    if (i < 8) status[i] = scal[i];
+    if (i >= 8 && i < 12) status[i] = tile_tail[i - 8];
+    if (i == 12 && rec_lo) reinterpret_cast<int*>(rec_lo)[0] = scal[SCAL_MIG_LO];
+    if (i == 13 && rec_hi) reinterpret_cast<int*>(rec_hi)[0] = scal[SCAL_MIG_HI];
+}
+}  // namespace
+
+fluid_status fluid_slab_migrants_begin(fluid_sim* s, void** d_send_lower, void** d_send_upper) {
+    if (!s || !d_send_lower || !d_send_upper) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_migrants_begin: null argument");
+    if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_migrants_begin: fluid_slab_set has not been called");
+    CU_TRY(cudaSetDevice(s->device));
+    k_pack_status<<<1, 32, 0, s->stream>>>(s->scal, s->tile_base + s->geo.n_tiles, s->mig_rec[0], s->mig_rec[1], s->d_status);
+    ++s->launches;
+    CU_TRY(cudaGetLastError());
+    *d_send_lower = s->mig_rec[0];
+    *d_send_upper = s->mig_rec[1];
+    return FLUID_OK;
+}
+
+fluid_status fluid_slab_migrants_end(fluid_sim* s, const void* d_recv_lower, const void* d_recv_upper, int64_t n_out[2],
+                                     int64_t n_in[2]) {
+    if (!s || !n_out || !n_in) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_migrants_end: null argument");
+    if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_migrants_end: fluid_slab_set has not been called");
+    CU_TRY(cudaSetDevice(s->device));
+    int* h = s->h_status;
+    h[12] = h[13] = 0;
+    CU_TRY(cudaMemcpyAsync(h, s->d_status, 12 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (d_recv_lower) CU_TRY(cudaMemcpyAsync(h + 12, d_recv_lower, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (d_recv_upper) CU_TRY(cudaMemcpyAsync(h + 13, d_recv_upper, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));   // the one synchronisation of the substep
+    if (h[SCAL_MIG_OVERFLOW]) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_migrants_end: more particles left the slab in one substep than the migrant buffer holds");
+    n_out[0] = h[SCAL_MIG_LO];
+    n_out[1] = h[SCAL_MIG_HI];
+    n_in[0] = h[12];
+    n_in[1] = h[13];
+    if (s->n > 0 && s->counts_pending) {
+        // the buffer g2p + k_tail just wrote ends where this substep's sort put the dropped bucket
+        s->dropped_total += h[8 + 2] - h[8 + 1];
+        s->n = h[8 + 1];
+    }
+    return FLUID_OK;
+}
+
 // ---- peer-memory halo (NVLink P2P through CUDA IPC) ---------------------------------------------
 
 fluid_status fluid_slab_ipc_export(fluid_sim* s, void* handles) {
@@ -1463,8 +1519,8 @@ fluid_status fluid_slab_migrants(fluid_sim* s, void** d_lower, int64_t* n_lower,
     CU_TRY(cudaMemcpyAsync(h_base, s->tile_base + s->geo.n_tiles, sizeof(h_base), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));
     if (h_scal[SCAL_MIG_OVERFLOW]) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_migrants: more particles left the slab in one substep than the migrant buffer holds");
-    *d_lower = s->mig_rec[0];
-    *d_upper = s->mig_rec[1];
+    *d_lower = s->mig_rec[0] ? s->mig_rec[0] + MIG_WORDS : nullptr;
+    *d_upper = s->mig_rec[1] ? s->mig_rec[1] + MIG_WORDS : nullptr;
     *n_lower = h_scal[SCAL_MIG_LO];
     *n_upper = h_scal[SCAL_MIG_HI];
     if (s->n > 0 && s->counts_pending) {

@@ -135,6 +135,43 @@ class SlabDriver:
         self.migrated_out += sum(n_out)
         self.migrated_in += sum(n_in)
 
+    def migrate_fixed(self):
+        """Migration with one synchronisation: every neighbour pair swaps a fixed-size message (a header
+        record with the count, then up to `first_records` records) straight away; only then are the counts
+        read (engine.migrants_end, the substep's one host sync).  A count above `first_records` is known to
+        both sides and the rest follows in a second message."""
+        dist = self.dist
+        X = self.e.first_records
+        send = self.e.migrants_begin()                  # [lower, upper] full buffers (or None)
+        recv = [self.e.recv_buffer(side, X + 1) if self.nb[side] is not None else None for side in (0, 1)]
+        ops = []
+        for side in (0, 1):
+            if self.nb[side] is None:
+                continue
+            ops.append(dist.P2POp(dist.isend, send[side][: (X + 1) * MIG_WORDS], self.nb[side]))
+            ops.append(dist.P2POp(dist.irecv, recv[side][: (X + 1) * MIG_WORDS], self.nb[side]))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        n_out, n_in = self.e.migrants_end(recv)
+        ops = []
+        for side in (0, 1):
+            if self.nb[side] is None:
+                continue
+            if n_out[side] > X:
+                ops.append(dist.P2POp(dist.isend, send[side][(X + 1) * MIG_WORDS:(n_out[side] + 1) * MIG_WORDS], self.nb[side]))
+            if n_in[side] > X:
+                recv[side] = self.e.recv_buffer(side, n_in[side] + 1, keep=(X + 1) * MIG_WORDS)
+                ops.append(dist.P2POp(dist.irecv, recv[side][(X + 1) * MIG_WORDS:(n_in[side] + 1) * MIG_WORDS], self.nb[side]))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+        for side in (0, 1):
+            if self.nb[side] is not None and n_in[side]:
+                self.e.append(recv[side][MIG_WORDS:(n_in[side] + 1) * MIG_WORDS])
+        self.migrated_out += sum(n_out)
+        self.migrated_in += sum(n_in)
+
     def substep(self, mouse=None):
         self.e.phase(0, None)
         if self.p2p:
@@ -147,7 +184,11 @@ class SlabDriver:
         else:
             self.exchange_planes(1)
         self.e.phase(2, mouse)
-        self.migrate()      # always a send/recv pair with each neighbour: it also orders the next substep
+        # always a send/recv pair with each neighbour: it also orders the next substep
+        if hasattr(self.e, "migrants_begin"):
+            self.migrate_fixed()
+        else:
+            self.migrate()
 
 
 class _DevArray:
@@ -164,6 +205,8 @@ class CudaSlabEngine:
         self.pkg, self.sim = pkg, sim
         self.L = pkg.lib()
         self._recv = [None, None]
+        self._send_cap = None
+        self._send_views = None
 
     def _chk(self, st):
         if st != 0:
@@ -199,12 +242,36 @@ class CudaSlabEngine:
                 out.append(torch.empty(0, dtype=torch.float32, device="cuda"))
         return out
 
-    def recv_buffer(self, side, n):
+    def recv_buffer(self, side, n, keep: int = 0):
         import torch
         need = n * MIG_WORDS
         if self._recv[side] is None or self._recv[side].numel() < need:
+            old = self._recv[side]
             self._recv[side] = torch.empty(max(need, 1 << 16), dtype=torch.float32, device="cuda")
+            if keep and old is not None:
+                self._recv[side][:keep] = old[:keep]
         return self._recv[side][:need]
+
+    first_records = 4096      # records a neighbour pair exchanges before the counts are known
+
+    def migrants_begin(self):
+        import torch
+        lo, hi = C.c_void_p(), C.c_void_p()
+        self._chk(self.L.fluid_slab_migrants_begin(self.sim._h, C.byref(lo), C.byref(hi)))
+        if self._send_cap is None:
+            self._send_cap = 1 << 18       # fluid_slab_set's migrant buffer (records), + the header record
+        words = (self._send_cap + 1) * MIG_WORDS
+        key = (lo.value, hi.value)
+        if self._send_views is None or self._send_views[0] != key:      # the buffers only move with fluid_slab_set
+            self._send_views = (key, [torch.as_tensor(_DevArray(p.value, words), device="cuda") if p.value else None
+                                      for p in (lo, hi)])
+        return self._send_views[1]
+
+    def migrants_end(self, recv):
+        n_out, n_in = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+        ptrs = [C.c_void_p(t.data_ptr()) if t is not None else None for t in recv]
+        self._chk(self.L.fluid_slab_migrants_end(self.sim._h, ptrs[0], ptrs[1], n_out, n_in))
+        return [int(n_out[0]), int(n_out[1])], [int(n_in[0]), int(n_in[1])]
 
     def append(self, t):
         self._chk(self.L.fluid_slab_append(self.sim._h, C.c_void_p(t.data_ptr()), t.numel() // MIG_WORDS))

@@ -202,6 +202,19 @@ fluid_status fluid_slab_phase(fluid_sim* sim, int32_t phase, const float* mouse_
 fluid_status fluid_slab_accumulate(fluid_sim* sim, int32_t side, int32_t kind);
 /* After phase 2: device pointers to the packed records (17 words: 16 f32 + id) of the particles that
  * left through the lower / upper face and their counts.  Synchronises the stream. */
+/* Migration with ONE synchronisation per substep.  Phase 2 leaves the records of the particles that left
+ * through a face behind a one-record header whose first word is their number (int32).
+ *   fluid_slab_migrants_begin  writes the headers; returns the two send buffers (header + records, NULL
+ *                              where there is no neighbour).  The caller exchanges a fixed number of
+ *                              records (+ the header) with each neighbour without knowing the counts.
+ *   fluid_slab_migrants_end    the synchronisation: reads this rank's counters and the headers of the two
+ *                              received buffers (NULL where there is none); n_out / n_in = records sent /
+ *                              received through [lower, upper]; cuts the migrated tail off this rank.
+ * If a count exceeds what was exchanged, both sides know it and exchange the rest; then
+ * fluid_slab_append(received + one record, n_in). */
+fluid_status fluid_slab_migrants_begin(fluid_sim* sim, void** d_send_lower, void** d_send_upper);
+fluid_status fluid_slab_migrants_end(fluid_sim* sim, const void* d_recv_lower, const void* d_recv_upper,
+                                     int64_t n_out[2], int64_t n_in[2]);
 /* Peer-memory halo (NVLink P2P; one process per GPU, arrays mapped through CUDA IPC).  With the
  * neighbours' arrays imported, "p2g 1" and "p2g 2" add every deposit that falls into the two node planes
  * an interface shares into the neighbour's copy as well (red.global.add over NVLink, inside the tile
