@@ -483,10 +483,34 @@ def main():
     ap.add_argument("--scene", default="", help="scene function in scenes.py (default: dam break for --gpus)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_ours(args)
+    # stdout carries exactly one JSON line: anything a library writes to file descriptor 1 meanwhile (NCCL's
+    # version banner comes from C code) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    lines = []
+    import builtins
+    real_print = builtins.print
+
+    def capture(*a, **k):
+        if k.get("file") in (None, sys.stdout) and len(a) == 1 and isinstance(a[0], str) and a[0].startswith("{"):
+            lines.append(a[0])
+        else:
+            real_print(*a, **k)
+
+    builtins.print = capture
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_ours(args)
+    finally:
+        builtins.print = real_print
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    for ln in lines:
+        print(ln, flush=True)
 
 
 if __name__ == "__main__":
