@@ -106,6 +106,8 @@ SIGNATURES = {
     "fluid_slab_migrants_begin": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p)]),
     "fluid_slab_migrants_end": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fluid_slab_ipc_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "fluid_slab_peer_barrier": (C.c_int, [C.c_void_p]),
+    "fluid_slab_append_received": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64]),
     "fluid_slab_ipc_import": (C.c_int, [C.c_void_p, C.c_int32, C.c_void_p]),
 }
 

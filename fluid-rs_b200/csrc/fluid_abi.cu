@@ -101,7 +101,11 @@ struct fluid_sim {
     int2* tile_info = nullptr;   // per tile: {windows W (0 = plain cell order, < 0 = no class merge), tile-list entry}
     unsigned char* tab = nullptr;   // per tile-list entry: TAB_BYTES of class-in-window counts (k_tile_tables)
     PeerHalo peer{};             // neighbours' grids mapped through CUDA IPC (peer-memory halo), or all null
-    void* peer_base[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};   // opened IPC mappings
+    void* peer_base[2][6] = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
+                             {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};   // opened IPC mappings
+    float* mig_recv[2] = {nullptr, nullptr};   // records the neighbours write here over NVLink (header record first)
+    int* flags = nullptr;        // [0], [1]: arrival flags the lower / upper neighbour writes (peer barrier); [2]: time-out
+    int barrier_epoch = 0;
     bool p2p = false;            // deposits into the shared node planes go to the neighbour directly
     int* gz = nullptr;           // per tile: substep number in which k_g2p_tiled zeroed its node-mass block
     int epoch = 0;               // tiled substeps run so far (compared with gz)
@@ -494,8 +498,12 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             }
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
             ++s->epoch;
-            k_mass_tiled<<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                  s->gmass, s->grid, s->peer);
+            if (s->p2p)
+                k_mass_tiled<true><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
+                                                                                            s->gmass, s->grid, s->peer);
+            else
+                k_mass_tiled<false><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
+                                                                                             s->gmass, s->grid, s->peer);
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
@@ -509,8 +517,12 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     }
     if (phases & 2) {
         Particles q = s->buf[s->cur];
-        if (tiled)
-            k_p2g_tiled<<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
+        if (tiled && s->p2p)
+            k_p2g_tiled<true><<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
+                s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
+                dbg ? dbg->pressure : nullptr, s->peer);
+        else if (tiled)
+            k_p2g_tiled<false><<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
                 s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
                 dbg ? dbg->pressure : nullptr, s->peer);
         else
@@ -527,8 +539,11 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             // state at the sorted slots of the other buffer (no reorder pass)
             Particles qn = s->buf[s->cur ^ 1];
             SlabBufs sb{};
-            sb.rec[0] = s->mig_rec[0] ? s->mig_rec[0] + MIG_WORDS : nullptr;   // behind the header record
-            sb.rec[1] = s->mig_rec[1] ? s->mig_rec[1] + MIG_WORDS : nullptr;
+            // behind the header record; with the neighbours' buffers mapped the records go there directly (NVLink)
+            for (int sd = 0; sd < 2; ++sd) {
+                float* dst = s->peer.mig[sd] ? s->peer.mig[sd] : s->mig_rec[sd];
+                sb.rec[sd] = dst ? dst + MIG_WORDS : nullptr;
+            }
             sb.cap = s->mig_cap;
             k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
                 s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch);
@@ -733,14 +748,15 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
 
-    cudaFuncSetAttribute(k_p2g_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
+    cudaFuncSetAttribute(k_p2g_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
+    cudaFuncSetAttribute(k_p2g_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
     {   // persistent grids: one wave of resident CTAs per kernel (148 SMs x occupancy)
         cudaDeviceProp prop{};
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
         int occ = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mass_tiled, T3::THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mass_tiled<false>, T3::THREADS, 0);
         s->grid_mass = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_tiled, T3::THREADS, sizeof(P2GSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_tiled<false>, T3::THREADS, sizeof(P2GSmem));
         s->grid_p2g = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled<true>, T3::THREADS, 0);
         s->grid_g2p = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
@@ -752,13 +768,15 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
 
 // unmap a neighbour's arrays (peer-memory halo)
 static void close_peer(fluid_sim* s, int side) {
-    for (int k = 0; k < 4; ++k) {
+    for (int k = 0; k < 6; ++k) {
         if (s->peer_base[side][k]) cudaIpcCloseMemHandle(s->peer_base[side][k]);
         s->peer_base[side][k] = nullptr;
     }
     s->peer.grid[side] = nullptr;
     s->peer.gmass[side] = nullptr;
     s->peer.dirty[side][0] = s->peer.dirty[side][1] = nullptr;
+    s->peer.mig[side] = nullptr;
+    s->peer.flag[side] = nullptr;
     s->p2p = s->peer.grid[0] || s->peer.grid[1];
 }
 
@@ -793,6 +811,9 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->tab);
     cudaFree(s->d_status);
     if (s->h_status) cudaFreeHost(s->h_status);
+    cudaFree(s->flags);
+    cudaFree(s->mig_recv[0]);
+    cudaFree(s->mig_recv[1]);
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -1324,6 +1345,9 @@ fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t ha
     if (s->mig_cap == 0) s->mig_cap = 1 << 18;
     if (!s->d_status) CU_TRY(cudaMalloc(&s->d_status, 16 * sizeof(int)));
     if (!s->h_status) CU_TRY(cudaMallocHost(&s->h_status, 16 * sizeof(int)));
+    if (!s->flags) CU_TRY(cudaMalloc(&s->flags, 8 * sizeof(int)));
+    CU_TRY(cudaMemsetAsync(s->flags, 0, 8 * sizeof(int), s->stream));
+    s->barrier_epoch = 0;
     for (int sd = 0; sd < 2; ++sd) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
@@ -1333,6 +1357,10 @@ fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t ha
         s->halo_node_recv[sd] = nullptr;
         if (!s->has_nb[sd]) continue;
         CU_TRY(cudaMalloc(&s->mig_rec[sd], (static_cast<int64_t>(s->mig_cap) + 1) * MIG_WORDS * sizeof(float)));
+        cudaFree(s->mig_recv[sd]);
+        s->mig_recv[sd] = nullptr;
+        CU_TRY(cudaMalloc(&s->mig_recv[sd], (static_cast<int64_t>(s->mig_cap) + 1) * MIG_WORDS * sizeof(float)));
+        CU_TRY(cudaMemsetAsync(s->mig_recv[sd], 0, MIG_WORDS * sizeof(float), s->stream));
         CU_TRY(cudaMalloc(&s->halo_mass_recv[sd], plane2 * sizeof(float)));
         CU_TRY(cudaMalloc(&s->halo_node_recv[sd], plane2 * sizeof(float4)));
     }
@@ -1427,7 +1455,8 @@ fluid_status fluid_slab_migrants_begin(fluid_sim* s, void** d_send_lower, void**
     if (!s || !d_send_lower || !d_send_upper) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_migrants_begin: null argument");
     if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_migrants_begin: fluid_slab_set has not been called");
     CU_TRY(cudaSetDevice(s->device));
-    k_pack_status<<<1, 32, 0, s->stream>>>(s->scal, s->tile_base + s->geo.n_tiles, s->mig_rec[0], s->mig_rec[1], s->d_status);
+    k_pack_status<<<1, 32, 0, s->stream>>>(s->scal, s->tile_base + s->geo.n_tiles, s->peer.mig[0] ? s->peer.mig[0] : s->mig_rec[0],
+                                           s->peer.mig[1] ? s->peer.mig[1] : s->mig_rec[1], s->d_status);
     ++s->launches;
     CU_TRY(cudaGetLastError());
     *d_send_lower = s->mig_rec[0];
@@ -1443,9 +1472,15 @@ fluid_status fluid_slab_migrants_end(fluid_sim* s, const void* d_recv_lower, con
     int* h = s->h_status;
     h[12] = h[13] = 0;
     CU_TRY(cudaMemcpyAsync(h, s->d_status, 12 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    // with the peer-memory migration the neighbours have written into this rank's own receive buffers
+    if (!d_recv_lower && s->peer.mig[0]) d_recv_lower = s->mig_recv[0];
+    if (!d_recv_upper && s->peer.mig[1]) d_recv_upper = s->mig_recv[1];
     if (d_recv_lower) CU_TRY(cudaMemcpyAsync(h + 12, d_recv_lower, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     if (d_recv_upper) CU_TRY(cudaMemcpyAsync(h + 13, d_recv_upper, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    if (s->flags) CU_TRY(cudaMemcpyAsync(h + 14, s->flags + 2, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));   // the one synchronisation of the substep
+    if (s->flags && h[14]) return fail(FLUID_ERR_STATE, "fluid_slab_migrants_end: a peer barrier timed out (a neighbour rank stopped)");
+    if (h[12] > s->mig_cap || h[13] > s->mig_cap) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_migrants_end: a neighbour handed over more particles than the migrant buffer holds");
     if (h[SCAL_MIG_OVERFLOW]) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_migrants_end: more particles left the slab in one substep than the migrant buffer holds");
     n_out[0] = h[SCAL_MIG_LO];
     n_out[1] = h[SCAL_MIG_HI];
@@ -1461,16 +1496,62 @@ fluid_status fluid_slab_migrants_end(fluid_sim* s, const void* d_recv_lower, con
 
 // ---- peer-memory halo (NVLink P2P through CUDA IPC) ---------------------------------------------
 
+namespace {
+// Signal both neighbours (a store into their memory over NVLink) and wait for their signals.  Everything
+// this rank's earlier kernels wrote into the neighbours' arrays is visible to them once they see the flag.
+__global__ void k_peer_barrier(int* __restrict__ my_flags, int* peer_lo, int* peer_hi, int epoch) {
+    if (threadIdx.x != 0) return;
+    __threadfence_system();
+    if (peer_lo) *reinterpret_cast<volatile int*>(peer_lo) = epoch;
+    if (peer_hi) *reinterpret_cast<volatile int*>(peer_hi) = epoch;
+    __threadfence_system();
+    const long long t0 = clock64();
+    volatile int* f = my_flags;
+    while ((peer_lo && f[0] < epoch) || (peer_hi && f[1] < epoch)) {
+        if (clock64() - t0 > (1LL << 34)) {   // seconds: the neighbour is gone; report instead of hanging
+            my_flags[2] = 1;
+            break;
+        }
+        __nanosleep(64);
+    }
+    __threadfence_system();
+}
+}  // namespace
+
+fluid_status fluid_slab_peer_barrier(fluid_sim* s) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_peer_barrier: null handle");
+    if (!s->geo.slab_on || !s->p2p) return fail(FLUID_ERR_STATE, "fluid_slab_peer_barrier: no neighbour is mapped");
+    CU_TRY(cudaSetDevice(s->device));
+    ++s->barrier_epoch;
+    k_peer_barrier<<<1, 32, 0, s->stream>>>(s->flags, s->peer.flag[0], s->peer.flag[1], s->barrier_epoch);
+    ++s->launches;
+    CU_TRY(cudaGetLastError());
+    return FLUID_OK;
+}
+
+fluid_status fluid_slab_append_received(fluid_sim* s, int32_t side, int64_t n) {
+    if (!s || side < 0 || side > 1 || n < 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_append_received: bad argument");
+    if (!s->geo.slab_on || !s->mig_recv[side]) return fail(FLUID_ERR_STATE, "fluid_slab_append_received: no neighbour on that side");
+    if (n > s->mig_cap) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_append_received: more records than the buffer holds");
+    return fluid_slab_append(s, s->mig_recv[side] + MIG_WORDS, n);
+}
+
 fluid_status fluid_slab_ipc_export(fluid_sim* s, void* handles) {
     if (!s || !handles) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_ipc_export: null argument");
     if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_ipc_export: fluid_slab_set has not been called");
     CU_TRY(cudaSetDevice(s->device));
-    static_assert(FLUID_IPC_BYTES == 4 * sizeof(cudaIpcMemHandle_t), "FLUID_IPC_BYTES");
+    static_assert(FLUID_IPC_BYTES == 7 * sizeof(cudaIpcMemHandle_t), "FLUID_IPC_BYTES");
     cudaIpcMemHandle_t* h = static_cast<cudaIpcMemHandle_t*>(handles);
+    std::memset(h, 0, FLUID_IPC_BYTES);
     CU_TRY(cudaIpcGetMemHandle(&h[0], s->grid));
     CU_TRY(cudaIpcGetMemHandle(&h[1], s->gmass));
     CU_TRY(cudaIpcGetMemHandle(&h[2], s->dirty[0]));
     CU_TRY(cudaIpcGetMemHandle(&h[3], s->dirty[1]));
+    if (s->mig_recv[0]) CU_TRY(cudaIpcGetMemHandle(&h[4], s->mig_recv[0]));   // what the lower neighbour writes
+    if (s->mig_recv[1]) CU_TRY(cudaIpcGetMemHandle(&h[5], s->mig_recv[1]));   // what the upper neighbour writes
+    CU_TRY(cudaIpcGetMemHandle(&h[6], s->flags));
+    CU_TRY(cudaMemsetAsync(s->flags, 0, 8 * sizeof(int), s->stream));
+    s->barrier_epoch = 0;
     // The neighbours may deposit into this rank's planes before its own first substep gets to wipe the
     // arrays: wipe now (the caller puts a barrier between the imports and the first substep).
     const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
@@ -1494,8 +1575,11 @@ fluid_status fluid_slab_ipc_import(fluid_sim* s, int32_t side, const void* handl
     }
     if (!s->has_nb[side]) return fail(FLUID_ERR_STATE, "fluid_slab_ipc_import: no neighbour on that side");
     const cudaIpcMemHandle_t* h = static_cast<const cudaIpcMemHandle_t*>(handles);
-    for (int k = 0; k < 4; ++k) {
-        cudaError_t e = cudaIpcOpenMemHandle(&s->peer_base[side][k], h[k], cudaIpcMemLazyEnablePeerAccess);
+    // of the neighbour's two receive buffers this rank writes the one facing it: the lower neighbour's
+    // "from above" (handle 5), the upper neighbour's "from below" (handle 4)
+    const int which[6] = {0, 1, 2, 3, side == 0 ? 5 : 4, 6};
+    for (int k = 0; k < 6; ++k) {
+        cudaError_t e = cudaIpcOpenMemHandle(&s->peer_base[side][k], h[which[k]], cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) {
             close_peer(s, side);
             return fail(FLUID_ERR_CUDA, cudaGetErrorString(e));
@@ -1505,6 +1589,9 @@ fluid_status fluid_slab_ipc_import(fluid_sim* s, int32_t side, const void* handl
     s->peer.gmass[side] = static_cast<float*>(s->peer_base[side][1]);
     s->peer.dirty[side][0] = static_cast<unsigned char*>(s->peer_base[side][2]);
     s->peer.dirty[side][1] = static_cast<unsigned char*>(s->peer_base[side][3]);
+    s->peer.mig[side] = static_cast<float*>(s->peer_base[side][4]);
+    // this rank is the neighbour's upper (side 0) or lower (side 1) neighbour: its arrival flag there
+    s->peer.flag[side] = static_cast<int*>(s->peer_base[side][5]) + (side == 0 ? 1 : 0);
     s->p2p = true;
     return FLUID_OK;
 }

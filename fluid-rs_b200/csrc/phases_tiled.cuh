@@ -246,6 +246,7 @@ __device__ __forceinline__ void zero_own_block(const Geo& g, const TileCtx& tc, 
 
 // ---- p2g 1: node masses ---------------------------------------------------------------------
 
+template <bool PEER>   // PEER: slab run with the neighbours' arrays mapped (deposits into the shared planes go there too)
 __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
@@ -309,8 +310,8 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                 }
         }
         // flush: lane -> footprint column c = lane + 32*it (100 columns), six nodes along z
-        float* peer_lo = (g.slab_on && tc.c0[2] == g.slab_lo) ? ph.gmass[0] : nullptr;              // warp-uniform
-        float* peer_hi = (g.slab_on && tc.c0[2] + T3::Z == g.slab_hi) ? ph.gmass[1] : nullptr;
+        float* peer_lo = (PEER && tc.c0[2] == g.slab_lo) ? ph.gmass[0] : nullptr;              // warp-uniform
+        float* peer_hi = (PEER && tc.c0[2] + T3::Z == g.slab_hi) ? ph.gmass[1] : nullptr;
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int c = lane + 32 * it;
@@ -327,14 +328,14 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                             const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
                             atomicAdd(&gmass[gi], m6[k]);
                             // the two node planes a slab face shares: the neighbour's copy as well (NVLink)
-                            if (k < 2 && peer_lo) atomicAdd(&peer_lo[gi], m6[k]);
-                            if (k >= 4 && peer_hi) atomicAdd(&peer_hi[gi], m6[k]);
+                            if (PEER && k < 2 && peer_lo) atomicAdd(&peer_lo[gi], m6[k]);
+                            if (PEER && k >= 4 && peer_hi) atomicAdd(&peer_hi[gi], m6[k]);
                         }
                     }
                 }
             }
         }
-        if (peer_lo || peer_hi) __threadfence_system();
+        if (PEER && (peer_lo || peer_hi)) __threadfence_system();
         __syncwarp();
     }
 }
@@ -361,6 +362,7 @@ __device__ __forceinline__ void load_prec(const Particles& q, int i, bool ok, PR
     }
 }
 
+template <bool PEER>
 __global__ void __launch_bounds__(T3::THREADS, 4)
 k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
@@ -504,23 +506,32 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 }
             }
         }
-        float4* peer_lo = (g.slab_on && tc.c0[2] == g.slab_lo) ? ph.grid[0] : nullptr;              // warp-uniform
-        float4* peer_hi = (g.slab_on && tc.c0[2] + T3::Z == g.slab_hi) ? ph.grid[1] : nullptr;
 #pragma unroll 4
         for (int it = 0; it < FOOT_STEPS; ++it) {
             int gi;
             const int sl = foot_step(g, tc, fl, it, gi);
             if (gi >= 0) {
                 const float4 v = acc[sl];
-                if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) {
-                    atomicAdd(&grid[gi], v);
-                    // the two node planes a slab face shares: the neighbour's copy as well (NVLink)
-                    if (sl < 2 * T3::PLANE && peer_lo) atomicAdd(&peer_lo[gi], v);
-                    if (sl >= 4 * T3::PLANE && peer_hi) atomicAdd(&peer_hi[gi], v);
-                }
+                if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) atomicAdd(&grid[gi], v);
             }
         }
-        if (peer_lo || peer_hi) __threadfence_system();
+        if (PEER) {
+            // the two node planes a slab face shares: the neighbour's copy as well (red.add over NVLink)
+            float4* peer_lo = tc.c0[2] == g.slab_lo ? ph.grid[0] : nullptr;              // warp-uniform
+            float4* peer_hi = tc.c0[2] + T3::Z == g.slab_hi ? ph.grid[1] : nullptr;
+            if (peer_lo || peer_hi) {
+                for (int it = 0; it < FOOT_STEPS; ++it) {
+                    int gi;
+                    const int sl = foot_step(g, tc, fl, it, gi);
+                    if (gi < 0) continue;
+                    float4* dst = sl < 2 * T3::PLANE ? peer_lo : (sl >= 4 * T3::PLANE ? peer_hi : nullptr);
+                    if (!dst) continue;
+                    const float4 v = acc[sl];
+                    if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) atomicAdd(&dst[gi], v);
+                }
+                __threadfence_system();
+            }
+        }
         __syncwarp();
     }
 }

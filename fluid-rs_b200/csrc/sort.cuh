@@ -52,6 +52,8 @@ struct PeerHalo {
     float4* grid[2];            // neighbour's node records (same geometry, same indexing) or nullptr
     float* gmass[2];            // neighbour's node masses
     unsigned char* dirty[2][2]; // neighbour's two dirty-block flag arrays
+    float* mig[2];              // neighbour's receive buffer for the particles this rank hands over (header record first)
+    int* flag[2];               // neighbour's arrival flag for this rank (peer barrier)
 };
 
 constexpr int TILE_CELLS = 256;

@@ -172,17 +172,33 @@ class SlabDriver:
         self.migrated_out += sum(n_out)
         self.migrated_in += sum(n_in)
 
+    def migrate_peer(self):
+        """Peer-memory migration: phase 2 wrote the leavers' records into the neighbours' receive buffers,
+        migrants_begin adds the count headers, a peer barrier makes them visible; the one host
+        synchronisation of the substep reads the counts."""
+        self.e.migrants_begin()
+        self.e.peer_barrier()
+        n_out, n_in = self.e.migrants_end([None, None])
+        for side in (0, 1):
+            if self.nb[side] is not None and n_in[side]:
+                self.e.append_received(side, n_in[side])
+        self.migrated_out += sum(n_out)
+        self.migrated_in += sum(n_in)
+
     def substep(self, mouse=None):
+        if self.p2p:
+            # nothing here goes through the process group: deposits, records and barriers are stores over NVLink
+            self.e.phase(0, None)
+            self.e.peer_barrier()
+            self.e.phase(1, None)
+            self.e.peer_barrier()
+            self.e.phase(2, mouse)
+            self.migrate_peer()      # its barrier also orders the next substep's deposits behind this one's reads
+            return
         self.e.phase(0, None)
-        if self.p2p:
-            self.neighbour_barrier()
-        else:
-            self.exchange_planes(0)
+        self.exchange_planes(0)
         self.e.phase(1, None)
-        if self.p2p:
-            self.neighbour_barrier()
-        else:
-            self.exchange_planes(1)
+        self.exchange_planes(1)
         self.e.phase(2, mouse)
         # always a send/recv pair with each neighbour: it also orders the next substep
         if hasattr(self.e, "migrants_begin"):
@@ -207,6 +223,7 @@ class CudaSlabEngine:
         self._recv = [None, None]
         self._send_cap = None
         self._send_views = None
+        self.peer_memory = False      # set by SlabSimulation once the neighbours' buffers are mapped
 
     def _chk(self, st):
         if st != 0:
@@ -258,6 +275,8 @@ class CudaSlabEngine:
         import torch
         lo, hi = C.c_void_p(), C.c_void_p()
         self._chk(self.L.fluid_slab_migrants_begin(self.sim._h, C.byref(lo), C.byref(hi)))
+        if self.peer_memory:
+            return None
         if self._send_cap is None:
             self._send_cap = 1 << 18       # fluid_slab_set's migrant buffer (records), + the header record
         words = (self._send_cap + 1) * MIG_WORDS
@@ -266,6 +285,12 @@ class CudaSlabEngine:
             self._send_views = (key, [torch.as_tensor(_DevArray(p.value, words), device="cuda") if p.value else None
                                       for p in (lo, hi)])
         return self._send_views[1]
+
+    def peer_barrier(self):
+        self._chk(self.L.fluid_slab_peer_barrier(self.sim._h))
+
+    def append_received(self, side, n):
+        self._chk(self.L.fluid_slab_append_received(self.sim._h, side, n))
 
     def migrants_end(self, recv):
         n_out, n_in = (C.c_int64 * 2)(), (C.c_int64 * 2)()
@@ -305,14 +330,16 @@ class SlabSimulation:
         if p2p:
             p2p = self._map_neighbours(L, dist, rank, world, device)
         self.p2p = p2p
-        self.driver = SlabDriver(CudaSlabEngine(pkg, self.sim), rank, world, dist, device=f"cuda:{device}", p2p=p2p)
+        engine = CudaSlabEngine(pkg, self.sim)
+        engine.peer_memory = p2p
+        self.driver = SlabDriver(engine, rank, world, dist, device=f"cuda:{device}", p2p=p2p)
         self.iterations = int(self.sim.config.iterations)
 
     def _map_neighbours(self, L, dist, rank, world, device) -> bool:
         """Peer-memory halo set-up: all-gather the CUDA IPC handles of every rank's arrays and map the two
         neighbours'.  Falls back to plane exchanges (on every rank) if any mapping fails."""
         import torch
-        IPC_BYTES = 256
+        IPC_BYTES = 448
         mine = (C.c_ubyte * IPC_BYTES)()
         ok = L.fluid_slab_ipc_export(self.sim._h, C.cast(mine, C.c_void_p)) == 0
         t = torch.tensor(list(bytes(mine)), dtype=torch.uint8, device=f"cuda:{device}")

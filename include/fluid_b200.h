@@ -225,8 +225,17 @@ fluid_status fluid_slab_migrants_end(fluid_sim* sim, const void* d_recv_lower, c
  *                          neighbours may deposit, i.e. before the barrier that ends the set-up)
  *   fluid_slab_ipc_import  map the arrays of the neighbour on `side` (0 = lower, 1 = upper); NULL unmaps.
  * fluid_set_rect reallocates the arrays: export / import again after it. */
-#define FLUID_IPC_BYTES 256
+#define FLUID_IPC_BYTES 448
 fluid_status fluid_slab_ipc_export(fluid_sim* sim, void* handles);
+/* With the neighbours mapped nothing in the substep loop goes through a communication library:
+ *   fluid_slab_peer_barrier     one tiny kernel: store this rank's epoch into both neighbours' flags over
+ *                               NVLink, wait for theirs (time-out after seconds -> error at migrants_end)
+ *   phase 2                     writes the leavers' records straight into the neighbour's receive buffer
+ *   fluid_slab_migrants_begin   writes the count headers there too; then a peer barrier
+ *   fluid_slab_migrants_end     (NULL, NULL): reads the headers of this rank's own receive buffers
+ *   fluid_slab_append_received  joins the n records the neighbour on `side` wrote */
+fluid_status fluid_slab_peer_barrier(fluid_sim* sim);
+fluid_status fluid_slab_append_received(fluid_sim* sim, int32_t side, int64_t n);
 fluid_status fluid_slab_ipc_import(fluid_sim* sim, int32_t side, const void* handles);
 fluid_status fluid_slab_migrants(fluid_sim* sim, void** d_lower, int64_t* n_lower, void** d_upper,
                                  int64_t* n_upper);
