@@ -232,6 +232,16 @@ k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const
     }
 }
 
+// Reductions into a neighbour GPU's memory (mapped through CUDA IPC): system scope, no return value
+// (SASS REDG; a plain atomicAdd on these pointers compiled to the returning ATOMG and slowed the whole flush).
+__device__ __forceinline__ void red_add_sys(float4* p, const float4 v) {
+    asm volatile("red.relaxed.sys.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void red_add_sys(float* p, const float v) {
+    asm volatile("red.relaxed.sys.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
 // Zero the tile's own 8x8x4 node block of `arr` (the nodes with the tile's cell indices).
 template <typename T>
 __device__ __forceinline__ void zero_own_block(const Geo& g, const TileCtx& tc, int lane, T* __restrict__ arr) {
@@ -328,14 +338,15 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                             const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
                             atomicAdd(&gmass[gi], m6[k]);
                             // the two node planes a slab face shares: the neighbour's copy as well (NVLink)
-                            if (PEER && k < 2 && peer_lo) atomicAdd(&peer_lo[gi], m6[k]);
-                            if (PEER && k >= 4 && peer_hi) atomicAdd(&peer_hi[gi], m6[k]);
+                            if (PEER && k < 2 && peer_lo) red_add_sys(&peer_lo[gi], m6[k]);
+                            if (PEER && k >= 4 && peer_hi) red_add_sys(&peer_hi[gi], m6[k]);
                         }
                     }
                 }
             }
         }
-        if (PEER && (peer_lo || peer_hi)) __threadfence_system();
+        // no fence here: the kernel boundary and the system fences of k_peer_barrier order these deposits
+        // before the flag the neighbour waits for
         __syncwarp();
     }
 }
@@ -527,9 +538,8 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                     float4* dst = sl < 2 * T3::PLANE ? peer_lo : (sl >= 4 * T3::PLANE ? peer_hi : nullptr);
                     if (!dst) continue;
                     const float4 v = acc[sl];
-                    if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) atomicAdd(&dst[gi], v);
+                    if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) red_add_sys(&dst[gi], v);
                 }
-                __threadfence_system();
             }
         }
         __syncwarp();
