@@ -66,7 +66,46 @@ class MockEngine:
         self.rec = np.concatenate([self.rec, t.numpy().reshape(-1, 17)])
 
 
-def _worker(rank, world, port, result_dir):
+class FixedMessageEngine(MockEngine):
+    """The same mock behind the one-synchronisation migration interface (migrants_begin / migrants_end):
+    every neighbour pair first swaps a fixed-size message — a header record with the count, then up to
+    `first_records` records — and only then learns the counts; the rest follows in a second message."""
+
+    first_records = 8          # small, so that the second message is exercised
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self._recv = [None, None]
+        self._n_out = [0, 0]
+
+    def migrants_begin(self):
+        out = self.migrants()
+        bufs = []
+        for side, t in enumerate(out):
+            n = t.numel() // 17
+            self._n_out[side] = n
+            buf = torch.zeros((max(n, self.first_records) + 1) * 17, dtype=torch.float32)
+            buf[:1].view(torch.int32)[0] = n          # header: the count as an int32 in the first word
+            buf[17:17 + n * 17] = t
+            has_nb = (side == 0 and self.rank > 0) or (side == 1 and self.rank < self.world - 1)
+            bufs.append(buf if has_nb else None)
+        return bufs
+
+    def recv_buffer(self, side, n, keep: int = 0):
+        need = n * 17
+        if self._recv[side] is None or self._recv[side].numel() < need:
+            old = self._recv[side]
+            self._recv[side] = torch.zeros(need, dtype=torch.float32)
+            if keep and old is not None:
+                self._recv[side][:keep] = old[:keep]
+        return self._recv[side][:need]
+
+    def migrants_end(self, recv):
+        n_in = [int(t[:1].view(torch.int32)[0]) if t is not None else 0 for t in recv]
+        return list(self._n_out), n_in
+
+
+def _worker(rank, world, port, result_dir, engine="MockEngine"):
     sys.path.insert(0, str(ROOT))
     import fluidpkg
     slab = fluidpkg.load().slab
@@ -80,7 +119,7 @@ def _worker(rank, world, port, result_dir):
     rec[:, 16] = np.arange(n, dtype=np.int32).view(np.float32)
     lo, hi = slabs[rank]
     mine = (np.floor(rec[:, 2]) >= lo) & (np.floor(rec[:, 2]) < hi)
-    eng = MockEngine(rank, world, slabs, rec[mine].copy())
+    eng = globals()[engine](rank, world, slabs, rec[mine].copy())
     drv = slab.SlabDriver(eng, rank, world, dist, device="cpu")
     for _ in range(12):
         drv.substep()
@@ -95,10 +134,11 @@ def _worker(rank, world, port, result_dir):
 
 
 @pytest.mark.timeout(120)
-def test_slab_protocol_world2_gloo(tmp_path):
+@pytest.mark.parametrize("engine", ["MockEngine", "FixedMessageEngine"])
+def test_slab_protocol_world2_gloo(tmp_path, engine):
     world = 2
     port = _free_port()
-    mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, str(tmp_path), engine), nprocs=world, join=True)
     r = [np.load(tmp_path / f"r{k}.npz") for k in range(world)]
     ids = np.concatenate([x["ids"] for x in r])
     assert sorted(ids.tolist()) == list(range(4000))          # every particle exactly once
