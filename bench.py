@@ -264,6 +264,17 @@ def run_ours(args):
     sim.profile(False)
     launches = sim.launch_count() - launches0
     clocks = sampler.stop()
+    # occupancy of the last timed substep (from the engine's tile list; outside the timed region)
+    tiles_now = sim.debug_tiles()
+    tiles_now = tiles_now[tiles_now[:, 2] > 0]
+    occupancy = None
+    if len(tiles_now):
+        n_t, w_t = tiles_now[:, 2].astype(np.int64), tiles_now[:, 3].astype(np.int64)
+        occupancy = {"active_tiles": int(len(tiles_now)), "particles_per_tile": float(n_t.mean()),
+                     "window_fill": float(n_t.sum() / (32.0 * w_t.sum())),
+                     "A_over_N": float(len(tiles_now) * 256 / sc.n),
+                     "A_note": "A = nodes of the 8x8x4 blocks of the tiles that hold particles (SURVEY.md 8d fixes A/N = 1 "
+                               "for the roofline; the rim the stencils reach adds about a quarter)"}
     counts = sim.particle_counts()
     assert counts["active"] == sc.n, counts
     value = sc.n * iters * args.steps / (ms * 1e-3)
@@ -282,6 +293,7 @@ def run_ours(args):
         "limiter": "shared-memory (LSU) pipe, not HBM: ncu l1tex data-pipe wavefronts 79% of peak, dram 23% (profiles/r01_ncu_full_16M_v19.csv)",
         "step_frac": value * ALG_BYTES_STEP / 1e9 / peak,
         "per_phase_ms": per_phase_ms,
+        "occupancy": occupancy,
     }
 
     # ---- end to end through the C ABI with host buffers -----------------------------------------
@@ -303,6 +315,24 @@ def run_ours(args):
     e2e_s = time.perf_counter() - t0
     e2e_value = sc.n * iters * e2e_steps / e2e_s
     rec_bytes = sc.n * rf * 4
+
+    # ---- the reference's own main loop through the API: step(mouse) then the 80x40 frame `draw` prints
+    # (3d:541-560): the mouse position goes up, the frame's bin counts come back, the state stays resident
+    def loop_step(k):
+        sim.step(mouse_pos=(0.25 * sc.rect_max[0] + k, 0.5 * sc.rect_max[1]))
+        return sim.frame_counts(viewport=(float(sc.rect_max[0]), float(sc.rect_max[1])))
+
+    loop_step(0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        frame = loop_step(k + 1)
+    torch.cuda.synchronize()
+    loop_s = time.perf_counter() - t0
+    e2e_loop = {"value": sc.n * iters * e2e_steps / loop_s, "unit": UNIT, "h2d_bytes_per_step": 8,
+                "d2h_bytes_per_step": int(frame.size * 4), "steps": e2e_steps,
+                "what": "the reference's main loop: step(mouse position from the host) + the 80x40 frame's bin counts "
+                        "read back (draw's binning runs on the device); particle state stays resident"}
 
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
@@ -327,6 +357,7 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes,
                 "d2h_bytes_per_step": rec_bytes, "steps": e2e_steps,
                 "what": "clear + add_particles(pinned host records) + step() + read_particles(all records)"},
+        "e2e_main_loop": e2e_loop,
         "gpu_launches": launches,
         "clocks": clocks,
         "ms_per_substep": ms / args.steps / iters,
