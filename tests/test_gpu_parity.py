@@ -451,6 +451,47 @@ def test_two_gpu_slab_run_matches_single_gpu():
     assert r.returncode == 0 and "SLAB CHECK OK" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]
 
 
+def test_slab_entry_points_on_one_gpu(pkg, scenes):
+    """The multi-GPU entry points on a single device: state errors before fluid_slab_set / without a
+    mapped neighbour, and a one-slab run driven phase by phase (with the one-synchronisation migration
+    calls) that must reproduce step()."""
+    import ctypes as C
+    L = pkg.lib()
+    sc = scenes.dam_break_3d(24, 16, 16)
+    rec = randomised(sc, vel=0.3)
+    sim = pkg.Simulation.new(sc.cfg)
+    sim.add_particles(rec)
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    buf = (C.c_ubyte * 448)()
+    assert L.fluid_slab_peer_barrier(sim._h) == 5                       # FLUID_ERR_STATE: no slab
+    assert L.fluid_slab_ipc_export(sim._h, C.cast(buf, C.c_void_p)) == 5
+    r = sim.rects()
+    z0, nz = int(r["origin"][2]), int(r["size"][2])
+    assert L.fluid_slab_set(sim._h, z0, z0 + nz, 0, 0) == 0             # one slab, no neighbours
+    assert L.fluid_slab_peer_barrier(sim._h) == 5                       # no neighbour mapped
+    assert L.fluid_slab_ipc_import(sim._h, 0, C.cast(buf, C.c_void_p)) == 5
+    assert L.fluid_slab_ipc_export(sim._h, C.cast(buf, C.c_void_p)) == 0 and any(bytes(buf))
+    lo, hi = C.c_void_p(), C.c_void_p()
+    n_out, n_in = (C.c_int64 * 2)(), (C.c_int64 * 2)()
+    for _ in range(5):
+        for ph in range(3):
+            assert L.fluid_slab_phase(sim._h, ph, None) == 0
+        assert L.fluid_slab_migrants_begin(sim._h, C.byref(lo), C.byref(hi)) == 0
+        assert lo.value is None and hi.value is None                    # no faces: no buffers
+        assert L.fluid_slab_migrants_end(sim._h, None, None, n_out, n_in) == 0
+        assert list(n_out) == [0, 0] and list(n_in) == [0, 0]
+    got, gid = sim.read_particles(sort_by_id=True)
+    sim.close()
+    ref = pkg.Simulation.new(sc.cfg)
+    ref.add_particles(rec)
+    ref.set_rect(sc.rect_min, sc.rect_max)
+    ref.substeps(5)
+    want, wid = ref.read_particles(sort_by_id=True)
+    ref.close()
+    assert np.array_equal(gid, wid)
+    np.testing.assert_allclose(got[:, :6], want[:, :6], rtol=0, atol=2e-4)   # float atomics: order-dependent sums
+
+
 def test_windows_hold_distinct_columns(pkg, scenes):
     """The invariant the shared-memory read-modify-writes rely on (sort.cuh, ORDER_CLASS_RR): inside
     one window of one tile no two particles share an (x,y) cell column, windows are <= 32 particles,
