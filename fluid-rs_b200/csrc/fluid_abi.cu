@@ -1508,7 +1508,7 @@ __global__ void k_peer_barrier(int* __restrict__ my_flags, int* peer_lo, int* pe
     const long long t0 = clock64();
     volatile int* f = my_flags;
     while ((peer_lo && f[0] < epoch) || (peer_hi && f[1] < epoch)) {
-        if (clock64() - t0 > (1LL << 34)) {   // seconds: the neighbour is gone; report instead of hanging
+        if (clock64() - t0 > (1LL << 35)) {   // ~17 s: the neighbour is gone; report instead of hanging
             my_flags[2] = 1;
             break;
         }
