@@ -483,6 +483,26 @@ def run_slabs(args, pkg, world, rank, local_rank):
     e2e_value = sc.n * iters * e2e_steps / float(e2e_t.item())
     rec_bytes = n_local * rf * 4
 
+    # the reference's main loop over the slabs: step(mouse) + the summed 80x40 frame, state resident
+    def loop_step(k):
+        sim.step(mouse=(0.25 * float(sc.rect_max[0]) + k, 0.5 * float(sc.rect_max[1])))
+        return sim.frame_counts(viewport=(float(sc.rect_max[0]), float(sc.rect_max[1])))
+
+    loop_step(0)
+    torch.cuda.synchronize()
+    dist.barrier()
+    t0 = time.perf_counter()
+    for k in range(e2e_steps):
+        frame = loop_step(k + 1)
+    torch.cuda.synchronize()
+    dist.barrier()
+    loop_t = torch.tensor([time.perf_counter() - t0], device="cuda")
+    dist.all_reduce(loop_t, op=dist.ReduceOp.MAX)
+    e2e_loop = {"value": sc.n * iters * e2e_steps / float(loop_t.item()), "unit": UNIT, "h2d_bytes_per_step": 8,
+                "d2h_bytes_per_step": int(frame.size * 4), "steps": e2e_steps,
+                "what": "the reference's main loop: step(mouse position from the host) on every rank + the 80x40 frame's "
+                        "bin counts summed over the ranks and read back; particle state stays resident"}
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -495,6 +515,7 @@ def run_slabs(args, pkg, world, rank, local_rank):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes, "d2h_bytes_per_step": rec_bytes,
                 "steps": e2e_steps, "what": "per rank: clear + add_particles(pinned host records) + step() + "
                                             "read_particles(all records); bytes are per rank"},
+        "e2e_main_loop": e2e_loop,
         "gpu_launches": int(launches_t.item()), "clocks": clocks, "ms_per_substep": ms / args.steps / iters,
         "migrated_particles": int(cnt[1].item()),
     }

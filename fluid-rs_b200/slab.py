@@ -378,5 +378,14 @@ class SlabSimulation:
     def step(self, mouse=None):
         self.substeps(self.iterations, mouse)
 
+    def frame_counts(self, viewport, cols: int = 80, rows: int = 40):
+        """`draw`'s 80x40 binning (3d:469-486) over all slabs: every rank bins its own particles on the
+        device, the bin counts are summed over the process group."""
+        import torch
+        counts = self.sim.frame_counts(viewport=viewport, cols=cols, rows=rows)
+        t = torch.from_numpy(counts).to(f"cuda:{torch.cuda.current_device()}")
+        self.driver.dist.all_reduce(t)
+        return t.cpu().numpy()
+
     def close(self):
         self.sim.close()
