@@ -5,6 +5,7 @@
 // There is no CPU fallback: without a CUDA device fluid_create fails with FLUID_ERR_NO_DEVICE.
 #include "../../include/fluid_b200.h"
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -100,6 +101,8 @@ struct fluid_sim {
     int dirty_cur = 0;
     int2* tile_info = nullptr;   // per tile: {windows W (0 = plain cell order, < 0 = no class merge), tile-list entry}
     unsigned char* tab = nullptr;   // per tile-list entry: TAB_BYTES of class-in-window counts (k_tile_tables)
+    alignas(64) CUtensorMap tm_grid;   // the node grid as a TMA tensor {4 floats, x, y, z}, box = one 10x10 footprint plane
+    bool tma = false;            // tm_grid is valid (3D grids; FLUID_B200_NO_TMA=1 keeps the LDGSTS / REDG paths)
     PeerHalo peer{};             // neighbours' grids mapped through CUDA IPC (peer-memory halo), or all null
     void* peer_base[2][6] = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
                              {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}};   // opened IPC mappings
@@ -517,14 +520,19 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     }
     if (phases & 2) {
         Particles q = s->buf[s->cur];
-        if (tiled && s->p2p)
-            k_p2g_tiled<true><<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
-                s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
-                dbg ? dbg->pressure : nullptr, s->peer);
-        else if (tiled)
-            k_p2g_tiled<false><<<std::min(tb, s->grid_p2g), T3::THREADS, sizeof(P2GSmem), s->stream>>>(
-                s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid, dbg ? dbg->density : nullptr,
-                dbg ? dbg->pressure : nullptr, s->peer);
+        if (tiled) {
+            const unsigned gp = std::min(tb, s->grid_p2g);
+            float* dd = dbg ? dbg->density : nullptr;
+            float* dp = dbg ? dbg->pressure : nullptr;
+#define P2G_LAUNCH(PEER, TMA)                                                                                       \
+    k_p2g_tiled<PEER, TMA><<<gp, T3::THREADS, sizeof(P2GSmem), s->stream>>>(s->geo, q, s->src, s->tiles, n_act, s->gmass, \
+                                                                           s->grid, dd, dp, s->peer, s->tm_grid)
+            if (s->p2p && s->tma) P2G_LAUNCH(true, true);
+            else if (s->p2p) P2G_LAUNCH(true, false);
+            else if (s->tma) P2G_LAUNCH(false, true);
+            else P2G_LAUNCH(false, false);
+#undef P2G_LAUNCH
+        }
         else
             k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid,
                                                                           dbg ? dbg->density : nullptr,
@@ -545,8 +553,12 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                 sb.rec[sd] = dst ? dst + MIG_WORDS : nullptr;
             }
             sb.cap = s->mig_cap;
-            k_g2p_tiled<true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch);
+            if (s->tma)
+                k_g2p_tiled<true, true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
+                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch, s->tm_grid);
+            else
+                k_g2p_tiled<true, false><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
+                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch, s->tm_grid);
             // ignored (and, outside slab runs, dropped) particles sit behind the tiles: carried over
             // and counted here; a slab run ends dropped / migrated particles at this point
             const int* n_end = s->geo.slab_on ? s->tile_base + s->geo.n_tiles + 1 : nullptr;
@@ -748,17 +760,19 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
 
-    cudaFuncSetAttribute(k_p2g_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
-    cudaFuncSetAttribute(k_p2g_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
+    cudaFuncSetAttribute(k_p2g_tiled<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
+    cudaFuncSetAttribute(k_p2g_tiled<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
+    cudaFuncSetAttribute(k_p2g_tiled<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
+    cudaFuncSetAttribute(k_p2g_tiled<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
     {   // persistent grids: one wave of resident CTAs per kernel (148 SMs x occupancy)
         cudaDeviceProp prop{};
         if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) s->sm_count = prop.multiProcessorCount;
         int occ = 0;
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mass_tiled<false>, T3::THREADS, 0);
         s->grid_mass = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_tiled<false>, T3::THREADS, sizeof(P2GSmem));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_tiled<false, true>, T3::THREADS, sizeof(P2GSmem));
         s->grid_p2g = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled<true>, T3::THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled<true, true>, T3::THREADS, 0);
         s->grid_g2p = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
         (void)cudaGetLastError();
     }
@@ -848,6 +862,33 @@ fluid_status fluid_synchronize(fluid_sim* s) {
     CU_TRY(cudaStreamSynchronize(s->stream));
     return FLUID_OK;
 }
+
+namespace {
+// cuTensorMapEncodeTiled through the runtime's driver entry point: no link against libcuda
+using EncodeTiled = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+bool make_grid_map(const Geo& g, float4* first_node, CUtensorMap* out) {
+    if (const char* e = std::getenv("FLUID_B200_NO_TMA")) {
+        if (e[0] == '1') return false;
+    }
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t dims[4] = {4, static_cast<cuuint64_t>(g.size[0]), static_cast<cuuint64_t>(g.size[1]),
+                                static_cast<cuuint64_t>(g.size[2])};
+    const cuuint64_t strides[3] = {16, 16ull * g.size[0], 16ull * g.size[0] * g.size[1]};   // bytes, dims 1..3
+    const cuuint32_t box[4] = {4, T3::NX, T3::NY, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return reinterpret_cast<EncodeTiled>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, first_node, dims, strides, box, estr,
+                                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
 
 fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     if (!s || !mn || !mx) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_rect: null argument");
@@ -947,6 +988,7 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     const int64_t nb = (n_pt + SCAN_CHUNK - 1) / SCAN_CHUNK;
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
     if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
+    s->tma = D == 3 && make_grid_map(g, s->grid + g.guard, &s->tm_grid);
     CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + N_PSEUDO) * sizeof(int4)));
     CU_TRY(cudaMalloc(&s->cand, (n_pt + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->imm_cnt, (n_pt + 8) * sizeof(int)));

@@ -32,8 +32,11 @@
 #include "phases_generic.cuh"
 #include "sort.cuh"
 
+#include <cuda.h>   // CUtensorMap (the descriptor is built on the host in fluid_abi.cu; no driver API is linked)
+
 namespace fluid {
 
+constexpr int T3_NX_NY_BYTES = 10 * 10 * 16;   // one footprint plane of float4 nodes
 struct T3 {
     static constexpr int X = Tile<3>::X, Y = Tile<3>::Y, Z = Tile<3>::Z;
     static constexpr int NX = X + 2, NY = Y + 2, NZ = Z + 2;
@@ -53,6 +56,39 @@ struct T3 {
 constexpr int FOOT_ITERS = (T3::NODES + 31) / 32;    // 19 footprint nodes per lane
 constexpr int FOOT_ROWS = T3::NY * T3::NZ;           // 60 rows of 10 nodes
 constexpr int FOOT_STEPS = FOOT_ROWS / 3;            // a warp takes 3 rows (30 lanes) per step
+
+// ---- TMA (cp.async.bulk.tensor) helpers: the node grid as a 4-D tensor {4 floats, x, y, z}; one box =
+// one 10x10 plane of a tile's footprint, dense in shared memory (1600 B at a 128-byte aligned address).
+// The copies do not go through the LSU pipe, which is what binds the tile kernels.  Used for the tiles whose
+// footprint lies inside the grid (a box that started at coordinate -1 raised "illegal instruction" on B200).
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, int bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, int parity) {
+    const unsigned a = static_cast<unsigned>(__cvta_generic_to_shared(bar));
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_plane(void* smem_dst, const CUtensorMap* tm, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5}], [%6];"
+                 ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(reinterpret_cast<unsigned long long>(tm)), "r"(0),
+                 "r"(x), "r"(y), "r"(z), "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_plane(const CUtensorMap* tm, int x, int y, int z, const void* smem_src) {
+    asm volatile("cp.reduce.async.bulk.tensor.4d.global.shared::cta.add.tile.bulk_group [%0, {%1, %2, %3, %4}], [%5];"
+                 ::"l"(reinterpret_cast<unsigned long long>(tm)), "r"(0), "r"(x), "r"(y), "r"(z),
+                 "r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_src))) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+constexpr int FOOT_PLANE_BYTES = T3_NX_NY_BYTES;
 
 struct TileCtx {
     int c0[3];     // first cell of the tile, relative to the grid origin
@@ -373,13 +409,14 @@ __device__ __forceinline__ void load_prec(const Particles& q, int i, bool ok, PR
     }
 }
 
-template <bool PEER>
+template <bool PEER, bool TMA>   // TMA: the tile is flushed by tensor-memory-accelerator reductions (tm_grid)
 __global__ void __launch_bounds__(T3::THREADS, 4)
 k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float* __restrict__ gmass, float4* __restrict__ grid,
-            float* __restrict__ dbg_density, float* __restrict__ dbg_pressure, PeerHalo ph) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+            float* __restrict__ dbg_density, float* __restrict__ dbg_pressure, PeerHalo ph,
+            const __grid_constant__ CUtensorMap tm_grid) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* acc = sm.acc[warp];
@@ -517,13 +554,26 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 }
             }
         }
+        if (TMA && !tc.edge) {   // (tiles on the rim of the grid keep the per-node path: their boxes stick out of the tensor)
+            // six 10x10 planes as tensor reductions (cp.reduce.async.bulk.tensor .add, SASS UTMAREDG): no LDS, no
+            // per-node REDG, no index arithmetic
+            if (lane == 0) {
+                fence_proxy_async();      // the accumulators were written through the generic proxy
+#pragma unroll
+                for (int lz = 0; lz < T3::NZ; ++lz)
+                    tma_reduce_add_plane(&tm_grid, tc.c0[0] - 1, tc.c0[1] - 1, tc.c0[2] - 1 + lz, acc + lz * T3::PLANE);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                if (!PEER) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");   // acc may be reused
+            }
+        } else {
 #pragma unroll 4
-        for (int it = 0; it < FOOT_STEPS; ++it) {
-            int gi;
-            const int sl = foot_step(g, tc, fl, it, gi);
-            if (gi >= 0) {
-                const float4 v = acc[sl];
-                if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) atomicAdd(&grid[gi], v);
+            for (int it = 0; it < FOOT_STEPS; ++it) {
+                int gi;
+                const int sl = foot_step(g, tc, fl, it, gi);
+                if (gi >= 0) {
+                    const float4 v = acc[sl];
+                    if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) atomicAdd(&grid[gi], v);
+                }
             }
         }
         if (PEER) {
@@ -541,9 +591,11 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                     if (v.w != 0.0f || v.x != 0.0f || v.y != 0.0f || v.z != 0.0f) red_add_sys(&dst[gi], v);
                 }
             }
+            if (TMA && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         }
         __syncwarp();
     }
+    if (TMA && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // reductions performed before the warp exits
 }
 
 // ---- update + g2p -----------------------------------------------------------------------------
@@ -557,19 +609,28 @@ struct SlabBufs {
 // COUNT: also start the next substep's neighbour search (sort.cuh): every particle of the tile
 // gets its new bucket; the ones that stay in this tile are ranked with shared-memory integer
 // atomics (native ATOMS.ADD), the few that change tile or are dropped go to the immigrant list.
-template <bool COUNT>
+template <bool COUNT, bool TMA>   // TMA: the footprint is loaded by the tensor memory accelerator (tm_grid)
 __global__ void __launch_bounds__(T3::THREADS, 4)
 k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb,
-            float* __restrict__ gmass, int* __restrict__ gz, int epoch) {
-    __shared__ float4 sm[T3::WARPS * T3::SLOTS];
+            float* __restrict__ gmass, int* __restrict__ gz, int epoch, const __grid_constant__ CUtensorMap tm_grid) {
+    __shared__ __align__(128) float4 sm[T3::WARPS * T3::SLOTS];
     __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
+    __shared__ __align__(8) unsigned long long bars[T3::WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* vt = sm + warp * T3::SLOTS;
     int* scnt = scnt_all + warp * TILE_CELLS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
+    int tma_parity = 0;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(&bars[warp], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
@@ -600,19 +661,34 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         // node records of the footprint: cp.async (LDGSTS) straight into shared memory, all 19 per
         // lane in flight, zero-filled outside the p_rect grid; then update_grid in place
         const FootLane fl = foot_lane(lane);
+        if (TMA && !tc.edge) {   // (tiles on the rim of the grid keep the per-node path: their boxes stick out of the tensor)
+            // six 10x10 planes by the tensor memory accelerator (SASS UTMALDG): no LSU wavefronts;
+            // the warp's previous reads and writes of the tile are ordered before it
+            if (lane == 0) {
+                fence_proxy_async();
+                mbar_expect_tx(&bars[warp], T3::NZ * FOOT_PLANE_BYTES);
 #pragma unroll
-        for (int it = 0; it < FOOT_STEPS; ++it) {
-            int gi;
-            const int sl = foot_step(g, tc, fl, it, gi);
-            if (fl.rsub < 3) {
-                const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + sl));
-                const float4* gp = grid + (gi >= 0 ? gi : 0);
-                const int bytes = gi >= 0 ? 16 : 0;
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(bytes) : "memory");
+                for (int lz = 0; lz < T3::NZ; ++lz)
+                    tma_load_plane(vt + lz * T3::PLANE, &tm_grid, tc.c0[0] - 1, tc.c0[1] - 1, tc.c0[2] - 1 + lz, &bars[warp]);
             }
+            __syncwarp();
+            mbar_wait(&bars[warp], tma_parity);
+            tma_parity ^= 1;
+        } else {
+#pragma unroll
+            for (int it = 0; it < FOOT_STEPS; ++it) {
+                int gi;
+                const int sl = foot_step(g, tc, fl, it, gi);
+                if (fl.rsub < 3) {
+                    const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(vt + sl));
+                    const float4* gp = grid + (gi >= 0 ? gi : 0);
+                    const int bytes = gi >= 0 ? 16 : 0;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(gp), "r"(bytes) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
 #pragma unroll 4
         for (int it = 0; it < FOOT_STEPS; ++it) {
             int gi;
