@@ -46,7 +46,7 @@ UNIT = "particle-updates/s"
 ALG_BYTES = {"clear": 20.0, "p2g 1": 24.0, "p2g 2": 100.0, "update": 0.0, "g2p": 88.0}
 ALG_BYTES_STEP = 280.0
 KERNEL_OF_PHASE = {"clear": "k_clear_tiles", "p2g 1": "k_mass_tiled", "p2g 2": "k_p2g_tiled", "g2p": "k_g2p_tiled"}
-NCU_CAPTURE = "profiles/r01_ncu_full_16M_v27.csv"   # ncu --set full, config 4, same kernels
+NCU_CAPTURE = "profiles/r01_ncu_full_16M_v30.csv"   # ncu --set full, config 4, same kernels
 
 
 def ncu_traffic(kernel: str):
@@ -290,7 +290,7 @@ def run_ours(args):
         "frac": achieved / peak, "traffic": ncu_traffic(KERNEL_OF_PHASE[dom]) if sc.n == (1 << 24) else None,
         "traffic_source": NCU_CAPTURE, "peak_source": peak_src,
         "alg_bytes_per_particle": ALG_BYTES[dom], "ms_per_launch": per_phase_ms[dom],
-        "limiter": "shared-memory (LSU) pipe, not HBM: ncu l1tex data-pipe wavefronts 79% of peak, dram 23% (profiles/r01_ncu_full_16M_v27.csv)",
+        "limiter": "shared-memory (LSU) pipe, not HBM: ncu l1tex data-pipe wavefronts 80% of peak, dram 24% (profiles/r01_ncu_full_16M_v30.csv)",
         "step_frac": value * ALG_BYTES_STEP / 1e9 / peak,
         "per_phase_ms": per_phase_ms,
         "occupancy": occupancy,

@@ -46,7 +46,8 @@ def full(path):
     idx = [hdr.index(w) for w in WANT if w in hdr]
     print("kernel," + ",".join(f"{hdr[i]} [{units[i]}]" for i in idx))
     for r in rows[2:]:
-        print(r[ik].split("(")[0] + "," + ",".join(r[i].replace(",", "") for i in idx))
+        name = r[ik].split("(")[0].replace(", ", ";")     # template arguments: keep the row's column count
+        print(name + "," + ",".join(r[i].replace(",", "") for i in idx))
 
 
 if __name__ == "__main__":
