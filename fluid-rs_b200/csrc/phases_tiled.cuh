@@ -556,9 +556,11 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         }
         if (TMA && !tc.edge) {   // (tiles on the rim of the grid keep the per-node path: their boxes stick out of the tensor)
             // six 10x10 planes as tensor reductions (cp.reduce.async.bulk.tensor .add, SASS UTMAREDG): no LDS, no
-            // per-node REDG, no index arithmetic
+            // per-node REDG, no index arithmetic.  Every lane orders its own accumulator stores (generic proxy)
+            // before the async proxy, then the warp meets, then one lane issues.
+            fence_proxy_async();
+            __syncwarp();
             if (lane == 0) {
-                fence_proxy_async();      // the accumulators were written through the generic proxy
 #pragma unroll
                 for (int lz = 0; lz < T3::NZ; ++lz)
                     tma_reduce_add_plane(&tm_grid, tc.c0[0] - 1, tc.c0[1] - 1, tc.c0[2] - 1 + lz, acc + lz * T3::PLANE);
@@ -662,10 +664,11 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         // lane in flight, zero-filled outside the p_rect grid; then update_grid in place
         const FootLane fl = foot_lane(lane);
         if (TMA && !tc.edge) {   // (tiles on the rim of the grid keep the per-node path: their boxes stick out of the tensor)
-            // six 10x10 planes by the tensor memory accelerator (SASS UTMALDG): no LSU wavefronts;
-            // the warp's previous reads and writes of the tile are ordered before it
+            // six 10x10 planes by the tensor memory accelerator (SASS UTMALDG): no LSU wavefronts; every
+            // lane orders its previous reads and writes of the tile before the async proxy, then the warp meets
+            fence_proxy_async();
+            __syncwarp();
             if (lane == 0) {
-                fence_proxy_async();
                 mbar_expect_tx(&bars[warp], T3::NZ * FOOT_PLANE_BYTES);
 #pragma unroll
                 for (int lz = 0; lz < T3::NZ; ++lz)
