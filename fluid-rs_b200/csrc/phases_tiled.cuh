@@ -8,14 +8,21 @@
 // alone, so the read-modify-writes into the shared-memory tile are plain LDS / FFMA / STS — three
 // independent chains in flight per lane, one __syncwarp per (ox,oy) — with no atomics (shared
 // float atomics are a CAS loop on sm_100a, ATOMS.CAST.SPIN) and no conflict passes.
-// Tiles are flushed to the dense grid with vector reductions (red.global.add.v4.f32,
-// SASS REDG.E.ADD.F32x4).  Particle streams are gathered through src[] (sorted slot -> storage
-// index); g2p writes the advanced particles at their sorted slots of the other buffer, so no
-// separate reorder pass exists.
+// Tiles move between HBM and shared memory through the tensor memory accelerator where their
+// footprint lies inside the grid: k_p2g_tiled flushes its accumulators with six tensor reductions
+// (cp.reduce.async.bulk.tensor.4d .add, SASS UTMAREDG.4D.ADD), k_g2p_tiled loads its footprint with
+// six tensor copies (cp.async.bulk.tensor.4d, SASS UTMALDG.4D, mbarrier completion); tiles on the rim
+// of the grid and the node masses use vector / scalar reductions (red.global.add, SASS REDG) and
+// cp.async.  In slab runs (PEER) the deposits into the node planes shared with a neighbour GPU also go
+// into the neighbour's mapped arrays (red.relaxed.sys).  Particle streams are gathered through src[]
+// (sorted slot -> storage index); g2p writes the advanced particles at their sorted slots of the other
+// buffer, so no separate reorder pass exists.  The tile kernels also clear the grid on the way
+// (k_mass_tiled the node records, k_g2p_tiled the node masses of the blocks they own).
 //
 // Shared-memory node index: x + 10*y + 104*z.  The plane stride is padded from 100 to 104
-// (= 0 mod 8) so that the 16-byte bank group of a float4 node, (x + 2y) mod 8, depends on the
-// column only; the sort enumerates columns so that neighbouring lanes fall into different groups.
+// (= 0 mod 8, and 104 nodes = 13 * 128 bytes for the TMA boxes) so that the 16-byte bank group of a
+// float4 node, (x + 2y) mod 8, depends on the column only; the sort enumerates columns so that
+// neighbouring lanes fall into different groups.  Node masses are kept as z quads (T3::QSLOTS).
 //
 // Phase mapping to the reference (3d:110-134):
 //   k_mass_tiled  "p2g 1"  node mass   m_i  = sum_p w_ip m_p                      (3d:164,175)
