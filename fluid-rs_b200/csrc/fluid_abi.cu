@@ -102,6 +102,8 @@ struct fluid_sim {
     int2* tile_info = nullptr;   // per tile: {windows W (0 = plain cell order, < 0 = no class merge), tile-list entry}
     unsigned char* tab = nullptr;   // per tile-list entry: TAB_BYTES of class-in-window counts (k_tile_tables)
     alignas(64) CUtensorMap tm_grid;   // the node grid as a TMA tensor {4 floats, x, y, z}, box = one 10x10 footprint plane
+    alignas(64) CUtensorMap tm_mass;   // the node masses {x + 1, y, z} (base one float early: 16-byte aligned), box 12 x 10 x 6
+    bool tma_mass = false;
     bool tma = false;            // tm_grid is valid (3D grids; FLUID_B200_NO_TMA=1 keeps the LDGSTS / REDG paths)
     PeerHalo peer{};             // neighbours' grids mapped through CUDA IPC (peer-memory halo), or all null
     void* peer_base[2][6] = {{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr},
@@ -526,7 +528,8 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             float* dp = dbg ? dbg->pressure : nullptr;
 #define P2G_LAUNCH(PEER, TMA)                                                                                       \
     k_p2g_tiled<PEER, TMA><<<gp, T3::THREADS, sizeof(P2GSmem), s->stream>>>(s->geo, q, s->src, s->tiles, n_act, s->gmass, \
-                                                                           s->grid, dd, dp, s->peer, s->tm_grid)
+                                                                           s->grid, dd, dp, s->peer, s->tm_grid, s->tm_mass,     \
+                                                                           s->tma_mass ? 1 : 0)
             if (s->p2p && s->tma) P2G_LAUNCH(true, true);
             else if (s->p2p) P2G_LAUNCH(true, false);
             else if (s->tma) P2G_LAUNCH(false, true);
@@ -888,6 +891,29 @@ bool make_grid_map(const Geo& g, float4* first_node, CUtensorMap* out) {
                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                              CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
+// node masses: x rows of g.size[0] floats.  TMA wants a 16-byte aligned base and strides: needs size[0] % 4 == 0,
+// and the tensor starts one float before node 0 (g.guard - 1 is a multiple of 4 then), so x_tensor = x_node + 1.
+bool make_mass_map(const Geo& g, float* gmass_alloc, CUtensorMap* out) {
+    if (const char* e = std::getenv("FLUID_B200_NO_TMA")) {
+        if (e[0] == '1') return false;
+    }
+    if (g.size[0] % 4 != 0 || (g.guard - 1) % 4 != 0) return false;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t dims[3] = {static_cast<cuuint64_t>(g.size[0]), static_cast<cuuint64_t>(g.size[1]),
+                                static_cast<cuuint64_t>(g.size[2])};
+    const cuuint64_t strides[2] = {4ull * g.size[0], 4ull * g.size[0] * g.size[1]};
+    const cuuint32_t box[3] = {MBOX_X, T3::NY, T3::NZ};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    return reinterpret_cast<EncodeTiled>(fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, gmass_alloc + g.guard - 1, dims, strides, box,
+                                             estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 }  // namespace
 
 fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
@@ -989,6 +1015,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
     if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
     s->tma = D == 3 && make_grid_map(g, s->grid + g.guard, &s->tm_grid);
+    s->tma_mass = D == 3 && s->tma && make_mass_map(g, s->gmass, &s->tm_mass);
+    if (!s->tma_mass) std::memset(&s->tm_mass, 0, sizeof(s->tm_mass));
     CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + N_PSEUDO) * sizeof(int4)));
     CU_TRY(cudaMalloc(&s->cand, (n_pt + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->imm_cnt, (n_pt + 8) * sizeof(int)));

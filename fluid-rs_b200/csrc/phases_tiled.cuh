@@ -94,8 +94,16 @@ __device__ __forceinline__ void tma_reduce_add_plane(const CUtensorMap* tm, int 
                  ::"l"(reinterpret_cast<unsigned long long>(tm)), "r"(0), "r"(x), "r"(y), "r"(z),
                  "r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_src))) : "memory");
 }
+__device__ __forceinline__ void tma_load_box3(void* smem_dst, const CUtensorMap* tm, int x, int y, int z, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(smem_dst))), "l"(reinterpret_cast<unsigned long long>(tm)),
+                 "r"(x), "r"(y), "r"(z), "r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 constexpr int FOOT_PLANE_BYTES = T3_NX_NY_BYTES;
+// node-mass box of the TMA footprint load: rows of 12 floats (the inner extent of a box has to be a multiple
+// of 16 bytes), 10 rows, 6 planes
+constexpr int MBOX_X = 12, MBOX_FLOATS = MBOX_X * 10 * 6;
 
 struct TileCtx {
     int c0[3];     // first cell of the tile, relative to the grid origin
@@ -422,12 +430,21 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float* __restrict__ gmass, float4* __restrict__ grid,
             float* __restrict__ dbg_density, float* __restrict__ dbg_pressure, PeerHalo ph,
-            const __grid_constant__ CUtensorMap tm_grid) {
+            const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_mass, int tma_mass) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
+    __shared__ __align__(8) unsigned long long bars[T3::WARPS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* acc = sm.acc[warp];
     float4* ms = sm.mass[warp];
+    int load_parity = 0;
+    if (TMA) {
+        if (lane == 0) {
+            mbar_init(&bars[warp], 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
     for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
@@ -445,6 +462,35 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         window_range(tc, 1, off, len);
         int i_next = lane < len ? __ldg(&src[tc.base + off + lane]) : 0;
         const FootLane fl = foot_lane(lane);
+        // the node masses of the footprint as ONE tensor copy (box 12 x 10 x 6 floats) into the accumulator
+        // tile, which is idle until the first window; unpacked into z quads below
+        const bool tma_load = TMA && tma_mass && !tc.edge && tc.c0[0] + MBOX_X <= g.size[0];
+        if (tma_load) {
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_expect_tx(&bars[warp], MBOX_FLOATS * 4);
+                // the tensor's x coordinate is the node's x + 1 (base shifted for alignment): node c0 - 1 -> c0
+                tma_load_box3(acc, &tm_mass, tc.c0[0], tc.c0[1] - 1, tc.c0[2] - 1, &bars[warp]);
+            }
+            mbar_wait(&bars[warp], load_parity);
+            load_parity ^= 1;
+            const float* st = reinterpret_cast<const float*>(acc);
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int c = lane + 32 * it;
+                if (c < T3::NX * T3::NY) {
+                    const int ly = c / T3::NX, lx = c - ly * T3::NX;
+                    const float* col = st + lx + MBOX_X * ly;
+                    const float m0 = col[0], m1 = col[MBOX_X * T3::NY], m2 = col[2 * MBOX_X * T3::NY],
+                                m3 = col[3 * MBOX_X * T3::NY], m4 = col[4 * MBOX_X * T3::NY], m5 = col[5 * MBOX_X * T3::NY];
+                    ms[c] = make_float4(m0, m1, m2, m3);
+                    ms[c + T3::PLANE] = make_float4(m2, m3, m4, m5);
+                }
+            }
+            __syncwarp();
+            for (int k = lane; k < T3::SLOTS; k += 32) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        } else
         {   // node masses of the footprint, column by column (six nodes along z -> two quads): all loads
             // in flight before the first store
             float mv[4][6];
