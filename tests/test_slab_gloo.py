@@ -105,6 +105,57 @@ class FixedMessageEngine(MockEngine):
         return list(self._n_out), n_in
 
 
+class PeerMemoryEngine(MockEngine):
+    """The mock behind the peer-memory interface the CUDA engine offers once the neighbours' buffers are
+    mapped: phase 2 'writes' the leavers into the neighbour's receive buffer (here: a message sent at once),
+    peer_barrier() orders it, migrants_end([None, None]) reads the counts of this rank's own receive buffers
+    and append_received() joins them.  Exercises SlabDriver's communication-library-free substep path."""
+
+    def __init__(self, *a):
+        super().__init__(*a)
+        self._n_out = [0, 0]
+        self._inbox = [None, None]
+        self.barriers = 0
+
+    def migrants_begin(self):
+        out = self.migrants()
+        reqs, recv_cnt = [], [torch.zeros(1, dtype=torch.int64) for _ in (0, 1)]
+        nbs = [self.rank - 1 if self.rank > 0 else None, self.rank + 1 if self.rank < self.world - 1 else None]
+        for side, t in enumerate(out):
+            self._n_out[side] = t.numel() // 17
+            if nbs[side] is None:
+                continue
+            reqs.append(dist.isend(torch.tensor([self._n_out[side]], dtype=torch.int64), nbs[side], tag=10 + side))
+            reqs.append(dist.irecv(recv_cnt[side], nbs[side], tag=10 + (1 - side)))
+        for r in reqs:
+            r.wait()
+        reqs = []
+        for side, t in enumerate(out):
+            if nbs[side] is None:
+                self._inbox[side] = torch.zeros(0)
+                continue
+            self._inbox[side] = torch.zeros(int(recv_cnt[side]) * 17, dtype=torch.float32)
+            if t.numel():
+                reqs.append(dist.isend(t, nbs[side], tag=20 + side))
+            if self._inbox[side].numel():
+                reqs.append(dist.irecv(self._inbox[side], nbs[side], tag=20 + (1 - side)))
+        for r in reqs:
+            r.wait()
+        return None
+
+    def peer_barrier(self):
+        self.barriers += 1
+        dist.barrier()
+
+    def migrants_end(self, recv):
+        assert recv == [None, None]
+        return list(self._n_out), [t.numel() // 17 for t in self._inbox]
+
+    def append_received(self, side, n):
+        assert n == self._inbox[side].numel() // 17
+        self.append(self._inbox[side])
+
+
 def _worker(rank, world, port, result_dir, engine="MockEngine"):
     sys.path.insert(0, str(ROOT))
     import fluidpkg
@@ -120,7 +171,7 @@ def _worker(rank, world, port, result_dir, engine="MockEngine"):
     lo, hi = slabs[rank]
     mine = (np.floor(rec[:, 2]) >= lo) & (np.floor(rec[:, 2]) < hi)
     eng = globals()[engine](rank, world, slabs, rec[mine].copy())
-    drv = slab.SlabDriver(eng, rank, world, dist, device="cpu")
+    drv = slab.SlabDriver(eng, rank, world, dist, device="cpu", p2p=engine == "PeerMemoryEngine")
     for _ in range(12):
         drv.substep()
     cz = np.floor(eng.rec[:, 2])
@@ -134,7 +185,7 @@ def _worker(rank, world, port, result_dir, engine="MockEngine"):
 
 
 @pytest.mark.timeout(120)
-@pytest.mark.parametrize("engine", ["MockEngine", "FixedMessageEngine"])
+@pytest.mark.parametrize("engine", ["MockEngine", "FixedMessageEngine", "PeerMemoryEngine"])
 def test_slab_protocol_world2_gloo(tmp_path, engine):
     world = 2
     port = _free_port()
@@ -144,10 +195,13 @@ def test_slab_protocol_world2_gloo(tmp_path, engine):
     assert sorted(ids.tolist()) == list(range(4000))          # every particle exactly once
     assert all(bool(x["inside"]) for x in r)                  # and in the slab that owns its cell
     assert int(r[0]["out"]) + int(r[1]["out"]) == int(r[0]["inn"]) + int(r[1]["inn"]) > 0
-    # halo planes: rank 0's upper interface and rank 1's lower interface hold the same sums
-    l0 = r[0]["log"][r[0]["log"][:, 0] == 1][:, 2]
-    l1 = r[1]["log"][r[1]["log"][:, 0] == 0][:, 2]
-    np.testing.assert_array_equal(l0, l1)
+    if engine != "PeerMemoryEngine":     # (with peer memory the kernels deposit into both copies: no plane exchange)
+        # halo planes: rank 0's upper interface and rank 1's lower interface hold the same sums
+        l0 = r[0]["log"][r[0]["log"][:, 0] == 1][:, 2]
+        l1 = r[1]["log"][r[1]["log"][:, 0] == 0][:, 2]
+        np.testing.assert_array_equal(l0, l1)
+    else:
+        assert all(len(x["log"]) == 0 for x in r)
     # positions advanced exactly as in a single-process run
     z_expect = r[0]["z0"] + 12 * r[0]["vz"]
     for x in r:
