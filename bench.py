@@ -46,28 +46,66 @@ UNIT = "particle-updates/s"
 ALG_BYTES = {"clear": 20.0, "p2g 1": 24.0, "p2g 2": 100.0, "update": 0.0, "g2p": 88.0}
 ALG_BYTES_STEP = 280.0
 KERNEL_OF_PHASE = {"clear": "k_clear_tiles", "p2g 1": "k_mass_tiled", "p2g 2": "k_p2g_tiled", "g2p": "k_g2p_tiled"}
-NCU_CAPTURE = "profiles/r01_ncu_full_16M_v30.csv"   # ncu --set full, config 4, same kernels
+NCU_CAPTURES = ["profiles/r02_ncu_full_16M.csv", "profiles/r01_ncu_full_16M_v30.csv"]   # newest first: ncu --set full, config 4
+
+
+def ncu_capture():
+    for c in NCU_CAPTURES:
+        if (ROOT / c).exists():
+            return c
+    return None
+
+
+def ncu_row(kernel: str):
+    """Metrics of `kernel` from the committed ncu --set full summary (profiles/summarize.py full): a dict
+    {column name without unit: value in base units}, or None."""
+    import csv
+    cap = ncu_capture()
+    if cap is None:
+        return None
+    rows = list(csv.reader((ROOT / cap).read_text().splitlines()))
+    hdr = rows[0]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0}
+    for r in rows[1:]:
+        if kernel in r[0]:
+            out = {}
+            for h, v in zip(hdr[1:], r[1:]):
+                name, unit = h[:h.index(" [")], h[h.index("[") + 1:-1]
+                try:
+                    out[name] = float(v) * scale.get(unit, 1.0)
+                except ValueError:
+                    pass
+            return out
+    return None
 
 
 def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu
-    --set full capture (profiles/), or None."""
-    import csv
-    f = ROOT / NCU_CAPTURE
-    if not f.exists():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel`, or None."""
+    m = ncu_row(kernel)
+    if not m or "dram__bytes_read.sum" not in m:
         return None
-    rows = list(csv.reader(f.read_text().splitlines()))
-    hdr = rows[0]
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    tot = None
-    for r in rows[1:]:
-        if kernel in r[0]:
-            tot = 0.0
-            for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-                for i, h in enumerate(hdr):
-                    if h.startswith(name + " ["):
-                        tot += float(r[i]) * scale[h[h.index("[") + 1:-1]]
-    return tot
+    return m["dram__bytes_read.sum"] + m["dram__bytes_write.sum"]
+
+
+def ncu_limiter(kernel: str):
+    """Which unit the capture shows closest to its peak for `kernel` (derived, not a literal)."""
+    m = ncu_row(kernel)
+    if not m:
+        return None
+    cand = {"shared-memory / L1 data pipe (l1tex__data_pipe_lsu_wavefronts)":
+                m.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+            "HBM (gpu__dram_throughput)": m.get("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "instruction issue (smsp__issue_active)": m.get("smsp__issue_active.avg.pct_of_peak_sustained_active")}
+    cand = {k: v for k, v in cand.items() if v is not None}
+    if not cand:
+        return None
+    top = max(cand, key=cand.get)
+    out = {"unit": top, "pct_of_peak": cand[top], "all_pct": cand, "source": ncu_capture()}
+    wf, bc = m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum"), m.get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")
+    if wf:
+        out["smem_wavefronts_per_launch"] = wf
+        out["smem_bank_conflict_frac"] = (bc or 0.0) / wf
+    return out
 
 
 def measured_peaks():
@@ -142,11 +180,11 @@ def cpu_info():
     return model, os.cpu_count()
 
 
-def oracle_sample(scenes, seconds_target: float = 15.0):
-    """Time the CPU oracle on a scaled-down dam break of the same construction (1 thread)."""
+def oracle_sample(scenes, seconds_target: float = 15.0, scene=None):
+    """Time the CPU oracle on a scaled-down dam break of the same construction (1 thread), or on `scene`."""
     from oracle import oracle
     oracle.build()
-    sc = scenes.dam_break_3d(64, 64, 64)          # 262,144 particles, same column shape as 256^3
+    sc = scene or scenes.dam_break_3d(64, 64, 64)  # 262,144 particles, same column shape as 256^3
     sim = oracle.OracleSim(sc.cfg)
     sim.add_particles(sc.records())
     sim.set_rect(sc.rect_min, sc.rect_max)
@@ -166,7 +204,16 @@ def oracle_sample(scenes, seconds_target: float = 15.0):
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path.  The Rust binary cannot
     be built here (no rustc), so this is the oracle port: same five phases, same order, 1 thread
-    (the reference has no parallel loops — SURVEY.md section 0.2)."""
+    (the reference has no parallel loops — SURVEY.md section 0.2).
+
+    Workload = our arm's (BASELINE config 4, the 2^24-particle dam break; for N > 1 one GPU's share of the
+    weak-scaling scene is the same 2^24 particles, and a single-threaded CPU rate does not depend on N).
+    A full substep of it costs about 20 s on one core, so K steps + W warm-ups at the true size would take
+    ten minutes.  One `step` of this arm is therefore a bounded sample: ONE substep over a quarter of the
+    column (256 x 256 x 64 cells = 2^22 particles: the true depth and length of the column, a quarter of its
+    translation-invariant z extent; `config` says so).  After the timed steps the TRUE 2^24 scene is timed for
+    two substeps (`same_config_probe`): that is the same-config CPU rate (lower: the working set is larger).
+    --scene runs the named small scene in full (31 substeps per step)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -174,30 +221,58 @@ def run_reference(args):
     scenes = fluidpkg.load().scenes
     from oracle import oracle
     oracle.build()
-    sc = scenes.dam_break_3d(64, 64, 64)
-    sim = oracle.OracleSim(sc.cfg)
-    sim.add_particles(sc.records())
-    sim.set_rect(sc.rect_min, sc.rect_max)
-    # one step = one step() of the bounded sample = 31 substeps x 262,144 particles (~11 s)
+    chunk = 1 << 22
+
+    def build(sc):
+        sim = oracle.OracleSim(sc.cfg)
+        for s0 in range(0, sc.n, chunk):
+            sim.add_particles(sc.records(s0, min(chunk, sc.n - s0)))
+        sim.set_rect(sc.rect_min, sc.rect_max)
+        return sim
+
+    full = scenes.dam_break_16m()
+    if args.scene:
+        sc = getattr(scenes, args.scene)()
+        sub_per_step = sc.cfg["iterations"]
+        sample = f"{sc.name}: all {sc.n} particles x {sub_per_step} substeps per step (the whole scene)"
+    else:
+        sc = scenes.dam_break_3d(256, 256, 64, "dam_break_3d_16M_quarter_z")
+        sub_per_step = 1
+        sample = (f"{sc.name}: {sc.n} particles (256 x 256 x 64 cells: a quarter of the 2^24-particle column along z, true "
+                  f"depth and length) x 1 substep per step; the true-size rate is in same_config_probe")
+    sim = build(sc)
     for _ in range(args.warmup):
-        sim.substeps(2)                            # warm-up is shortened: nothing to warm on a CPU but caches
+        sim.substeps(sub_per_step)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        sim.step()
+        sim.substeps(sub_per_step)
     dt = time.perf_counter() - t0
-    value = sc.n * sc.cfg["iterations"] * args.steps / dt
+    phases = sim.phase_seconds()
+    sim.close()
+    value = sc.n * sub_per_step * args.steps / dt
+    probe = None
+    if not args.scene:
+        sim = build(full)
+        sim.substeps(1)                            # first touch of the 1.6 GB grid
+        t0 = time.perf_counter()
+        sim.substeps(2)
+        pdt = time.perf_counter() - t0
+        sim.close()
+        probe = {"workload": full.name, "particles": full.n, "substeps": 2, "seconds": pdt,
+                 "value": full.n * 2 / pdt, "unit": UNIT}
     model, cores = cpu_info()
-    full = scenes.dam_break_for_gpus(args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": dict(full.describe(), substeps_per_step=sc.cfg["iterations"]),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
-                         "sample": f"{sc.name}: {sc.n} particles x {sc.cfg['iterations']} substeps per step "
-                                   f"(1/64 of the 2^24-particle column, same construction)",
-                         "host_cpu": model, "host_cores": cores},
+        "config": dict(sc.describe(), substeps_per_step=sub_per_step,
+                       sample_of=(scenes.dam_break_for_gpus(args.gpus).name or full.name) if not args.scene else sc.name,
+                       sample_of_particles=scenes.dam_break_for_gpus(args.gpus).n if not args.scene else sc.n,
+                       sample_of_substeps_per_step=sc.cfg["iterations"]),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                         "host_cpu": model, "host_cores": cores, "phase_seconds_last_substep": phases},
+        "same_config_probe": probe,
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -223,7 +298,8 @@ def run_ours(args):
 
     sc = scenes.dam_break_for_gpus(args.gpus) if not args.scene else getattr(scenes, args.scene)()
     iters = sc.cfg["iterations"]
-    rf = scenes.rec_floats(3)
+    rf = scenes.rec_floats(sc.dim)
+    headline = not args.scene          # BASELINE config 4; --scene lines are the small parity configs (profiles/)
 
     # host records in pinned memory (also the e2e upload source)
     host = torch.empty((sc.n, rf), dtype=torch.float32, pin_memory=True)
@@ -252,14 +328,15 @@ def run_ours(args):
     sampler.start()
     launches0 = sim.launch_count()
     sim.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
-    e0.record(stream)
-    for _ in range(args.steps):
+    ev[0].record(stream)
+    for k in range(args.steps):
         sim.step()
-    e1.record(stream)
+        ev[k + 1].record(stream)       # an event record costs nothing on the stream; no sync inside the timed region
     torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    ms = ev[0].elapsed_time(ev[-1])
+    ms_by_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
     prof = sim.profile_read()
     sim.profile(False)
     launches = sim.launch_count() - launches0
@@ -278,20 +355,28 @@ def run_ours(args):
     counts = sim.particle_counts()
     assert counts["active"] == sc.n, counts
     value = sc.n * iters * args.steps / (ms * 1e-3)
+    value_by_step = [sc.n * iters / (m * 1e-3) for m in ms_by_step]
 
     # ---- roofline of the dominant kernel ------------------------------------------------------
     peak, peak_src = measured_peaks()
     nsub = max(prof["substeps"], 1)
     per_phase_ms = {k: prof[k] / nsub * 1e3 for k in ("sort", "clear", "p2g 1", "p2g 2", "update", "g2p")}
     dom = max(("clear", "p2g 1", "p2g 2", "g2p"), key=lambda k: per_phase_ms[k])
-    achieved = ALG_BYTES[dom] * sc.n / (per_phase_ms[dom] * 1e-3) / 1e9
+    alg, alg_step, kernel_of = ALG_BYTES, ALG_BYTES_STEP, KERNEL_OF_PHASE
+    if sc.dim == 2:      # SURVEY.md 8(d), 2D, A/N = 0.25: 121 B per particle-substep; the 2D path = particle-per-thread kernels
+        alg = {"clear": 3.0, "p2g 1": 36.0 + 6.0, "p2g 2": 28.0 + 5.0, "update": 0.0, "g2p": 40.0 + 3.0}
+        alg_step = 121.0
+        kernel_of = {"clear": "memset", "p2g 1": "k_p2g1_generic", "p2g 2": "k_p2g2_generic", "g2p": "k_g2p_generic"}
+    achieved = alg[dom] * sc.n / (per_phase_ms[dom] * 1e-3) / 1e9
     roofline = {
-        "bound": "hbm", "kernel": f"{KERNEL_OF_PHASE[dom]} ({dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": f"{kernel_of[dom]} ({dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": ncu_traffic(KERNEL_OF_PHASE[dom]) if sc.n == (1 << 24) else None,
-        "traffic_source": NCU_CAPTURE, "peak_source": peak_src,
-        "alg_bytes_per_particle": ALG_BYTES[dom], "ms_per_launch": per_phase_ms[dom],
-        "limiter": "shared-memory (LSU) pipe, not HBM: ncu l1tex data-pipe wavefronts 80% of peak, dram 24% (profiles/r01_ncu_full_16M_v30.csv)",
-        "step_frac": value * ALG_BYTES_STEP / 1e9 / peak,
+        "traffic_source": ncu_capture(), "peak_source": peak_src,
+        "alg_bytes_per_particle": alg[dom], "ms_per_launch": per_phase_ms[dom],
+        "limiter": ncu_limiter(KERNEL_OF_PHASE[dom]) if sc.n == (1 << 24) else
+                   "launch latency: a few thousand particles per kernel (see step_latency_ms)",
+        "step_frac": value * alg_step / 1e9 / peak,
+        "step_frac_range": [min(value_by_step) * alg_step / 1e9 / peak, max(value_by_step) * alg_step / 1e9 / peak],
         "per_phase_ms": per_phase_ms,
         "occupancy": occupancy,
     }
@@ -337,11 +422,11 @@ def run_ours(args):
     # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu:
-        bsc, n_sub, dt, cpu_value, phases = oracle_sample(scenes)
+        bsc, n_sub, dt, cpu_value, phases = oracle_sample(scenes, scene=None if headline else sc)
         model, cores = cpu_info()
         cpu = {"value": cpu_value, "unit": UNIT, "cores": 1, "kind": "port",
-               "sample": f"{bsc.name}: {bsc.n} particles x {n_sub} substeps in {dt:.1f} s "
-                         f"(1/64 of the 2^24-particle column, same construction)",
+               "sample": f"{bsc.name}: {bsc.n} particles x {n_sub} substeps in {dt:.1f} s " +
+                         ("(1/64 of the 2^24-particle column, same construction)" if headline else "(the whole scene)"),
                "host_cpu": model, "host_cores": cores,
                "phase_seconds_last_substep": phases}
 
@@ -350,8 +435,11 @@ def run_ours(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": dict(sc.describe(), substeps_per_step=iters,
-                       l2="inputs larger than L2 (particle state 1.1 GB, node grid 1.2 GB per GPU)",
+                       l2="inputs larger than L2 (particle state 1.1 GB, node grid 1.2 GB per GPU)" if sc.n >= (1 << 24)
+                          else "working set smaller than L2 (a parity config, not the headline workload)",
                        parallelism=f"z-slabs x{args.gpus}" if args.gpus > 1 else "single GPU"),
+        "value_by_step": value_by_step,
+        "step_latency_ms": ms / args.steps,
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes,
@@ -377,6 +465,9 @@ def run_slabs(args, pkg, world, rank, local_rank):
     if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
         os.environ["NCCL_DEBUG"] = "WARN"
     dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    # Parity first, outside every timed region: the N-rank slab run of a small sloshing scene against the one-GPU
+    # run of the same scene (ids exactly once, sent == received, |dpos|, |dvel| under the stated bound).
+    parity = pkg.slab.parity_check(pkg, dist, rank, world, local_rank)
     sc = scenes.dam_break_for_gpus(world)
     iters = sc.cfg["iterations"]
     rf = scenes.rec_floats(3)
@@ -425,18 +516,19 @@ def run_slabs(args, pkg, world, rank, local_rank):
     sampler.start()
     launches0 = sim.sim.launch_count()
     sim.sim.profile(True)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
     dist.barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
+    ev[0].record(stream)
+    for k in range(args.steps):
         sim.step()
-    e1.record(stream)
+        ev[k + 1].record(stream)
     torch.cuda.synchronize()
     dist.barrier()
-    ms_t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+    ms_t = torch.tensor([ev[0].elapsed_time(ev[-1])] + [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)], device="cuda")
     dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
-    ms = float(ms_t.item())
+    ms = float(ms_t[0].item())
+    value_by_step = [sc.n * iters / (float(m) * 1e-3) for m in ms_t[1:].tolist()]
     prof = sim.sim.profile_read()
     sim.sim.profile(False)
     launches_t = torch.tensor([sim.sim.launch_count() - launches0], device="cuda", dtype=torch.int64)
@@ -454,7 +546,8 @@ def run_slabs(args, pkg, world, rank, local_rank):
     achieved = ALG_BYTES[dom] * n_local / (per_phase_ms[dom] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": f"{KERNEL_OF_PHASE[dom]} ({dom})", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic(KERNEL_OF_PHASE[dom]),
-                "traffic_source": NCU_CAPTURE + " (single-GPU capture of the same kernel and per-GPU size)",
+                "traffic_source": f"{ncu_capture()} (single-GPU capture of the same kernel and per-GPU size)",
+                "limiter": ncu_limiter(KERNEL_OF_PHASE[dom]),
                 "peak_source": peak_src,
                 "alg_bytes_per_particle": ALG_BYTES[dom], "ms_per_launch": per_phase_ms[dom],
                 "step_frac": value * ALG_BYTES_STEP / 1e9 / (peak * world),
@@ -511,7 +604,8 @@ def run_slabs(args, pkg, world, rank, local_rank):
                        l2="inputs larger than L2 (particle state 1.1 GB, node grid > 1 GB per GPU)",
                        parallelism=f"z-slabs x{world}", particles_per_gpu=n_rank,
                        slabs=[list(x) for x in slabs]),
-        "roofline": roofline, "cpu_baseline": None,
+        "value_by_step": value_by_step,
+        "roofline": roofline, "cpu_baseline": None, "parity_check": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes, "d2h_bytes_per_step": rec_bytes,
                 "steps": e2e_steps, "what": "per rank: clear + add_particles(pinned host records) + step() + "
                                             "read_particles(all records); bytes are per rank"},
@@ -524,6 +618,8 @@ def run_slabs(args, pkg, world, rank, local_rank):
     sim.close()
     dist.barrier()
     dist.destroy_process_group()
+    if not parity["ok"]:
+        raise SystemExit("bench.py: the multi-GPU parity check failed: " + json.dumps(parity))
 
 
 def main():

@@ -41,6 +41,7 @@ extern "C" {
     fn fluid_add_particles(sim: *mut FluidSim, rec: *const f32, ids: *const i32, n: i64) -> c_int; // add_particle, 3d:104
     fn fluid_step(sim: *mut FluidSim, mouse_xy: *const f32) -> c_int; // step, 3d:110
     fn fluid_particle_count(sim: *mut FluidSim, n: *mut i64) -> c_int;
+    fn fluid_slot_count(sim: *const FluidSim, n: *mut i64) -> c_int;
     fn fluid_read_particles(sim: *mut FluidSim, rec: *mut f32, ids: *mut i32, cap: i64, n: *mut i64) -> c_int; // iter_particle, 3d:383
     fn fluid_get_phase_times(sim: *mut FluidSim, sec: *mut f64, sort: *mut f64) -> c_int; // debug_elapseds, 3d:502
     fn fluid_render_frame(sim: *mut FluidSim, viewport_xy: *const f32, cols: i32, rows: i32, counts: *mut i32) -> c_int; // draw's binning, 3d:469-486
@@ -88,7 +89,7 @@ impl Handle {
     }
     fn read(&mut self) -> usize {
         let mut n = 0i64;
-        check(unsafe { fluid_particle_count(self.h, &mut n) });
+        check(unsafe { fluid_slot_count(self.h, &mut n) });   // upper bound, no device work
         self.staging.resize(n as usize * self.rec_floats, 0.0);
         check(unsafe { fluid_read_particles(self.h, self.staging.as_mut_ptr(), std::ptr::null_mut(), n, &mut n) });
         n as usize

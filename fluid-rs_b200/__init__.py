@@ -83,6 +83,7 @@ SIGNATURES = {
     "fluid_substeps": (C.c_int, [C.c_void_p, C.c_int32, _fp]),
     "fluid_particle_count": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_particle_counts": (C.c_int, [C.c_void_p, _i64p]),
+    "fluid_slot_count": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_read_particles": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, _i64p]),
     "fluid_get_dt": (C.c_int, [C.c_void_p, _fp]),
     "fluid_get_phase_times": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
@@ -319,8 +320,14 @@ class Simulation:
         _check(lib().fluid_particle_counts(self._h, c))
         return dict(active=c[0], frozen=c[1], outside=c[2], dropped=c[3])
 
+    def slot_count(self) -> int:
+        """Upper bound on the number of records read_particles returns; no device work."""
+        n = C.c_int64()
+        _check(lib().fluid_slot_count(self._h, C.byref(n)))
+        return n.value
+
     def read_particles(self, sort_by_id: bool = False):
-        n = self.particle_count()
+        n = self.slot_count()      # not particle_count(): that re-runs the neighbour search from scratch
         rec = np.empty((max(n, 1), self.rec_floats), dtype=np.float32)
         ids = np.empty(max(n, 1), dtype=np.int32)
         w = C.c_int64()

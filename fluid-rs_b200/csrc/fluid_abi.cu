@@ -188,31 +188,45 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     if (want > INT_MAX - 1024) return fail(FLUID_ERR_INVALID_ARG, "more than 2^31 particles per handle");
     int64_t cap = std::max<int64_t>(want, s->cap + s->cap / 2);
     cap = std::min<int64_t>((cap + 1023) / 1024 * 1024, INT_MAX - 1024);
+    // every new buffer first; the handle is only touched once all of them exist
     Particles nb[2]{};
-    for (int b = 0; b < 2; ++b) ST_TRY(alloc_particles(nb[b], cap));
-    if (s->n > 0) {
+    int* tabs[4] = {nullptr, nullptr, nullptr, nullptr};   // gcell, rank, imm_list, src
+    fluid_status st = FLUID_OK;
+    for (int b = 0; b < 2 && st == FLUID_OK; ++b) st = alloc_particles(nb[b], cap);
+    for (int k = 0; k < 4 && st == FLUID_OK; ++k)
+        if (cudaMalloc(&tabs[k], cap * sizeof(int)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            st = fail(FLUID_ERR_OUT_OF_MEMORY, "ensure_capacity: device allocation failed");
+        }
+    if (st == FLUID_OK && s->n > 0) {
         const Particles& o = s->buf[s->cur];
-        CU_TRY(cudaMemcpyAsync(nb[0].P, o.P, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
-        CU_TRY(cudaMemcpyAsync(nb[0].V, o.V, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
-        CU_TRY(cudaMemcpyAsync(nb[0].CA, o.CA, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
-        CU_TRY(cudaMemcpyAsync(nb[0].CB, o.CB, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream));
-        CU_TRY(cudaMemcpyAsync(nb[0].CC, o.CC, s->n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream));
+        cudaError_t e = cudaMemcpyAsync(nb[0].P, o.P, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nb[0].V, o.V, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nb[0].CA, o.CA, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nb[0].CB, o.CB, s->n * sizeof(float4), cudaMemcpyDeviceToDevice, s->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(nb[0].CC, o.CC, s->n * sizeof(float), cudaMemcpyDeviceToDevice, s->stream);
+        if (e != cudaSuccess) st = fail(FLUID_ERR_CUDA, std::string("ensure_capacity: ") + cudaGetErrorString(e));
     }
-    CU_TRY(cudaStreamSynchronize(s->stream));
+    if (st == FLUID_OK && cudaStreamSynchronize(s->stream) != cudaSuccess) st = fail(FLUID_ERR_CUDA, "ensure_capacity: copy failed");
+    if (st != FLUID_OK) {   // the handle keeps its old buffers and capacity
+        for (int b = 0; b < 2; ++b) free_particles(nb[b]);
+        for (int k = 0; k < 4; ++k) cudaFree(tabs[k]);
+        (void)cudaGetLastError();
+        return st;
+    }
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->gcell);
     cudaFree(s->rank);
     cudaFree(s->imm_list);
     cudaFree(s->src);
-    s->gcell = s->rank = s->imm_list = s->src = nullptr;
-    s->sorted_valid = s->counts_pending = false;
     s->buf[0] = nb[0];
     s->buf[1] = nb[1];
     s->cur = 0;
-    CU_TRY(cudaMalloc(&s->gcell, cap * sizeof(int)));
-    CU_TRY(cudaMalloc(&s->rank, cap * sizeof(int)));
-    CU_TRY(cudaMalloc(&s->imm_list, cap * sizeof(int)));
-    CU_TRY(cudaMalloc(&s->src, cap * sizeof(int)));
+    s->gcell = tabs[0];
+    s->rank = tabs[1];
+    s->imm_list = tabs[2];
+    s->src = tabs[3];
+    s->sorted_valid = s->counts_pending = false;
     s->cap = cap;
     return FLUID_OK;
 }
@@ -662,7 +676,7 @@ __global__ void k_accumulate_planes(const __grid_constant__ Geo g, T* __restrict
 }
 
 __global__ void k_append_migrants(const __grid_constant__ Geo g, const float* __restrict__ rec, int m, Particles to,
-                                  int first, SortTables t, bool count) {
+                                  int first, SortTables t, bool count, int* __restrict__ n_lost) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = j < m;
     int cls = -1, bucket = 0;
@@ -676,6 +690,9 @@ __global__ void k_append_migrants(const __grid_constant__ Geo g, const float* __
         to.CB[d] = make_float4(r[10], r[11], r[12], r[13]);
         to.CC[d] = r[14];
         bucket = bucket_of<3>(g, p, cls);
+        // a record that belongs to neither this rank nor the rank it came from (it crossed a whole slab in one
+        // substep, or was appended by the caller outside the slab) would vanish at the next substep: count it
+        if (n_lost && bucket == migrated_bucket(g)) atomicAdd(n_lost, 1);
     }
     if (count) count_global(t, d, bucket, valid);   // `count` is uniform over the grid
 }
@@ -1140,6 +1157,12 @@ fluid_status fluid_particle_count(fluid_sim* s, int64_t* n_active) {
     return FLUID_OK;
 }
 
+fluid_status fluid_slot_count(const fluid_sim* s, int64_t* n_slots) {
+    if (!s || !n_slots) return fail(FLUID_ERR_INVALID_ARG, "fluid_slot_count: null argument");
+    *n_slots = s->n;
+    return FLUID_OK;
+}
+
 fluid_status fluid_read_particles(fluid_sim* s, float* records, int32_t* ids, int64_t capacity, int64_t* n_written) {
     if (!s || capacity < 0 || (capacity > 0 && !records)) return fail(FLUID_ERR_INVALID_ARG, "fluid_read_particles: bad argument");
     CU_TRY(cudaSetDevice(s->device));
@@ -1547,9 +1570,14 @@ fluid_status fluid_slab_migrants_end(fluid_sim* s, const void* d_recv_lower, con
     if (!d_recv_upper && s->peer.mig[1]) d_recv_upper = s->mig_recv[1];
     if (d_recv_lower) CU_TRY(cudaMemcpyAsync(h + 12, d_recv_lower, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     if (d_recv_upper) CU_TRY(cudaMemcpyAsync(h + 13, d_recv_upper, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
-    if (s->flags) CU_TRY(cudaMemcpyAsync(h + 14, s->flags + 2, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    h[14] = h[15] = 0;
+    if (s->flags) CU_TRY(cudaMemcpyAsync(h + 14, s->flags + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
     CU_TRY(cudaStreamSynchronize(s->stream));   // the one synchronisation of the substep
     if (s->flags && h[14]) return fail(FLUID_ERR_STATE, "fluid_slab_migrants_end: a peer barrier timed out (a neighbour rank stopped)");
+    if (s->flags && h[15])   // (counted by the append of the PREVIOUS substep: the records are gone by now)
+        return fail(FLUID_ERR_STATE, "fluid_slab_migrants_end: " + std::to_string(h[15]) +
+                    " received particle(s) lay outside this rank's slab and were lost (a particle crossed a whole slab in one "
+                    "substep: use thicker slabs)");
     if (h[12] > s->mig_cap || h[13] > s->mig_cap) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_migrants_end: a neighbour handed over more particles than the migrant buffer holds");
     if (h[SCAL_MIG_OVERFLOW]) return fail(FLUID_ERR_TOO_SMALL, "fluid_slab_migrants_end: more particles left the slab in one substep than the migrant buffer holds");
     n_out[0] = h[SCAL_MIG_LO];
@@ -1700,7 +1728,8 @@ fluid_status fluid_slab_append(fluid_sim* s, const void* d_records, int64_t n) {
     const bool join = s->sorted_valid && s->counts_pending;
     k_append_migrants<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, static_cast<const float*>(d_records),
                                                                 static_cast<int>(n), s->buf[s->cur],
-                                                                static_cast<int>(s->n), sort_tables(s), join);
+                                                                static_cast<int>(s->n), sort_tables(s), join,
+                                                                s->flags ? s->flags + 3 : nullptr);
     if (!join) s->sorted_valid = s->counts_pending = false;
     ++s->launches;
     CU_TRY(cudaGetLastError());

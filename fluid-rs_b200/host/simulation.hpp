@@ -73,7 +73,7 @@ class Simulation {
     // iter_particle (3d:383): a host copy of every particle stored in an a_rect block
     const std::vector<Particle<DIM>>& iter_particle(std::vector<int32_t>* ids = nullptr) {
         int64_t n = 0;
-        check(fluid_particle_count(h_, &n));
+        check(fluid_slot_count(h_, &n));   // upper bound, no device work
         readback_.resize(static_cast<size_t>(n));
         if (ids) ids->resize(static_cast<size_t>(n));
         check(fluid_read_particles(h_, reinterpret_cast<float*>(readback_.data()), ids ? ids->data() : nullptr, n, &n));

@@ -112,6 +112,10 @@ fluid_status fluid_substeps(fluid_sim* sim, int32_t n_substeps, const float* mou
 /* ---- Simulation::iter_particle (3d:383-387) ------------------------------------------ */
 /* Number of particles `iter_particle` would yield (those stored in a_rect blocks). */
 fluid_status fluid_particle_count(fluid_sim* sim, int64_t* n_active);
+/* Particle slots in use: an upper bound on what fluid_read_particles can return (every class, tombstones
+ * not yet compacted included).  No device work and no side effects, unlike the exact counts above and
+ * below, which re-run the neighbour search; size read-back buffers with this. */
+fluid_status fluid_slot_count(const fluid_sim* sim, int64_t* n_slots);
 /* Counts by class: [0] in a_rect blocks (advanced), [1] in the p_rect halo ring (deposit to
  * the grid but frozen, 3d:149 vs 3d:263), [2] outside p_rect (kept, ignored), [3] dropped so
  * far by migration out of p_rect (3d:356-366). */

@@ -306,42 +306,85 @@ def test_ragged_cell_occupancy(pkg, orc, scenes):
 
 
 # ---- long-run invariants ----------------------------------------------------------------------------
+# north_star: "over 1,000 steps, aggregate invariants (total mass, mean density error, kinetic energy,
+# free-surface height) must stay within a stated tolerance".  One step() = 31 substeps (3d:21,111), so this
+# is 31,000 substeps of the two default scenes (BASELINE configs 1 and 2), with the oracle beside the GPU at
+# seven checkpoints.  Trajectories are chaotic, so particles are not compared one by one; the tolerances
+# below are about 5x what the ORACLE ITSELF shows between two runs whose initial positions differ by one
+# ulp (measured: after 1,000 steps KE differs by 1.3 % in 2D and by 7 of 14 units in the settled 3D puddle,
+# the mean height by 0.007 cells, the 1 % height quantile by 0.1 cells, the mean density error by 0.002).
 
-def invariants(rec, dim, density):
+CHECKPOINT_STEPS = (1, 3, 10, 30, 100, 300, 1000)
+
+
+def invariants(rec, dim, density, rho0):
     m = rec[:, -1].astype(np.float64)
     v = rec[:, dim:2 * dim].astype(np.float64)
     return dict(count=rec.shape[0], mass=m.sum(), ke=0.5 * (m * (v * v).sum(axis=1)).sum(),
-                surface=float(rec[:, 1].min()),       # +y is down (3d:23): free surface = min y
-                y_mean=float(rec[:, 1].mean()))
+                surface=float(np.percentile(rec[:, 1], 1.0)),   # +y is down (3d:23): free surface = low-y edge (1 % quantile)
+                y_mean=float(rec[:, 1].mean()),
+                density_err=float(np.mean(np.abs(density.astype(np.float64) - rho0)) / rho0))
+
+
+def _long_run(step_fn, taps_fn, read_fn, dim, rho0, iters):
+    """Run to every checkpoint; the last substep of a checkpoint step is the tapped one."""
+    out, done = [], 0
+    for ck in CHECKPOINT_STEPS:
+        step_fn(ck * iters - done - 1)
+        density = taps_fn()
+        done = ck * iters
+        out.append(invariants(read_fn(), dim, density, rho0))
+    return out
+
+
+@pytest.fixture(scope="module")
+def oracle_long_runs(orc, scenes):
+    """Both oracle runs start in background threads (the C++ oracle releases the GIL) so that the
+    ~2.5 minutes of single-threaded CPU time of the 3D run overlap the 2D run and the GPU runs."""
+    import threading
+    runs = {}
+    for dim in (2, 3):
+        sc = scenes.default_2d(4096) if dim == 2 else scenes.default_3d(4096)
+        box = {}
+
+        def work(sc=sc, dim=dim, box=box):
+            ref = orc.OracleSim(sc.cfg)
+            ref.add_particles(sc.records())
+            ref.set_rect(sc.rect_min, sc.rect_max)
+            box["inv"] = _long_run(ref.substeps, lambda: oracle_substep_with_taps(ref)[0]["density"],
+                                   lambda: ref.read()[0], dim, sc.cfg["rest_density"], sc.cfg["iterations"])
+            ref.close()
+
+        t = threading.Thread(target=work)
+        t.start()
+        runs[dim] = (t, box, sc)
+    yield runs
+    for t, _, _ in runs.values():
+        t.join()
 
 
 @pytest.mark.parametrize("dim", [2, 3])
-def test_1000_substep_invariants(pkg, orc, scenes, dim):
-    sc = scenes.default_2d(2048) if dim == 2 else scenes.default_3d(4096)
-    rec = sc.records()
-    sim, ref = build_pair(pkg, orc, sc.cfg, rec, sc.rect_min, sc.rect_max)
-    sim.substeps(999)
-    ref.substeps(999)
-    gt = sim.debug_substep()
-    rt, _ = oracle_substep_with_taps(ref)
-    g_rec, _ = sim.read_particles()
-    r_rec, _ = ref.read()
-    gi, ri = invariants(g_rec, dim, gt["density"]), invariants(r_rec, dim, rt["density"])
-    assert gi["count"] == ri["count"] == sc.n
-    assert gi["mass"] == ri["mass"]
-    rho0 = sc.cfg["rest_density"]
-    g_derr = float(np.mean(np.abs(gt["density"] - rho0)) / rho0)
-    r_derr = float(np.mean(np.abs(rt["density"] - rho0)) / rho0)
-    # stated tolerances for chaotic 1000-substep trajectories:
-    assert abs(g_derr - r_derr) < 0.02                     # mean density error: 2 % of rho0
-    assert abs(gi["y_mean"] - ri["y_mean"]) < 0.25         # centre of mass height: 0.25 cell
-    assert abs(gi["surface"] - ri["surface"]) < 1.5        # free-surface height: 1.5 cells
-    ke_scale = max(ri["ke"], 1e-3 * sc.n)
-    assert abs(gi["ke"] - ri["ke"]) / ke_scale < 0.25      # kinetic energy: 25 % (settling sloshes)
-    pos = g_rec[:, :dim]
+def test_1000_step_invariants(pkg, scenes, oracle_long_runs, dim):
+    thread, box, sc = oracle_long_runs[dim]
+    sim = pkg.Simulation.new(sc.cfg, device=0)
+    sim.add_particles(sc.records())
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    got = _long_run(sim.substeps, lambda: sim.debug_substep()["density"], lambda: sim.read_particles()[0],
+                    dim, sc.cfg["rest_density"], sc.cfg["iterations"])
+    pos = sim.read_particles()[0][:, :dim]
     assert (pos >= 0).all() and (pos <= 64).all()
     sim.close()
-    ref.close()
+    thread.join()
+    want = box["inv"]
+    for ck, gi, ri in zip(CHECKPOINT_STEPS, got, want):
+        msg = f"dim {dim}, after {ck} steps: gpu {gi} oracle {ri}"
+        assert gi["count"] == ri["count"] == sc.n, msg                       # particle count: exact
+        assert gi["mass"] == ri["mass"], msg                                 # total mass: exact
+        assert abs(gi["density_err"] - ri["density_err"]) < 0.01, msg        # mean density error: 1 % of rho0
+        assert abs(gi["y_mean"] - ri["y_mean"]) < 0.05, msg                  # centre-of-mass height: 0.05 cell
+        assert abs(gi["surface"] - ri["surface"]) < 0.5, msg                 # free-surface height: 0.5 cell
+        # kinetic energy: 10 % of max(KE_ref, 0.05 N) (the settled 3D puddle holds ~15 units of noise-like KE)
+        assert abs(gi["ke"] - ri["ke"]) < 0.10 * max(ri["ke"], 0.05 * sc.n), msg
 
 
 # ---- BASELINE full sizes: size-independent properties -------------------------------------------------

@@ -105,6 +105,16 @@ int main() {
         for (int l = 0; l < 32; l += 2) odd[l] = 1;
         P("consecutive, odd lanes off", [](int l) { return l; }, odd);
         P("even lanes: 16 distinct groups across warp", [](int l) { return l / 2 + 8 * 9 * (l % 2); }, odd);
+        // idle quarters whose lanes mirror lane 0's address (what the tile kernels do): is the quarter free?
+        P("quarter 3 off, mirrors lane 0", [](int l) { return l < 24 ? l : 0; }, q3);
+        P("lanes 16..31 off, mirror lane 0", [](int l) { return l < 16 ? l : 0; }, half);
+        std::vector<int> q0(32, 0);
+        for (int l = 0; l < 8; ++l) q0[l] = 1;
+        P("only quarter 0 on, rest mirror lane 0", [](int l) { return l < 8 ? l : 0; }, q0);
+        P("only quarter 0 on, rest consecutive", [](int l) { return l; }, q0);
+        std::vector<int> l20(32, 0);
+        for (int l = 0; l < 20; ++l) l20[l] = 1;
+        P("lanes 0..19 on, 20..23 mirror lane 16, q3 mirrors 0", [](int l) { return l < 20 ? l : (l < 24 ? 16 : 0); }, l20);
     }
     // scalar
     auto S = [&](const char* name, auto f) {
