@@ -342,14 +342,13 @@ def run_ours(args):
     launches = sim.launch_count() - launches0
     clocks = sampler.stop()
     # occupancy of the last timed substep (from the engine's tile list; outside the timed region)
-    tiles_now = sim.debug_tiles()           # rows {tile, first slot, N, W, overflow}
+    tiles_now = sim.debug_tiles()
     tiles_now = tiles_now[tiles_now[:, 2] > 0]
     occupancy = None
-    if len(tiles_now) and sc.dim == 3:
-        n_t, w_t, o_t = (tiles_now[:, k].astype(np.int64) for k in (2, 3, 4))
+    if len(tiles_now):
+        n_t, w_t = tiles_now[:, 2].astype(np.int64), tiles_now[:, 3].astype(np.int64)
         occupancy = {"active_tiles": int(len(tiles_now)), "particles_per_tile": float(n_t.mean()),
-                     "window_fill": float((n_t - o_t).sum() / (32.0 * w_t.sum())),
-                     "overflow_frac": float(o_t.sum() / n_t.sum()),
+                     "window_fill": float(n_t.sum() / (32.0 * w_t.sum())),
                      "A_over_N": float(len(tiles_now) * 256 / sc.n),
                      "A_note": "A = nodes of the 8x8x4 blocks of the tiles that hold particles (SURVEY.md 8d fixes A/N = 1 "
                                "for the roofline; the rim the stencils reach adds about a quarter)"}

@@ -383,20 +383,12 @@ class Simulation:
         return dict(ids=ids[:n], cell=cell[:n], key=key[:n], density=den[:n], pressure=prs[:n])
 
     def debug_tiles(self):
-        """Active tile list of the current sort (after neighbour_table()), one row per tile:
-        {tile, first slot, N, W, overflow}: W windows hold the slots [first, first + N - overflow), the
-        overflow segment follows (sort.cuh: the raw entry packs W | overflow << 6, or -W)."""
+        """Active tile list {tile, first slot, N, W} of the current sort (after neighbour_table())."""
         n = C.c_int64()
         _check(lib().fluid_debug_tiles(self._h, 0, None, C.byref(n)))
-        raw = np.empty((max(n.value, 1), 4), dtype=np.int32)
-        _check(lib().fluid_debug_tiles(self._h, n.value, raw.ctypes.data_as(_ip), C.byref(n)))
-        raw = raw[: n.value]
-        wf = raw[:, 3]
-        out = np.empty((raw.shape[0], 5), dtype=np.int32)
-        out[:, :3] = raw[:, :3]
-        out[:, 3] = np.where(wf < 0, -wf, wf & 63)
-        out[:, 4] = np.where(wf < 0, 0, wf >> 6)
-        return out
+        out = np.empty((max(n.value, 1), 4), dtype=np.int32)
+        _check(lib().fluid_debug_tiles(self._h, n.value, out.ctypes.data_as(_ip), C.byref(n)))
+        return out[: n.value]
 
     def neighbour_table(self):
         c = self.particle_counts()

@@ -110,7 +110,6 @@ struct TileCtx {
     int tile;      // tile id
     int base;      // first particle slot
     int count;     // particles in the tile
-    int n_main;    // of them in the window sequence; slots [n_main, count) are the overflow segment (sort.cuh)
     int windows;   // W
     int per, extra;
     bool edge;     // the footprint sticks out of the p_rect grid
@@ -123,10 +122,9 @@ __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileC
     tc.tile = t;
     tc.base = e.y;
     tc.count = e.z;
-    tc.windows = tile_windows(e.w);
-    tc.n_main = e.z - tile_overflow(e.w);
-    tc.per = tc.n_main / tc.windows;
-    tc.extra = tc.n_main - tc.per * tc.windows;
+    tc.windows = e.w;
+    tc.per = e.z / e.w;
+    tc.extra = e.z - tc.per * e.w;
     int tx = t % g.tdim[0];
     int r = t / g.tdim[0];
     int ty = r % g.tdim[1];
@@ -190,7 +188,6 @@ struct TStencil {
     int node0;                   // shared-memory slot of stencil offset (0,0,0) in a float4 tile
     int node0q;                  // stencil column (0,0) in a mass tile: x + 10*y + 104*(lz >> 1)
     float wq[4];                 // z weights laid over the quad: nodes (lz & 1) .. (lz & 1) + 2
-    int lx, ly, lz;              // cell inside the tile (only the overflow paths read these)
 };
 
 __device__ __forceinline__ void axis_weights(float c, float* w) {
@@ -224,9 +221,6 @@ __device__ __forceinline__ void tile_stencil(const Geo& g, const TileCtx& tc, fl
     int lx = min(max(rx - tc.c0[0], 0), T3::X - 1);
     int ly = min(max(ry - tc.c0[1], 0), T3::Y - 1);
     int lz = min(max(rz - tc.c0[2], 0), T3::Z - 1);
-    s.lx = lx;
-    s.ly = ly;
-    s.lz = lz;
     s.node0 = lx + T3::NX * ly + T3::PLANE * lz;
     s.node0q = lx + T3::NX * ly + T3::PLANE * (lz >> 1);
     const bool hi = (lz & 1) != 0;
@@ -376,33 +370,9 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                     __syncwarp();
                 }
         }
+        // flush: lane -> footprint column c = lane + 32*it (100 columns), six nodes along z
         float* peer_lo = (PEER && tc.c0[2] == g.slab_lo) ? ph.gmass[0] : nullptr;              // warp-uniform
         float* peer_hi = (PEER && tc.c0[2] + T3::Z == g.slab_hi) ? ph.gmass[1] : nullptr;
-        // overflow segment (particles beyond W in their column, sort.cuh): straight to the node masses
-        for (int it = tc.n_main; it < tc.count; it += 32) {
-            if (it + lane < tc.count) {
-                const float4 p = __ldg(&P[__ldg(&src[tc.base + it + lane])]);
-                TStencil s;
-                tile_stencil(g, tc, p.x, p.y, p.z, s);
-#pragma unroll
-                for (int oz = 0; oz < 3; ++oz)
-#pragma unroll
-                    for (int oy = 0; oy < 3; ++oy)
-#pragma unroll
-                        for (int ox = 0; ox < 3; ++ox) {
-                            const float w = s.wx[ox] * s.wy[oy] * s.wz[oz] * p.w;
-                            if (w != 0.0f) {   // (zero outside the grid: the index is never formed from a bad node)
-                                const int k = s.lz + oz;   // footprint plane
-                                const int gi = g.guard + (tc.c0[0] - 1 + s.lx + ox) +
-                                               ((tc.c0[1] - 1 + s.ly + oy) + (tc.c0[2] - 1 + k) * g.size[1]) * g.size[0];
-                                atomicAdd(&gmass[gi], w);
-                                if (PEER && k < 2 && peer_lo) red_add_sys(&peer_lo[gi], w);
-                                if (PEER && k >= 4 && peer_hi) red_add_sys(&peer_hi[gi], w);
-                            }
-                        }
-            }
-        }
-        // flush: lane -> footprint column c = lane + 32*it (100 columns), six nodes along z
 #pragma unroll
         for (int it = 0; it < 4; ++it) {
             const int c = lane + 32 * it;
@@ -635,70 +605,6 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                     if (active) nd[2 * T3::PLANE] = a2;
                     __syncwarp();
                 }
-            }
-        }
-        // overflow segment (particles beyond W in their column, sort.cuh): same density / stress, but the 27
-        // deposits go straight to the node records with vector reductions (a per cent or two of the particles)
-        for (int it = tc.n_main; it < tc.count; it += 32) {
-            if (it + lane < tc.count) {
-                const int d = tc.base + it + lane;
-                PRec cur;
-                load_prec(q, __ldg(&src[d]), true, cur);
-                TStencil s;
-                tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
-                float density = 0.0f;
-#pragma unroll
-                for (int oy = 0; oy < 3; ++oy) {
-                    const float4* row = ms + s.node0q + T3::NX * oy;
-                    float rs = 0.0f;
-#pragma unroll
-                    for (int ox = 0; ox < 3; ++ox) {
-                        const float4 q4 = row[ox];
-                        rs += (q4.x * s.wq[0] + q4.y * s.wq[1] + q4.z * s.wq[2] + q4.w * s.wq[3]) * s.wx[ox];
-                    }
-                    density += rs * s.wy[oy];
-                }
-                const float m = cur.p.w;
-                const float volume = m * __frcp_rn(density);
-                const float pressure = tait_pressure_fast(g, density);
-                if (dbg_density) dbg_density[d] = density;
-                if (dbg_pressure) dbg_pressure[d] = pressure;
-                const float C[9] = {cur.ca.x, cur.ca.y, cur.ca.z, cur.ca.w, cur.cb.x, cur.cb.y, cur.cb.z, cur.cb.w, cur.cc};
-                const float s1 = -4.0f * volume * g.dt;
-                float M[9];
-#pragma unroll
-                for (int c = 0; c < 3; ++c)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        float stress = g.mu * (C[3 * c + r] + C[3 * r + c]);
-                        if (c == r) stress -= pressure;
-                        M[3 * c + r] = m * C[3 * c + r] + s1 * stress;
-                    }
-                const float dx0 = -1.0f - s.cx, dy0 = -1.0f - s.cy, dz0 = -1.0f - s.cz;
-                const float b0 = m * cur.v.x + M[0] * dx0 + M[3] * dy0 + M[6] * dz0;
-                const float b1 = m * cur.v.y + M[1] * dx0 + M[4] * dy0 + M[7] * dz0;
-                const float b2 = m * cur.v.z + M[2] * dx0 + M[5] * dy0 + M[8] * dz0;
-                float4* peer_lo = (PEER && tc.c0[2] == g.slab_lo) ? ph.grid[0] : nullptr;
-                float4* peer_hi = (PEER && tc.c0[2] + T3::Z == g.slab_hi) ? ph.grid[1] : nullptr;
-#pragma unroll 1
-                for (int oz = 0; oz < 3; ++oz)
-#pragma unroll
-                    for (int oy = 0; oy < 3; ++oy)
-#pragma unroll
-                        for (int ox = 0; ox < 3; ++ox) {
-                            const float w = s.wx[ox] * s.wy[oy] * s.wz[oz];
-                            if (w != 0.0f) {   // (zero outside the grid: the index is never formed from a bad node)
-                                const float4 v = make_float4(w * (b0 + ox * M[0] + oy * M[3] + oz * M[6]),
-                                                             w * (b1 + ox * M[1] + oy * M[4] + oz * M[7]),
-                                                             w * (b2 + ox * M[2] + oy * M[5] + oz * M[8]), w * m);
-                                const int k = s.lz + oz;   // footprint plane
-                                const int gi = g.guard + (tc.c0[0] - 1 + s.lx + ox) +
-                                               ((tc.c0[1] - 1 + s.ly + oy) + (tc.c0[2] - 1 + k) * g.size[1]) * g.size[0];
-                                atomicAdd(&grid[gi], v);
-                                if (PEER && k < 2 && peer_lo) red_add_sys(&peer_lo[gi], v);
-                                if (PEER && k >= 4 && peer_hi) red_add_sys(&peer_hi[gi], v);
-                            }
-                        }
             }
         }
         if (TMA && !tc.edge) {   // (tiles on the rim of the grid keep the per-node path: their boxes stick out of the tensor)

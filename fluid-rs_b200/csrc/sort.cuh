@@ -296,15 +296,6 @@ k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, in
 //                   quarter warp hit 8 different 16-byte bank groups of the float4 node tile.
 //                 The tile list carries W: {tile, first slot, N, W}; window w holds the slots
 //                 [w*(N/W) + min(w, N%W), + N/W + (w < N%W)).
-//                 OVERFLOW.  Letting the fullest column set W wastes lanes (one crowded column of 10 stretches
-//                 a 224-particle tile from 7 windows to 10).  So, where the merge table applies (W0 = ceil(N/32)
-//                 <= 32), W = W0 and every column keeps only its first W particles (cell order, then rank) in
-//                 the window sequence; the rest — a per cent or two of a settled fluid — form the tile's
-//                 OVERFLOW SEGMENT behind the windows, [first + N_main, first + N), and the tile kernels
-//                 deposit them with global reductions instead (phases_tiled.cuh).  The formulas above then run
-//                 on the main sequence: q' = q - (overflow particles of earlier columns), N -> N_main.
-//                 Tile list entry: {tile, first slot, N, W | overflow << 6}; tiles that are too crowded for the
-//                 merge table keep the old rule and carry -W (no overflow).
 enum TileOrder : int { ORDER_CELL = 0, ORDER_CLASS_RR = 1 };
 
 // floor(x / w) for 0 <= x < 8192, 1 <= w <= 32 without an integer division: (x + 0.5) / w is at least
@@ -315,13 +306,7 @@ __device__ __forceinline__ int small_div(int x, float inv_w) {
 
 constexpr int PERM_WARPS = 4;
 constexpr int PERM_MAX_W = 32;   // windows per tile covered by the in-window merge table
-constexpr int TAB_WIN_BYTES = PERM_MAX_W * 8;   // per listed tile: members of class b in window w, one byte each ...
-constexpr int TILE_COLS = 64;                   // ... then, as uint16: overflow particles before column c (c = 0..63), total at [64]
-constexpr int TAB_BYTES = TAB_WIN_BYTES + 136;  // 8-byte aligned rows
-
-// tile-list entry .w: W | overflow << 6 (merge table applies, W <= 32), or -W (no merge, no overflow)
-__host__ __device__ __forceinline__ int tile_windows(int w_field) { return w_field < 0 ? -w_field : (w_field & 63); }
-__host__ __device__ __forceinline__ int tile_overflow(int w_field) { return w_field < 0 ? 0 : (w_field >> 6); }
+constexpr int TAB_BYTES = PERM_MAX_W * 8;   // per listed tile: members of class b in window w, one byte each
 
 // What k_build_src needs to place a particle of a tile: {W (0 = plain cell order), tile-list entry}
 // W < 0: |W| windows but no class merge (more than PERM_MAX_W windows or >= 8192 particles).
@@ -374,7 +359,7 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
             if (lane == 0) {
                 cell_off[c_first] = base;
                 count[c_first] = 0;
-                tiles[a] = make_int4(t, base, 0, -1);  // listed, but nothing for the tile kernels to do
+                tiles[a] = make_int4(t, base, 0, 1);   // listed, but nothing for the tile kernels to do
                 tile_info[t] = make_int2(0, a);
             }
             continue;
@@ -426,45 +411,31 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
         }
         if (ORDER == ORDER_CELL) {
             if (lane == 0) {
-                tiles[a] = make_int4(t, base, n_t, -max((n_t + 31) / 32, 1));
+                tiles[a] = make_int4(t, base, n_t, (n_t + 31) / 32);
                 tile_info[t] = make_int2(0, a);
             }
             continue;
         }
-        const int col_a = cnt[0] + cnt[1] + cnt[2] + cnt[3], col_b = cnt[4] + cnt[5] + cnt[6] + cnt[7];
-        const int w0 = (n_t + 31) / 32;
-        const bool merge = w0 <= PERM_MAX_W && n_t < 8192;
-        // merge: W = ceil(N/32), columns above W overflow; else the fullest column sets W and nothing overflows
-        const int w_count = merge ? w0 : max(w0, __reduce_max_sync(0xffffffffu, max(col_a, col_b)));
-        const int ovf_a = merge ? max(col_a - w_count, 0) : 0, ovf_b = merge ? max(col_b - w_count, 0) : 0;
-        const int ovf_inc = warp_inclusive_scan(ovf_a + ovf_b);
-        const int ovf_first = ovf_inc - (ovf_a + ovf_b);          // overflow particles of the columns before mine
-        const int ovf_total = __shfl_sync(0xffffffffu, ovf_inc, 31);
+        const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
+        const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
+        const bool merge = w_count <= PERM_MAX_W && n_t < 8192;
         if (lane == 0) {
-            tiles[a] = make_int4(t, base, n_t, merge ? (w_count | (ovf_total << 6)) : -w_count);   // list slot = candidate index: no atomics
+            tiles[a] = make_int4(t, base, n_t, w_count);   // list slot = candidate index: no atomics
             tile_info[t] = make_int2(merge ? w_count : -w_count, a);
         }
         if (!merge) continue;
-        unsigned char* my_tab = tab + static_cast<size_t>(a) * TAB_BYTES;
-        {   // overflow before each of my two columns (uint16 pairs), the total behind them
-            unsigned* co = reinterpret_cast<unsigned*>(my_tab + TAB_WIN_BYTES);
-            co[lane] = static_cast<unsigned>(ovf_first) | (static_cast<unsigned>(ovf_first + ovf_a) << 16);
-            if (lane == 0) co[32] = static_cast<unsigned>(ovf_total);
-        }
-        // the window sequence = the cell order without the overflow particles
-        const int mine_main = mine - (ovf_a + ovf_b);
-        const int q_main = q_first - ovf_first;
         // class totals N_b (lanes 4b..4b+3 hold class b) and class starts S_b
-        int n_cls = mine_main;
+        int n_cls = mine;
         n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 1);
         n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 2);
-        const int s_cls = __shfl_sync(0xffffffffu, q_main, lane & ~3);   // start of my class
+        const int s_cls = __shfl_sync(0xffffffffu, q_first, lane & ~3);   // start of my class
         const float inv_w = 1.0f / static_cast<float>(w_count);
         // tab[w*8 + b] = members of class b in window w: those q in [S_b, S_b + N_b) with q = w (mod W)
         const int b = lane & 7;
         const int nb = __shfl_sync(0xffffffffu, n_cls, 4 * b);
         const int sb = __shfl_sync(0xffffffffu, s_cls, 4 * b);
         const int sb_mod = sb - small_div(sb, inv_w) * w_count;
+        unsigned char* my_tab = tab + static_cast<size_t>(a) * TAB_BYTES;
         for (int w = lane >> 3; w < w_count; w += 4) {
             int off = w - sb_mod;
             if (off < 0) off += w_count;
@@ -479,11 +450,8 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
 // order and the gathers stay nearly coalesced.
 //
 // Slot of a particle with (bucket, rank): q = cellStart[bucket] - first slot of the tile + rank is its
-// position in the tile's class-major cell order.  Its rank inside its (x,y) column is cellStart[bucket] -
-// cellStart[first cell of the column] + rank: from W on it belongs to the overflow segment.  Otherwise
-// q' = q - (overflow particles of earlier columns) is its position in the window sequence; window w = q' mod W;
-// inside the window the classes are merged round robin (ORDER_CLASS_RR above): with k = my index among my
-// class's members of the window,
+// position in the tile's class-major cell order; window w = q mod W; inside the window the classes are
+// merged round robin (ORDER_CLASS_RR above): with k = my index among my class's members of the window,
 //     pos = sum_b min(n_b, k) + #{b < my class : n_b > k},   n_b = tab[w][b].
 __global__ void __launch_bounds__(256)
 k_build_src(int n, const int* __restrict__ gcell, const int* __restrict__ rank,
@@ -510,26 +478,16 @@ k_build_src(int n, const int* __restrict__ gcell, const int* __restrict__ rank,
         slot = base + w * per + min(w, extra) + pos;
     } else {
         const int w_count = info.x;
-        const unsigned char* my_tab = tab + static_cast<size_t>(info.y) * TAB_BYTES;
-        const unsigned short* col_ovf = reinterpret_cast<const unsigned short*>(my_tab + TAB_WIN_BYTES);
-        const int local = bucket & (TILE_CELLS - 1);
-        const int col_rank = q_abs - __ldg(&cell_off[bucket & ~3]);
-        const int n_main = n_t - static_cast<int>(__ldg(&col_ovf[TILE_COLS]));
-        if (col_rank >= w_count) {   // overflow segment: behind the windows, in cell order
-            src[base + n_main + static_cast<int>(__ldg(&col_ovf[local >> 2])) + (col_rank - w_count)] = i;
-            return;
-        }
-        const int qm = q - static_cast<int>(__ldg(&col_ovf[local >> 2]));   // position in the window sequence
         const float inv_w = 1.0f / static_cast<float>(w_count);
-        const int per = small_div(n_main, inv_w), extra = n_main - per * w_count;
-        const int w = qm - small_div(qm, inv_w) * w_count;
-        const int cls = local >> 5;
-        const int s_cls = __ldg(&cell_off[(t << 8) + (cls << 5)]) - base - static_cast<int>(__ldg(&col_ovf[cls * 8]));
+        const int per = small_div(n_t, inv_w), extra = n_t - per * w_count;
+        const int w = q - small_div(q, inv_w) * w_count;
+        const int cls = (bucket & (TILE_CELLS - 1)) >> 5;
+        const int s_cls = __ldg(&cell_off[(t << 8) + (cls << 5)]) - base;
         const int s_mod = s_cls - small_div(s_cls, inv_w) * w_count;
         int off = w - s_mod;
         if (off < 0) off += w_count;
-        const int k = small_div(qm - (s_cls + off), inv_w);   // my index among my class in window w
-        const uint2 row = __ldg(reinterpret_cast<const uint2*>(my_tab + w * 8));
+        const int k = small_div(q - (s_cls + off), inv_w);   // my index among my class in window w
+        const uint2 row = __ldg(reinterpret_cast<const uint2*>(tab + static_cast<size_t>(info.y) * TAB_BYTES + w * 8));
         const unsigned kk = static_cast<unsigned>(min(k, 255)) * 0x01010101u;
         // sum_b min(n_b, k): per-byte minimum, then the byte sum
         int pos = __vsadu4(__vminu4(row.x, kk), 0u) + __vsadu4(__vminu4(row.y, kk), 0u);

@@ -538,7 +538,7 @@ def test_slab_entry_points_on_one_gpu(pkg, scenes):
 def test_windows_hold_distinct_columns(pkg, scenes):
     """The invariant the shared-memory read-modify-writes rely on (sort.cuh, ORDER_CLASS_RR): inside
     one window of one tile no two particles share an (x,y) cell column, windows are <= 32 particles,
-    and windows + overflow segment cover the tile's slots exactly.  Checked on the host from the engine's own tables, on a
+    and they cover the tile's slots exactly.  Checked on the host from the engine's own tables, on a
     sloshing scene over several substeps and on a deliberately crowded one."""
     def check(sim, sc):
         ids, cidx = sim.neighbour_table()
@@ -548,10 +548,9 @@ def test_windows_hold_distinct_columns(pkg, scenes):
         x, y = cidx % sx, (cidx // sx) % sy
         col = x.astype(np.int64) + 100000 * y
         seen = 0
-        for t, first, n, w, ovf in tiles.tolist():
-            n_main = n - ovf                         # the windows; [n_main, n) is the overflow segment (global reductions)
-            per, extra = divmod(n_main, w)
-            assert w >= -(-n_main // 32) and 0 <= ovf < n
+        for t, first, n, w in tiles.tolist():
+            per, extra = divmod(n, w)
+            assert w >= -(-n // 32)
             off = first
             for k in range(w):
                 ln = per + (1 if k < extra else 0)
@@ -559,10 +558,7 @@ def test_windows_hold_distinct_columns(pkg, scenes):
                 c = col[off:off + ln]
                 assert len(np.unique(c)) == ln, (t, k)
                 off += ln
-            assert off == first + n_main
-            if ovf:                                  # overflow = exactly the particles beyond W in their column
-                cnt = np.bincount(np.unique(col[first:first + n], return_inverse=True)[1])
-                assert ovf == int(np.maximum(cnt - w, 0).sum()), (t, ovf)
+            assert off == first + n
             seen += n
         assert seen == len(ids)
 

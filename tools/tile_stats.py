@@ -22,13 +22,11 @@ def main():
         sim.neighbour_table()
         t = sim.debug_tiles()
         t = t[t[:, 2] > 0]
-        n, w, ovf = (t[:, j].astype(np.int64) for j in (2, 3, 4))    # rows {tile, first, N, W, overflow}
+        n, w = t[:, 2].astype(np.int64), t[:, 3].astype(np.int64)
         need = (n + 31) // 32
-        quarters = ((n - ovf) // w + 7) // 8 * (w - (n - ovf) % w) + ((n - ovf) // w + 1 + 7) // 8 * ((n - ovf) % w)
         print(f"after {k} steps: tiles {len(t)} particles {n.sum()} mean N {n.mean():.1f} "
-              f"fill {(n - ovf).sum() / (32.0 * w.sum()):.3f} overflow {ovf.sum() / n.sum():.4f} "
-              f"lanes per active quarter warp {(n - ovf).sum() / (8.0 * quarters.sum()):.3f} "
-              f"mean W {w.mean():.2f} mean ceil(N/32) {need.mean():.2f}", flush=True)
+              f"fill {n.sum() / (32.0 * w.sum()):.3f} fill_if_no_column_rule {n.sum() / (32.0 * need.sum()):.3f} "
+              f"mean W {w.mean():.2f} mean ceil(N/32) {need.mean():.2f} W>need in {np.mean(w > need):.3f}", flush=True)
         if k < steps:
             sim.step()
     sim.close()
