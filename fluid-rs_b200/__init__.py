@@ -81,6 +81,8 @@ SIGNATURES = {
     "fluid_clear_particles": (C.c_int, [C.c_void_p]),
     "fluid_step": (C.c_int, [C.c_void_p, _fp]),
     "fluid_substeps": (C.c_int, [C.c_void_p, C.c_int32, _fp]),
+    "fluid_set_deterministic": (C.c_int, [C.c_void_p, C.c_int32]),
+    "fluid_set_resident_max": (C.c_int, [C.c_void_p, C.c_int64]),
     "fluid_particle_count": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_particle_counts": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_slot_count": (C.c_int, [C.c_void_p, _i64p]),
@@ -251,6 +253,14 @@ class Simulation:
     def substeps(self, n: int, mouse_pos=None):
         keep, p = self._mouse(mouse_pos)
         _check(lib().fluid_substeps(self._h, int(n), p))
+
+    def set_deterministic(self, on: bool = True):
+        """Order-independent (64-bit fixed-point) node sums: bit-for-bit reproducible runs."""
+        _check(lib().fluid_set_deterministic(self._h, 1 if on else 0))
+
+    def set_resident_max(self, max_particles: int):
+        """Largest particle count whose step() runs as one cooperative launch (0 = never)."""
+        _check(lib().fluid_set_resident_max(self._h, int(max_particles)))
 
     def iter_particle(self):
         """`iter_particle` (3d:383-387): yields (id, record) for every a_rect particle."""

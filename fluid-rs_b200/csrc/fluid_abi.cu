@@ -127,6 +127,14 @@ struct fluid_sim {
     int* class_count = nullptr;   // 4 ints (device)
 
     float4* grid = nullptr;      // {momentum.xyz, mass} per node, reference layout + guards
+    float4* grid2 = nullptr;     // second node buffer of the resident small-scene kernel (allocated on first use)
+    long long* fx[2] = {nullptr, nullptr};   // deterministic mode: 4 fixed-point sums per node (phases_generic.cuh)
+    bool det = false;            // FLUID_B200_DETERMINISTIC=1 / fluid_set_deterministic: order-independent node sums
+    bool grid_is_fixed = false;  // the last substep left its node sums in fx[0], not in `grid`
+    int64_t resident_max = 16384;   // step() of at most this many particles runs as ONE cooperative launch
+    bool coop = false;           // device supports cooperative launches
+    unsigned long long* d_stamps = nullptr;   // %globaltimer stamps of the resident kernel's last substep
+    bool resident_timed = false; // the phase timers of the last substep are in d_stamps, not in events
     float* gmass = nullptr;      // node masses alone (p2g 1 output, read by p2g 2), same layout
     int64_t grid_nodes = 0;      // reference node count (without guards)
     bool tiled = true;           // 3D: tiled sm_100a kernels; FLUID_B200_GENERIC=1 forces the generic ones
@@ -464,6 +472,58 @@ fluid_status clear_mass_rim(fluid_sim* s, bool fused) {
     return FLUID_OK;
 }
 
+// deterministic mode: the fixed-point node sums (count = 1: generic kernels, 2: the resident kernel's two buffers)
+fluid_status ensure_fixed(fluid_sim* s, int count) {
+    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    for (int b = 0; b < count; ++b)
+        if (!s->fx[b]) CU_TRY(cudaMalloc(&s->fx[b], n_alloc * 4 * sizeof(long long)));
+    return FLUID_OK;
+}
+
+// step() / substeps() of a small scene as ONE cooperative launch (k_substeps_resident, phases_generic.cuh).
+bool resident_eligible(const fluid_sim* s) {
+    return s->coop && s->rect_set && s->n > 0 && s->n <= s->resident_max && !s->geo.slab_on && !s->profiling;
+}
+
+template <int DIM, bool DET>
+fluid_status resident_launch(fluid_sim* s, const float* d_mouse, int n_substeps, unsigned blocks) {
+    const Geo geo = s->geo;
+    Particles q = s->buf[s->cur];
+    int n = static_cast<int>(s->n);
+    NodeGrid g0{s->grid, s->fx[0]}, g1{s->grid2, s->fx[1]};
+    unsigned long long* stamps = s->d_stamps;
+    void* args[] = {const_cast<Geo*>(&geo), &q, &n, &g0, &g1, &d_mouse, &n_substeps, &stamps};
+    CU_TRY(cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(&k_substeps_resident<DIM, DET>), dim3(blocks), dim3(128), args, 0,
+                                       s->stream));
+    return FLUID_OK;
+}
+
+fluid_status substeps_resident(fluid_sim* s, const float* d_mouse, int n_substeps) {
+    if (n_substeps <= 0) return FLUID_OK;
+    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    if (!s->grid2) CU_TRY(cudaMalloc(&s->grid2, n_alloc * sizeof(float4)));
+    if (!s->d_stamps) CU_TRY(cudaMalloc(&s->d_stamps, 8 * sizeof(unsigned long long)));
+    if (s->det) ST_TRY(ensure_fixed(s, 2));
+    // both node buffers clean at the start (the kernel only clears what it wrote itself)
+    if (s->det) {
+        CU_TRY(cudaMemsetAsync(s->fx[0], 0, n_alloc * 4 * sizeof(long long), s->stream));
+        CU_TRY(cudaMemsetAsync(s->fx[1], 0, n_alloc * 4 * sizeof(long long), s->stream));
+    } else {
+        CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+        CU_TRY(cudaMemsetAsync(s->grid2, 0, n_alloc * sizeof(float4), s->stream));
+    }
+    const unsigned blocks = blocks_for(s->n, 128);
+    if (s->dim == 3) ST_TRY(s->det ? (resident_launch<3, true>(s, d_mouse, n_substeps, blocks)) : (resident_launch<3, false>(s, d_mouse, n_substeps, blocks)));
+    else ST_TRY(s->det ? (resident_launch<2, true>(s, d_mouse, n_substeps, blocks)) : (resident_launch<2, false>(s, d_mouse, n_substeps, blocks)));
+    ++s->launches;
+    s->grid_is_fixed = s->det;
+    s->grid_clean = false;                              // the tiled path wipes the grid before it runs again
+    s->sorted_valid = s->counts_pending = false;        // positions moved; nothing was sorted
+    s->timers_recorded = true;
+    s->resident_timed = true;
+    return FLUID_OK;
+}
+
 // One substep = clear -> p2g 1 -> p2g 2 -> update -> g2p (3d:111-133).  `phases` selects the parts
 // (slab runs exchange halo planes between them): 1 = sort + clear + p2g 1, 2 = p2g 2, 4 = update + g2p.
 template <int DIM>
@@ -526,10 +586,18 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
-            CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+            if (s->det) {
+                ST_TRY(ensure_fixed(s, 1));
+                CU_TRY(cudaMemsetAsync(s->fx[0], 0, n_alloc * 4 * sizeof(long long), s->stream));
+            } else {
+                CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
+            }
+            s->grid_is_fixed = s->det;
             s->grid_clean = false;
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-            k_p2g1_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid);
+            const NodeGrid ng{s->grid, s->fx[0]};
+            if (s->det) k_p2g1_generic<DIM, true><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng);
+            else k_p2g1_generic<DIM, false><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng);
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         }
@@ -550,10 +618,13 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             else P2G_LAUNCH(false, false);
 #undef P2G_LAUNCH
         }
-        else
-            k_p2g2_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid,
-                                                                          dbg ? dbg->density : nullptr,
-                                                                          dbg ? dbg->pressure : nullptr);
+        else {
+            const NodeGrid ng{s->grid, s->fx[0]};
+            float* dd = dbg ? dbg->density : nullptr;
+            float* dp = dbg ? dbg->pressure : nullptr;
+            if (s->det) k_p2g2_generic<DIM, true><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, dd, dp);
+            else k_p2g2_generic<DIM, false><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, dd, dp);
+        }
         ++s->launches;
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
     }
@@ -585,7 +656,9 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             s->cur ^= 1;
             s->counts_pending = true;
         } else {
-            k_g2p_generic<DIM><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, s->grid, d_mouse);
+            const NodeGrid ng{s->grid, s->fx[0]};
+            if (s->det) k_g2p_generic<DIM, true><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, d_mouse);
+            else k_g2p_generic<DIM, false><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, d_mouse);
             ++s->launches;
             s->sorted_valid = false;   // positions moved; the generic path re-sorts from scratch
         }
@@ -593,6 +666,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             CU_TRY(cudaEventRecord(ev[5], s->stream));
             s->last_ev = ev;
             s->timers_recorded = true;
+            s->resident_timed = false;
         }
     }
     CU_TRY(cudaGetLastError());
@@ -779,6 +853,16 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     s->stream = s->own_stream;
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
+    if (const char* e = std::getenv("FLUID_B200_DETERMINISTIC")) {
+        s->det = e[0] == '1';
+        if (s->det) s->tiled = false;
+    }
+    {
+        int coop = 0;
+        cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+        s->coop = coop != 0;
+        if (const char* e = std::getenv("FLUID_B200_RESIDENT_MAX")) s->resident_max = std::atoll(e);
+    }
 
     cudaFuncSetAttribute(k_p2g_tiled<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
     cudaFuncSetAttribute(k_p2g_tiled<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(sizeof(P2GSmem)));
@@ -794,6 +878,11 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
         s->grid_p2g = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled<true, true>, T3::THREADS, 0);
         s->grid_g2p = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
+        // a cooperative launch needs every CTA resident: one particle per thread
+        int occ_r = 1;
+        if (cfg->dim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_substeps_resident<3, true>, 128, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_substeps_resident<2, true>, 128, 0);
+        s->resident_max = std::min<int64_t>(s->resident_max, static_cast<int64_t>(s->sm_count) * std::max(occ_r, 1) * 128);
         (void)cudaGetLastError();
     }
     *out = s;
@@ -855,6 +944,10 @@ fluid_status fluid_destroy(fluid_sim* s) {
     }
     cudaFree(s->class_count);
     cudaFree(s->grid);
+    cudaFree(s->grid2);
+    cudaFree(s->fx[0]);
+    cudaFree(s->fx[1]);
+    cudaFree(s->d_stamps);
     cudaFree(s->d_mouse);
     cudaFree(s->d_stage);
     cudaFree(s->d_stage_ids);
@@ -1000,6 +1093,12 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
 
     CU_TRY(cudaStreamSynchronize(s->stream));
     cudaFree(s->grid);
+    cudaFree(s->grid2);
+    cudaFree(s->fx[0]);
+    cudaFree(s->fx[1]);
+    s->grid2 = nullptr;
+    s->fx[0] = s->fx[1] = nullptr;
+    s->grid_is_fixed = false;
     cudaFree(s->gmass);
     cudaFree(s->tiles);
     cudaFree(s->count);
@@ -1133,8 +1232,30 @@ fluid_status fluid_substeps(fluid_sim* s, int32_t n_substeps, const float* mouse
     CU_TRY(cudaSetDevice(s->device));
     const float* d_mouse = nullptr;
     ST_TRY(upload_mouse(s, mouse_xy, &d_mouse));
+    if (resident_eligible(s)) return substeps_resident(s, d_mouse, n_substeps);
     for (int32_t i = 0; i < n_substeps; ++i)
         ST_TRY(substep(s, d_mouse, /*timed=*/i == n_substeps - 1, nullptr));
+    return FLUID_OK;
+}
+
+fluid_status fluid_set_deterministic(fluid_sim* s, int32_t on) {
+    if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_deterministic: null handle");
+    if (s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_set_deterministic: not available in slab runs");
+    CU_TRY(cudaSetDevice(s->device));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    s->det = on != 0;
+    // the fixed-point sums live in the particle-per-thread kernels; the tiled path keeps float reductions
+    const char* force_generic = std::getenv("FLUID_B200_GENERIC");
+    s->tiled = !s->det && !(force_generic && force_generic[0] == '1');
+    s->sorted_valid = s->counts_pending = false;
+    s->grid_clean = false;
+    s->grid_is_fixed = false;
+    return FLUID_OK;
+}
+
+fluid_status fluid_set_resident_max(fluid_sim* s, int64_t max_particles) {
+    if (!s || max_particles < 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_resident_max: bad argument");
+    s->resident_max = max_particles;
     return FLUID_OK;
 }
 
@@ -1206,6 +1327,17 @@ fluid_status fluid_get_phase_times(fluid_sim* s, double seconds[FLUID_NUM_PHASES
     if (sort_seconds) *sort_seconds = 0.0;
     if (!s->timers_recorded) return FLUID_OK;
     CU_TRY(cudaSetDevice(s->device));
+    if (s->resident_timed) {   // %globaltimer stamps (ns) of the resident kernel's last substep
+        unsigned long long t[5];
+        CU_TRY(cudaMemcpyAsync(t, s->d_stamps, sizeof(t), cudaMemcpyDeviceToHost, s->stream));
+        CU_TRY(cudaStreamSynchronize(s->stream));
+        seconds[0] = static_cast<double>(t[1] - t[0]) * 1e-9;   // clear
+        seconds[1] = static_cast<double>(t[2] - t[1]) * 1e-9;   // p2g 1
+        seconds[2] = static_cast<double>(t[3] - t[2]) * 1e-9;   // p2g 2
+        seconds[3] = 0.0;                                       // update: folded into g2p's node read
+        seconds[4] = static_cast<double>(t[4] - t[3]) * 1e-9;   // g2p
+        return FLUID_OK;
+    }
     const cudaEvent_t* ev = s->last_ev;
     CU_TRY(cudaEventSynchronize(ev[N_EVENTS - 1]));
     float ms[N_EVENTS - 1];
@@ -1391,6 +1523,11 @@ fluid_status fluid_read_grid(fluid_sim* s, float* nodes, int64_t capacity_nodes,
     if (!nodes) return FLUID_OK;
     if (capacity_nodes < s->grid_nodes) return fail(FLUID_ERR_TOO_SMALL, "fluid_read_grid: capacity too small");
     const int D = s->dim;
+    if (s->grid_is_fixed && s->fx[0]) {   // deterministic mode: the node sums are fixed-point; give the float view
+        const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+        k_fixed_to_float<<<blocks_for(n_alloc, 256), 256, 0, s->stream>>>(s->fx[0], s->grid, n_alloc);
+        ++s->launches;
+    }
     float* d_out = nullptr;
     CU_TRY(cudaMalloc(&d_out, s->grid_nodes * (D + 1) * sizeof(float)));
     const int n = static_cast<int>(s->grid_nodes);

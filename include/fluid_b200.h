@@ -108,6 +108,15 @@ fluid_status fluid_clear_particles(fluid_sim* sim);
 fluid_status fluid_step(fluid_sim* sim, const float* mouse_xy);
 /* Same phases, an explicit number of substeps (bench / parity harness). */
 fluid_status fluid_substeps(fluid_sim* sim, int32_t n_substeps, const float* mouse_xy);
+/* The reference fixes the order of every node sum (grid_search, 3d:403-408); float reductions do not, so two
+ * runs agree only to the last bits.  on != 0: deposits are rounded to 2^-34 and summed as 64-bit integers
+ * (order-independent): results are bit-for-bit reproducible from run to run.  Uses the particle-per-thread
+ * kernels (slower than the tiled path); also selectable with FLUID_B200_DETERMINISTIC=1. */
+fluid_status fluid_set_deterministic(fluid_sim* sim, int32_t on);
+/* step()/substeps() of at most this many particles run as one cooperative launch with the particle state in
+ * registers (the reference's 4,096-particle default scenes are launch-bound); 0 disables it.  Default 16384,
+ * clamped to what the device can keep resident; FLUID_B200_RESIDENT_MAX overrides the default. */
+fluid_status fluid_set_resident_max(fluid_sim* sim, int64_t max_particles);
 
 /* ---- Simulation::iter_particle (3d:383-387) ------------------------------------------ */
 /* Number of particles `iter_particle` would yield (those stored in a_rect blocks). */

@@ -51,9 +51,11 @@ def randomised(scene, seed=5, vel=0.3, aff=0.05):
     return rec
 
 
-def check_one_substep(pkg, orc, scene, rec, mouse=None):
+def check_one_substep(pkg, orc, scene, rec, mouse=None, deterministic=False):
     d = scene.dim
     sim, ref = build_pair(pkg, orc, scene.cfg, rec, scene.rect_min, scene.rect_max)
+    if deterministic:
+        sim.set_deterministic(True)
     g = sim.debug_substep(mouse)
     for ph in range(5):
         ref.phase(ph, mouse)
@@ -123,6 +125,104 @@ def test_non_power_of_two_grid_res(pkg, orc, scenes):
     sc = scenes.default_3d(3000)
     sc.cfg["grid_res"] = 10
     check_one_substep(pkg, orc, sc, randomised(sc))
+
+
+def test_mouse_push_2d_and_zero_distance(pkg, orc, scenes):
+    """2D mouse push (2d:293-298), and the normalize_or_zero branch: a particle that sits exactly on the
+    mouse position after advection gets no push (3d:306-308)."""
+    sc = scenes.default_2d()
+    check_one_substep(pkg, orc, sc, randomised(sc), mouse=[30.0, 30.0])
+    for dim, sc in ((2, scenes.default_2d()), (3, scenes.default_3d())):
+        cfg = dict(sc.cfg)
+        cfg["gravity"] = [0.0, 0.0, 0.0]
+        cfg["pressure_clamp"] = 0.0                   # a lone particle is under-dense: clamped pressure 0, no force at all
+        rec = np.zeros((1, scenes.rec_floats(dim)), dtype=np.float32)
+        rec[0, :dim] = 20.5
+        rec[0, -1] = 1.0
+        sim, ref = build_pair(pkg, orc, cfg, rec, sc.rect_min, sc.rect_max)
+        sim.substeps(1, mouse_pos=[20.5, 20.5])      # at rest, no gravity: stays at 20.5 = the mouse position
+        ref.substeps(1, [20.5, 20.5])
+        g, _ = sim.read_particles()
+        r, _ = ref.read()
+        np.testing.assert_array_equal(g[:, :2 * dim], r[:, :2 * dim])
+        assert (g[0, dim:2 * dim] == 0).all()
+        sim.close()
+        ref.close()
+
+
+# ---- the resident small-scene kernel and the deterministic mode --------------------------------------
+
+@pytest.mark.parametrize("dim", [2, 3])
+def test_resident_step_matches_phase_kernels_and_oracle(pkg, orc, scenes, dim):
+    """step() of a small scene runs as ONE cooperative launch (k_substeps_resident: particle state in registers,
+    grid-wide barriers between the phases).  Same arithmetic as the per-phase kernels: after 1 substep it must
+    meet the oracle bound, after 31 it must agree with the per-phase path up to summation-order rounding."""
+    sc = scenes.default_2d() if dim == 2 else scenes.default_3d()
+    rec = randomised(sc)
+    d = sc.dim
+    res, ref = build_pair(pkg, orc, sc.cfg, rec, sc.rect_min, sc.rect_max)
+    n0 = res.launch_count()
+    res.substeps(1)
+    assert res.launch_count() - n0 == 1                 # one launch, not a dozen
+    ref.substeps(1)
+    g_rec, g_ids = res.read_particles(sort_by_id=True)
+    r_rec, r_ids = ref.read()
+    o = np.argsort(r_ids)
+    r_rec = r_rec[o]
+    assert np.array_equal(g_ids, r_ids[o])
+    vs = max(float(np.abs(r_rec[:, d:2 * d]).max()), 1e-3)
+    cs = max(float(np.abs(r_rec[:, 2 * d:2 * d + d * d]).max()), 1e-3)
+    assert scaled_err(g_rec[:, d:2 * d], r_rec[:, d:2 * d], vs) < TOL
+    assert scaled_err(g_rec[:, 2 * d:2 * d + d * d], r_rec[:, 2 * d:2 * d + d * d], cs) < TOL
+    assert scaled_err(g_rec[:, :d], r_rec[:, :d], 64.0) < TOL
+    # the node grid the launch leaves behind is the last substep's (read-backs expect it in `grid`)
+    gg, rg = res.read_grid(), ref.read_grid()
+    ms = max(float(rg[:, -1].max()), 1e-3)
+    assert scaled_err(gg[:, -1], rg[:, -1], ms) < TOL
+    phases = dict(res.debug_elapseds)
+    assert set(phases) == {"clear", "p2g 1", "p2g 2", "update", "g2p"} and all(v >= 0 for v in phases.values())
+    assert phases["p2g 1"] > 0 and phases["g2p"] > 0    # %globaltimer stamps of the last substep
+    res.substeps(30)
+    ref.close()
+    per_phase = pkg.Simulation.new(sc.cfg)
+    per_phase.set_resident_max(0)
+    per_phase.add_particles(rec)
+    per_phase.set_rect(sc.rect_min, sc.rect_max)
+    n0 = per_phase.launch_count()
+    per_phase.substeps(31)
+    assert per_phase.launch_count() - n0 > 31 * 3
+    a, _ = res.read_particles(sort_by_id=True)
+    b, _ = per_phase.read_particles(sort_by_id=True)
+    assert np.abs(a[:, :d] - b[:, :d]).max() < 2e-3      # 31 substeps: same stated bound as the golden test
+    res.close()
+    per_phase.close()
+
+
+@pytest.mark.parametrize("dim,n", [(2, 4096), (3, 4096), (3, 61440)])
+def test_deterministic_mode_is_bit_reproducible(pkg, orc, scenes, dim, n):
+    """Deterministic mode (64-bit fixed-point node sums, order-independent): two runs that hold the same
+    particles in a DIFFERENT storage order end bit-for-bit equal after a full step(); the mode still meets the
+    oracle bound.  n = 4096 takes the resident kernel, 61,440 the per-phase kernels."""
+    if n == 4096:
+        sc = scenes.default_2d() if dim == 2 else scenes.default_3d()
+    else:
+        sc = scenes.dam_break_3d(48, 32, 40)
+    rec = randomised(sc)
+    ids = np.arange(sc.n, dtype=np.int32)
+    outs = []
+    for seed in (None, 11):
+        order = np.arange(sc.n) if seed is None else np.random.default_rng(seed).permutation(sc.n)
+        sim = pkg.Simulation.new(sc.cfg)
+        sim.set_deterministic(True)
+        sim.add_particles(rec[order], ids[order])
+        sim.set_rect(sc.rect_min, sc.rect_max)
+        sim.step()
+        r, i = sim.read_particles(sort_by_id=True)
+        assert np.array_equal(i, ids)
+        outs.append(r)
+        sim.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))     # every bit of every field
+    check_one_substep(pkg, orc, sc, rec, deterministic=True)
 
 
 # ---- golden fixtures (oracle self-goldens, committed) ----------------------------------------------
