@@ -316,6 +316,8 @@ def run_ours(args):
     torch.cuda.set_stream(stream)
     sim = pkg.Simulation.new(sc.cfg, device=local_rank)
     sim.set_stream(stream.cuda_stream)
+    if args.sparse_blocks:
+        sim.set_sparse(args.sparse_blocks)      # block-sparse node storage (not the headline configuration)
     sim.set_rect(sc.rect_min, sc.rect_max)
     sim.add_particles_pinned(host.data_ptr(), sc.n)
     sim.synchronize()
@@ -327,7 +329,12 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     sampler.start()
     launches0 = sim.launch_count()
-    sim.profile(True)
+    # Scenes of at most 16,384 particles (the reference's default scenes) run step() as ONE cooperative launch
+    # with grid-wide barriers between the phases: there are no kernel boundaries to bracket with events, so the
+    # per-phase times of those lines are the kernel's own %globaltimer stamps of the step's last substep.
+    resident = sc.n <= 16384
+    if not resident:
+        sim.profile(True)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
     torch.cuda.synchronize()
     ev[0].record(stream)
@@ -337,8 +344,11 @@ def run_ours(args):
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[-1])
     ms_by_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    prof = sim.profile_read()
-    sim.profile(False)
+    if resident:
+        prof = dict(sim.phase_times(), substeps=1)
+    else:
+        prof = sim.profile_read()
+        sim.profile(False)
     launches = sim.launch_count() - launches0
     clocks = sampler.stop()
     # occupancy of the last timed substep (from the engine's tile list; outside the timed region)
@@ -367,6 +377,8 @@ def run_ours(args):
         alg = {"clear": 3.0, "p2g 1": 36.0 + 6.0, "p2g 2": 28.0 + 5.0, "update": 0.0, "g2p": 40.0 + 3.0}
         alg_step = 121.0
         kernel_of = {"clear": "memset", "p2g 1": "k_p2g1_generic", "p2g 2": "k_p2g2_generic", "g2p": "k_g2p_generic"}
+    if resident:
+        kernel_of = {k: "k_substeps_resident" for k in kernel_of}
     achieved = alg[dom] * sc.n / (per_phase_ms[dom] * 1e-3) / 1e9
     roofline = {
         "bound": "hbm", "kernel": f"{kernel_of[dom]} ({dom})", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -440,6 +452,7 @@ def run_ours(args):
                        parallelism=f"z-slabs x{args.gpus}" if args.gpus > 1 else "single GPU"),
         "value_by_step": value_by_step,
         "step_latency_ms": ms / args.steps,
+        "memory": sim.memory_stats(),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes,
@@ -630,6 +643,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scene", default="", help="scene function in scenes.py (default: dam break for --gpus)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sparse-blocks", type=int, default=0, help="N > 0: block-sparse node storage with a pool of N blocks")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: anything a library writes to file descriptor 1 meanwhile (NCCL's
     # version banner comes from C code) goes to stderr instead

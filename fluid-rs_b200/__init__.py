@@ -83,6 +83,8 @@ SIGNATURES = {
     "fluid_substeps": (C.c_int, [C.c_void_p, C.c_int32, _fp]),
     "fluid_set_deterministic": (C.c_int, [C.c_void_p, C.c_int32]),
     "fluid_set_resident_max": (C.c_int, [C.c_void_p, C.c_int64]),
+    "fluid_set_sparse": (C.c_int, [C.c_void_p, C.c_int64]),
+    "fluid_memory_stats": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_particle_count": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_particle_counts": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_slot_count": (C.c_int, [C.c_void_p, _i64p]),
@@ -261,6 +263,16 @@ class Simulation:
     def set_resident_max(self, max_particles: int):
         """Largest particle count whose step() runs as one cooperative launch (0 = never)."""
         _check(lib().fluid_set_resident_max(self._h, int(max_particles)))
+
+    def set_sparse(self, max_blocks: int):
+        """Block-sparse node storage with a pool of `max_blocks` 8x8x4 blocks (from the next set_rect on)."""
+        _check(lib().fluid_set_sparse(self._h, int(max_blocks)))
+
+    def memory_stats(self) -> dict:
+        o = (C.c_int64 * 6)()
+        _check(lib().fluid_memory_stats(self._h, o))
+        return dict(node_bytes=o[0], dense_node_bytes=o[1], pool_blocks=o[2], blocks_in_use=o[3], dense_nodes=o[4],
+                    pool_exhausted=bool(o[5]))
 
     def iter_particle(self):
         """`iter_particle` (3d:383-387): yields (id, record) for every a_rect particle."""

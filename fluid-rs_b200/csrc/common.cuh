@@ -17,8 +17,20 @@ template <int DIM> struct Tile;
 template <> struct Tile<3> { static constexpr int X = 8, Y = 8, Z = 4, CELLS = 256; };
 template <> struct Tile<2> { static constexpr int X = 16, Y = 16, Z = 1, CELLS = 256; };
 
+// Block-sparse node storage (the reference keeps a hash map of blocks and a touched list so that cost follows
+// the fluid, not the domain: 3d:52-55, 89-96, 136-146).  With `blk` set, the node arrays are a POOL of 8x8x4
+// node blocks; blk[tile] is the pool block of a tile's node block (-1: none yet).  Blocks are taken from the
+// free list when a tile's 3x3x3 neighbourhood first holds particles (k_tile_tables) and returned, zeroed, when
+// it no longer does (k_clear_tiles).  scal[0] = free blocks left, scal[1] = pool exhausted (error).
+struct SparsePool {
+    int* blk;
+    int* free_list;
+    int* scal;
+};
+
 struct Geo {
     int dim;
+    SparsePool sp;     // blk == nullptr: dense node arrays in the reference's layout
     int org[3];        // grid origin cell = p_rect.0 * grid_res            (3d:169)
     int size[3];       // grid size in cells = (p_rect.1 - p_rect.0) * res  (3d:94)
     int a_lo[3], a_hi[3], p_lo[3], p_hi[3];   // block-key rects (3d:80-86)
@@ -137,6 +149,17 @@ __device__ __forceinline__ int ref_cell_index(const Geo& g, const int* rel) {
     int idx = rel[0] + rel[1] * g.size[0];
     if (DIM == 3) idx += rel[2] * g.size[0] * g.size[1];
     return idx;
+}
+
+// Index of node (x, y, z) (relative to the grid origin, inside the grid) in the node arrays: the reference's
+// linear index x + y*sx + z*sx*sy behind the guard (3d:169-172), or, block-sparse, 256 * pool block + the node's
+// place in its 8x8x4 block; -1 if that block has no storage (it cannot receive a deposit then: every block an
+// active tile's stencils reach is allocated by the sort).
+__device__ __forceinline__ int node_addr(const Geo& g, int x, int y, int z) {
+    if (!g.sp.blk) return g.guard + x + (y + z * g.size[1]) * g.size[0];
+    const int t = ((z >> 2) * g.tdim[1] + (y >> 3)) * g.tdim[0] + (x >> 3);
+    const int b = __ldg(&g.sp.blk[t]);
+    return b < 0 ? -1 : (b << 8) + (x & 7) + ((y & 7) << 3) + ((z & 3) << 6);
 }
 
 // ---- quadratic stencil (3d:153-161, 390-396) ----------------------------------------------

@@ -127,6 +127,10 @@ struct fluid_sim {
     int* class_count = nullptr;   // 4 ints (device)
 
     float4* grid = nullptr;      // {momentum.xyz, mass} per node, reference layout + guards
+    int64_t sparse_blocks = 0;   // > 0: block-sparse node storage with this many pool blocks (takes effect at set_rect)
+    int64_t pool_blocks = 0;     // pool blocks of the current grid (0 = dense)
+    int64_t node_alloc = 0;      // elements of `grid` / `gmass`: dense nodes + guards, or 256 * pool blocks
+    int* h_pool = nullptr;       // pinned: {free blocks, exhausted flag}
     float4* grid2 = nullptr;     // second node buffer of the resident small-scene kernel (allocated on first use)
     long long* fx[2] = {nullptr, nullptr};   // deterministic mode: 4 fixed-point sums per node (phases_generic.cuh)
     bool det = false;            // FLUID_B200_DETERMINISTIC=1 / fluid_set_deterministic: order-independent node sums
@@ -466,7 +470,7 @@ fluid_status clear_mass_rim(fluid_sim* s, bool fused) {
                                                                         s->scal + SCAL_N_DIRTY2, false);
     k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                       static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-        s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY2, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, fused, 2);
+        s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY2, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, fused, 2, nullptr);
     s->launches += 2;
     CU_TRY(cudaGetLastError());
     return FLUID_OK;
@@ -474,7 +478,7 @@ fluid_status clear_mass_rim(fluid_sim* s, bool fused) {
 
 // deterministic mode: the fixed-point node sums (count = 1: generic kernels, 2: the resident kernel's two buffers)
 fluid_status ensure_fixed(fluid_sim* s, int count) {
-    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    const int64_t n_alloc = s->node_alloc;
     for (int b = 0; b < count; ++b)
         if (!s->fx[b]) CU_TRY(cudaMalloc(&s->fx[b], n_alloc * 4 * sizeof(long long)));
     return FLUID_OK;
@@ -482,7 +486,8 @@ fluid_status ensure_fixed(fluid_sim* s, int count) {
 
 // step() / substeps() of a small scene as ONE cooperative launch (k_substeps_resident, phases_generic.cuh).
 bool resident_eligible(const fluid_sim* s) {
-    return s->coop && s->rect_set && s->n > 0 && s->n <= s->resident_max && !s->geo.slab_on && !s->profiling;
+    return s->coop && s->rect_set && s->n > 0 && s->n <= s->resident_max && !s->geo.slab_on && !s->profiling &&
+           !s->pool_blocks;
 }
 
 template <int DIM, bool DET>
@@ -500,7 +505,7 @@ fluid_status resident_launch(fluid_sim* s, const float* d_mouse, int n_substeps,
 
 fluid_status substeps_resident(fluid_sim* s, const float* d_mouse, int n_substeps) {
     if (n_substeps <= 0) return FLUID_OK;
-    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    const int64_t n_alloc = s->node_alloc;
     if (!s->grid2) CU_TRY(cudaMalloc(&s->grid2, n_alloc * sizeof(float4)));
     if (!s->d_stamps) CU_TRY(cudaMalloc(&s->d_stamps, 8 * sizeof(unsigned long long)));
     if (s->det) ST_TRY(ensure_fixed(s, 2));
@@ -545,7 +550,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     }
     cudaEvent_t* ev = s->cur_ev;
     timed = s->cur_timed;
-    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    const int64_t n_alloc = s->node_alloc;
     const unsigned tb = blocks_for(s->geo.n_tiles, T3::WARPS);   // never more CTAs than tiles / 4
     const int* n_act = s->scal + SCAL_N_ACTIVE;
     if (phases & 1) {
@@ -564,6 +569,11 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                 CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
                 CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
                 CU_TRY(cudaMemsetAsync(s->dirty[s->dirty_cur ^ 1], 0, s->geo.n_tiles, s->stream));
+                if (s->pool_blocks) {
+                    // block-sparse: every block back on the free list, then the blocks this sort's stencils reach
+                    // (k_tile_tables marked them in dirty[dirty_cur] before the pool existed in this state)
+                    return fail(FLUID_ERR_STATE, "internal: sparse pool must be reset before the sort");
+                }
                 s->grid_clean = true;
             } else {
                 // only the node blocks the previous or the coming deposits can touch
@@ -572,7 +582,8 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                 k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                                   static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
                     s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, true,
-                    s->p2p ? 1 : 3);   // peer-halo runs clear the node masses at the end of the substep instead
+                    s->p2p ? 1 : 3,    // peer-halo runs clear the node masses at the end of the substep instead
+                    s->dirty[s->dirty_cur]);
                 s->launches += 2;
             }
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
@@ -772,6 +783,38 @@ __global__ void k_append_migrants(const __grid_constant__ Geo g, const float* __
 }
 }  // namespace
 
+// block-sparse pool: every tile without storage, blocks 1 .. n-1 on the free list (block 0 = overflow block)
+__global__ void k_pool_init(SparsePool sp, int n_tiles, int n_blocks) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tiles) sp.blk[i] = -1;
+    if (i < n_blocks - 1) sp.free_list[i] = n_blocks - 1 - i;     // popped from the top: 1, 2, 3, ...
+    if (i == 0) {
+        sp.scal[0] = n_blocks - 1;
+        sp.scal[1] = 0;
+    }
+}
+
+// fluid_read_grid from either layout (reference order out; nodes without storage are zero)
+__global__ void k_export_grid_any(const __grid_constant__ Geo g, const float4* __restrict__ grid, int n_nodes,
+                                  float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_nodes) return;
+    const int x = i % g.size[0], r = i / g.size[0], y = r % g.size[1], z = r / g.size[1];
+    const int gi = node_addr(g, x, y, z);
+    float4 nd = gi >= 0 ? grid[gi] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (nd.w > 0.0f) {
+        const float inv = 1.0f;
+        (void)inv;
+        nd.x = __fdiv_rn(nd.x, nd.w) + g.dtg[0];
+        nd.y = __fdiv_rn(nd.y, nd.w) + g.dtg[1];
+        nd.z = __fdiv_rn(nd.z, nd.w) + g.dtg[2];
+    }
+    out[i * 4 + 0] = nd.x;
+    out[i * 4 + 1] = nd.y;
+    out[i * 4 + 2] = nd.z;
+    out[i * 4 + 3] = nd.w;
+}
+
 // `draw`'s binning (3d:472-481): console_xy = (pos.xy / viewport * console) as ivec2
 template <int DIM>
 __global__ void k_render_frame(const __grid_constant__ Geo g, Particles q, int n, float vx, float vy, int cols, int rows,
@@ -853,6 +896,9 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     s->stream = s->own_stream;
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
+    if (const char* e = std::getenv("FLUID_B200_SPARSE_BLOCKS")) {
+        if (cfg->dim == 3) s->sparse_blocks = std::max<long long>(std::atoll(e), 0);
+    }
     if (const char* e = std::getenv("FLUID_B200_DETERMINISTIC")) {
         s->det = e[0] == '1';
         if (s->det) s->tiled = false;
@@ -943,6 +989,10 @@ fluid_status fluid_destroy(fluid_sim* s) {
         cudaFree(s->halo_node_recv[sd]);
     }
     cudaFree(s->class_count);
+    cudaFree(s->geo.sp.blk);
+    cudaFree(s->geo.sp.free_list);
+    cudaFree(s->geo.sp.scal);
+    if (s->h_pool) cudaFreeHost(s->h_pool);
     cudaFree(s->grid);
     cudaFree(s->grid2);
     cudaFree(s->fx[0]);
@@ -1128,9 +1178,29 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     const int64_t n_pt = static_cast<int64_t>(g.n_tiles) + N_PSEUDO;     // tiles + the pseudo tiles
     const int64_t m = n_pt * TILE_CELLS;                                  // buckets
     const int64_t nb = (n_pt + SCAN_CHUNK - 1) / SCAN_CHUNK;
-    CU_TRY(cudaMalloc(&s->grid, (nodes + 2 * g.guard) * sizeof(float4)));
-    if (D == 3) CU_TRY(cudaMalloc(&s->gmass, (nodes + 2 * g.guard) * sizeof(float)));
-    s->tma = D == 3 && make_grid_map(g, s->grid + g.guard, &s->tm_grid);
+    // node storage: dense in the reference's layout, or (fluid_set_sparse) a pool of 8x8x4 blocks behind blk[tile]
+    cudaFree(s->geo.sp.blk);
+    cudaFree(s->geo.sp.free_list);
+    cudaFree(s->geo.sp.scal);
+    s->geo.sp = SparsePool{nullptr, nullptr, nullptr};
+    g.sp = SparsePool{nullptr, nullptr, nullptr};
+    s->pool_blocks = (D == 3 && s->tiled && s->sparse_blocks > 0) ? std::min<int64_t>(s->sparse_blocks, tiles + 1) : 0;
+    if (s->pool_blocks > 0 && s->pool_blocks < 28) s->pool_blocks = 28;   // one tile's 3x3x3 neighbourhood + the overflow block
+    s->node_alloc = s->pool_blocks ? s->pool_blocks * TILE_CELLS : nodes + 2 * g.guard;
+    CU_TRY(cudaMalloc(&s->grid, s->node_alloc * sizeof(float4)));
+    if (D == 3) CU_TRY(cudaMalloc(&s->gmass, s->node_alloc * sizeof(float)));
+    if (s->pool_blocks) {
+        CU_TRY(cudaMalloc(&g.sp.blk, (tiles + 8) * sizeof(int)));
+        CU_TRY(cudaMalloc(&g.sp.free_list, s->pool_blocks * sizeof(int)));
+        CU_TRY(cudaMalloc(&g.sp.scal, 2 * sizeof(int)));
+        if (!s->h_pool) CU_TRY(cudaMallocHost(&s->h_pool, 2 * sizeof(int)));
+        s->geo.sp = g.sp;   // (owned by the handle from here on, also if a later allocation fails)
+        const int64_t m_init = std::max<int64_t>(tiles, s->pool_blocks);
+        k_pool_init<<<blocks_for(m_init, 256), 256, 0, s->stream>>>(g.sp, static_cast<int>(tiles), static_cast<int>(s->pool_blocks));
+        CU_TRY(cudaMemsetAsync(s->gmass, 0, s->node_alloc * sizeof(float), s->stream));
+        CU_TRY(cudaGetLastError());
+    }
+    s->tma = D == 3 && !s->pool_blocks && make_grid_map(g, s->grid + g.guard, &s->tm_grid);
     s->tma_mass = D == 3 && s->tma && make_mass_map(g, s->gmass, &s->tm_mass);
     if (!s->tma_mass) std::memset(&s->tm_mass, 0, sizeof(s->tm_mass));
     CU_TRY(cudaMalloc(&s->tiles, (static_cast<int64_t>(g.n_tiles) + N_PSEUDO) * sizeof(int4)));
@@ -1155,7 +1225,8 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaMemsetAsync(s->count, 0, (m + 8) * sizeof(int), s->stream));
     CU_TRY(cudaMemsetAsync(s->tile_total, 0, (n_pt + 8) * sizeof(int), s->stream));
     CU_TRY(cudaMemsetAsync(s->tile_base, 0, (n_pt + 8) * sizeof(int), s->stream));
-    CU_TRY(cudaMemsetAsync(s->grid, 0, (nodes + 2 * g.guard) * sizeof(float4), s->stream));
+    CU_TRY(cudaMemsetAsync(s->grid, 0, s->node_alloc * sizeof(float4), s->stream));
+    s->grid_clean = s->pool_blocks > 0;   // block-sparse: arrays, flags and pool are consistent from the start
     s->grid_nodes = nodes;
     s->n_scan_blocks = nb;
     s->geo = g;
@@ -1238,9 +1309,37 @@ fluid_status fluid_substeps(fluid_sim* s, int32_t n_substeps, const float* mouse
     return FLUID_OK;
 }
 
+fluid_status fluid_set_sparse(fluid_sim* s, int64_t max_blocks) {
+    if (!s || max_blocks < 0) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_sparse: bad argument");
+    if (s->dim != 3 && max_blocks > 0) return fail(FLUID_ERR_STATE, "fluid_set_sparse: the block-sparse grid belongs to the tiled 3D path");
+    s->sparse_blocks = max_blocks;   // takes effect at the next fluid_set_rect
+    return FLUID_OK;
+}
+
+fluid_status fluid_memory_stats(fluid_sim* s, int64_t out[6]) {
+    if (!s || !out) return fail(FLUID_ERR_INVALID_ARG, "fluid_memory_stats: null argument");
+    for (int k = 0; k < 6; ++k) out[k] = 0;
+    if (!s->rect_set) return FLUID_OK;
+    CU_TRY(cudaSetDevice(s->device));
+    const int64_t per_node = sizeof(float4) + (s->dim == 3 ? sizeof(float) : 0);
+    out[0] = s->node_alloc * per_node;                                   // node storage allocated
+    out[1] = (s->grid_nodes + 2 * s->geo.guard) * per_node;              // what the dense layout takes
+    out[2] = s->pool_blocks;
+    out[4] = s->grid_nodes;
+    if (s->pool_blocks) {
+        CU_TRY(cudaMemcpyAsync(s->h_pool, s->geo.sp.scal, 2 * sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+        CU_TRY(cudaStreamSynchronize(s->stream));
+        out[3] = s->pool_blocks - 1 - s->h_pool[0];                      // blocks in use
+        out[5] = s->h_pool[1];                                           // pool ran out at some point
+        if (s->h_pool[1]) return fail(FLUID_ERR_OUT_OF_MEMORY, "block-sparse node pool exhausted: results are invalid (raise fluid_set_sparse's block count)");
+    }
+    return FLUID_OK;
+}
+
 fluid_status fluid_set_deterministic(fluid_sim* s, int32_t on) {
     if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_deterministic: null handle");
     if (s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_set_deterministic: not available in slab runs");
+    if (s->pool_blocks && on) return fail(FLUID_ERR_STATE, "fluid_set_deterministic: not available with block-sparse node storage");
     CU_TRY(cudaSetDevice(s->device));
     CU_TRY(cudaStreamSynchronize(s->stream));
     s->det = on != 0;
@@ -1524,14 +1623,15 @@ fluid_status fluid_read_grid(fluid_sim* s, float* nodes, int64_t capacity_nodes,
     if (capacity_nodes < s->grid_nodes) return fail(FLUID_ERR_TOO_SMALL, "fluid_read_grid: capacity too small");
     const int D = s->dim;
     if (s->grid_is_fixed && s->fx[0]) {   // deterministic mode: the node sums are fixed-point; give the float view
-        const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+        const int64_t n_alloc = s->node_alloc;
         k_fixed_to_float<<<blocks_for(n_alloc, 256), 256, 0, s->stream>>>(s->fx[0], s->grid, n_alloc);
         ++s->launches;
     }
     float* d_out = nullptr;
     CU_TRY(cudaMalloc(&d_out, s->grid_nodes * (D + 1) * sizeof(float)));
     const int n = static_cast<int>(s->grid_nodes);
-    if (D == 3) k_export_grid<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid, n, d_out);
+    if (s->pool_blocks) k_export_grid_any<<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid, n, d_out);
+    else if (D == 3) k_export_grid<3><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid, n, d_out);
     else k_export_grid<2><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->grid, n, d_out);
     ++s->launches;
     cudaError_t ce = cudaMemcpyAsync(nodes, d_out, s->grid_nodes * (D + 1) * sizeof(float), cudaMemcpyDeviceToHost, s->stream);
@@ -1559,6 +1659,7 @@ fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t ha
     if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_set: null handle");
     if (s->dim != 3 || !s->tiled) return fail(FLUID_ERR_STATE, "fluid_slab_set: needs the tiled 3D path");
     if (!s->rect_set) return fail(FLUID_ERR_STATE, "fluid_slab_set: call set_rect first");
+    if (s->pool_blocks) return fail(FLUID_ERR_STATE, "fluid_slab_set: block-sparse node storage is single-GPU (the neighbours index each other's dense planes)");
     CU_TRY(cudaSetDevice(s->device));
     const int lo = z_lo - s->geo.org[2], hi = z_hi - s->geo.org[2];
     if (lo < 0 || hi > s->geo.size[2] || lo >= hi || (lo % T3::Z) != 0 || (has_upper && (hi % T3::Z) != 0))
@@ -1625,7 +1726,7 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
     if (s->n == 0) {
         // a rank may hold no particles yet still has to take part in the exchanges: its planes must be zero
         if (phase == 0 && !s->grid_clean) {
-            const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+            const int64_t n_alloc = s->node_alloc;
             CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
             CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
             CU_TRY(cudaMemsetAsync(s->dirty[0], 0, s->geo.n_tiles, s->stream));
@@ -1638,7 +1739,7 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
             k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                               static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
                 s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, 0, false,
-                s->p2p ? 1 : 3);
+                s->p2p ? 1 : 3, nullptr);
             ++s->epoch;   // no g2p ran: no stamp of an earlier substep may match the next clear
             s->dirty_cur ^= 1;
         } else if (phase == 2 && s->p2p) {
@@ -1789,7 +1890,7 @@ fluid_status fluid_slab_ipc_export(fluid_sim* s, void* handles) {
     s->barrier_epoch = 0;
     // The neighbours may deposit into this rank's planes before its own first substep gets to wipe the
     // arrays: wipe now (the caller puts a barrier between the imports and the first substep).
-    const int64_t n_alloc = s->grid_nodes + 2 * s->geo.guard;
+    const int64_t n_alloc = s->node_alloc;
     CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
     CU_TRY(cudaMemsetAsync(s->gmass, 0, n_alloc * sizeof(float), s->stream));
     CU_TRY(cudaMemsetAsync(s->dirty[0], 0, s->geo.n_tiles, s->stream));

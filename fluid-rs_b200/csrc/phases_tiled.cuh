@@ -155,7 +155,7 @@ __device__ __forceinline__ int footprint_to_global(const Geo& g, const TileCtx& 
     int x = tc.c0[0] - 1 + lx, y = tc.c0[1] - 1 + ly, z = tc.c0[2] - 1 + lz;
     if (k >= T3::NODES || x < 0 || y < 0 || z < 0 || x >= g.size[0] || y >= g.size[1] || z >= g.size[2])
         return -1;
-    return g.guard + x + (y + z * g.size[1]) * g.size[0];
+    return node_addr(g, x, y, z);
 }
 
 // Row-wise walk over the footprint: step `it` (0..19), lanes 0..29 -> row 3*it + lane/10, x = lane%10.
@@ -177,7 +177,7 @@ __device__ __forceinline__ int foot_step(const Geo& g, const TileCtx& tc, const 
     if (f.rsub < 3) {
         const int x = tc.c0[0] - 1 + f.x, y = tc.c0[1] - 1 + ly, z = tc.c0[2] - 1 + lz;
         if (!tc.edge || (x >= 0 && y >= 0 && z >= 0 && x < g.size[0] && y < g.size[1] && z < g.size[2]))
-            gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
+            gi = node_addr(g, x, y, z);
     }
     return f.x + T3::NX * ly + T3::PLANE * lz;
 }
@@ -257,7 +257,8 @@ k_dirty_list(const __grid_constant__ Geo g, const unsigned char* __restrict__ di
 __global__ void __launch_bounds__(128)
 k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const int* __restrict__ n_list,
               float4* __restrict__ grid, float* __restrict__ gmass, const int* __restrict__ tile_base,
-              const int* __restrict__ gz, int epoch_prev, bool fused, int what) {
+              const int* __restrict__ gz, int epoch_prev, bool fused, int what,
+              const unsigned char* __restrict__ dirty_now) {
     const int lane = threadIdx.x & 31;
     const int n = *n_list;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -266,7 +267,10 @@ k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const
         // what: 1 = node records, 2 = node masses, 3 = both (peer-halo slab runs clear them at different times)
         const bool do_grid = (what & 1) && (!fused || tile_base[t + 1] == tile_base[t]);   // else k_mass_tiled zeroes it
         const bool do_mass = (what & 2) && (!fused || gz[t] != epoch_prev);                // else k_g2p_tiled did
-        if (!do_grid && !do_mass) continue;
+        // block-sparse: a block no stencil reaches any more (dirty only from the sort before) goes back to the
+        // free list, zeroed (below, or already by k_g2p_tiled)
+        const bool release = g.sp.blk && dirty_now && !dirty_now[t];
+        if (!do_grid && !do_mass && !release) continue;
         const int tx = t % g.tdim[0], r = t / g.tdim[0], ty = r % g.tdim[1], tz = r / g.tdim[1];
         // 256 nodes: lane -> x = lane & 7, y = (lane >> 3) + 4*(j & 1), z = j >> 1
 #pragma unroll
@@ -275,9 +279,21 @@ k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const
             const int y = ty * T3::Y + (lane >> 3) + 4 * (j & 1);
             const int z = tz * T3::Z + (j >> 1);
             if (x < g.size[0] && y < g.size[1] && z < g.size[2]) {
-                const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
-                if (do_grid) grid[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (do_mass) gmass[gi] = 0.0f;
+                const int gi = node_addr(g, x, y, z);
+                if (gi >= 0) {
+                    if (do_grid) grid[gi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (do_mass) gmass[gi] = 0.0f;
+                }
+            }
+        }
+        if (release) {
+            __syncwarp();
+            if (lane == 0) {
+                const int b = g.sp.blk[t];
+                if (b > 0) {   // (block 0 is the overflow block of an exhausted pool: never recycled)
+                    g.sp.blk[t] = -1;
+                    g.sp.free_list[atomicAdd(&g.sp.scal[0], 1)] = b;
+                }
             }
         }
     }
@@ -301,7 +317,7 @@ __device__ __forceinline__ void zero_own_block(const Geo& g, const TileCtx& tc, 
         const int x = tc.c0[0] + (lane & 7);
         const int y = tc.c0[1] + (lane >> 3) + 4 * (j & 1);
         const int z = tc.c0[2] + (j >> 1);
-        if (x < g.size[0] && y < g.size[1] && z < g.size[2]) arr[g.guard + x + (y + z * g.size[1]) * g.size[0]] = T{};
+        if (x < g.size[0] && y < g.size[1] && z < g.size[2]) arr[node_addr(g, x, y, z)] = T{};
     }
 }
 
@@ -386,7 +402,7 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
                     for (int k = 0; k < 6; ++k) {
                         const int z = tc.c0[2] - 1 + k;
                         if (m6[k] != 0.0f && (!tc.edge || (z >= 0 && z < g.size[2]))) {
-                            const int gi = g.guard + x + (y + z * g.size[1]) * g.size[0];
+                            const int gi = node_addr(g, x, y, z);
                             atomicAdd(&gmass[gi], m6[k]);
                             // the two node planes a slab face shares: the neighbour's copy as well (NVLink)
                             if (PEER && k < 2 && peer_lo) red_add_sys(&peer_lo[gi], m6[k]);
@@ -504,7 +520,8 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 for (int k = 0; k < 6; ++k) {
                     const int z = tc.c0[2] - 1 + k;
                     const bool ok = col_ok && (!tc.edge || (z >= 0 && z < g.size[2]));
-                    mv[it][k] = ok ? __ldg(&gmass[g.guard + x + (y + z * g.size[1]) * g.size[0]]) : 0.0f;
+                    const int gi = ok ? node_addr(g, x, y, z) : -1;
+                    mv[it][k] = gi >= 0 ? __ldg(&gmass[gi]) : 0.0f;
                 }
             }
 #pragma unroll

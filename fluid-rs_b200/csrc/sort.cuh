@@ -372,6 +372,17 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
             if (nx >= 0 && ny >= 0 && nz >= 0 && nx < g.tdim[0] && ny < g.tdim[1] && nz < g.tdim[2]) {
                 const int blk = (nz * g.tdim[1] + ny) * g.tdim[0] + nx;
                 dirty[blk] = 1;
+                // block-sparse node storage: the first tile to reach a block takes one from the free list
+                if (g.sp.blk && atomicCAS(&g.sp.blk[blk], -1, -2) == -1) {
+                    const int top = atomicSub(&g.sp.scal[0], 1);
+                    int b = 0;                      // pool exhausted: the overflow block, and an error for the host
+                    if (top > 0) b = g.sp.free_list[top - 1];
+                    else {
+                        atomicAdd(&g.sp.scal[0], 1);
+                        g.sp.scal[1] = 1;
+                    }
+                    g.sp.blk[blk] = b;              // consumed by later kernels only (kernel boundary orders it)
+                }
                 // a tile on a slab face also deposits into the neighbour's copy of the two shared node
                 // planes (block layers tz-1, tz below / tz, tz+1 above): the neighbour has to clear them
                 if (ph.dirty[0][0] && tz * Tile<3>::Z == g.slab_lo && nz <= tz) {

@@ -113,6 +113,17 @@ fluid_status fluid_substeps(fluid_sim* sim, int32_t n_substeps, const float* mou
  * (order-independent): results are bit-for-bit reproducible from run to run.  Uses the particle-per-thread
  * kernels (slower than the tiled path); also selectable with FLUID_B200_DETERMINISTIC=1. */
 fluid_status fluid_set_deterministic(fluid_sim* sim, int32_t on);
+/* Block-sparse node storage (the reference keeps a hash map of blocks plus a touched list so that cost follows
+ * the fluid, not the domain: 3d:52-55, 89-96, 136-146).  max_blocks > 0: from the next fluid_set_rect on, the
+ * node arrays are a pool of max_blocks blocks of 8x8x4 nodes (5 KB each) behind a per-tile indirection table;
+ * blocks are taken when a tile's 3x3x3 neighbourhood first holds particles and given back when it no longer
+ * does.  3D tiled path, single GPU; the TMA tile transfers need the dense layout, so this mode uses the
+ * per-node loads and reductions instead.  0 = dense (default).  Also FLUID_B200_SPARSE_BLOCKS=N. */
+fluid_status fluid_set_sparse(fluid_sim* sim, int64_t max_blocks);
+/* out[0] node storage allocated (bytes), [1] what the dense layout would take, [2] pool blocks (0 = dense),
+ * [3] pool blocks in use, [4] dense node count, [5] 1 if the pool ever ran out (then this call also returns
+ * FLUID_ERR_OUT_OF_MEMORY: deposits were lost). */
+fluid_status fluid_memory_stats(fluid_sim* sim, int64_t out[6]);
 /* step()/substeps() of at most this many particles run as one cooperative launch with the particle state in
  * registers (the reference's 4,096-particle default scenes are launch-bound); 0 disables it.  Default 16384,
  * clamped to what the device can keep resident; FLUID_B200_RESIDENT_MAX overrides the default. */

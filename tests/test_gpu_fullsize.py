@@ -109,3 +109,26 @@ def test_config3_dam_break_1m_vs_oracle(pkg, orc, scenes):
 
 def test_config4_dam_break_16m_vs_oracle(pkg, orc, scenes):
     check_full_size(pkg, orc, scenes.dam_break_16m())
+
+
+def test_config4_block_sparse_storage(pkg, scenes):
+    """Config 4 (2^24 particles) on the block-sparse grid: node storage follows the fluid (the dense arrays take
+    1.6 GB), node masses still sum to the particle mass, every particle is kept."""
+    sc = scenes.dam_break_16m()
+    sim = pkg.Simulation.new(sc.cfg)
+    sim.set_sparse(120000)
+    for s in range(0, sc.n, CHUNK):
+        sim.add_particles(sc.records(s, min(CHUNK, sc.n - s)))
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    sim.substeps(3)
+    st = sim.memory_stats()
+    assert not st["pool_exhausted"]
+    assert st["node_bytes"] == 120000 * 256 * 20 and st["node_bytes"] < 0.4 * st["dense_node_bytes"]
+    assert st["blocks_in_use"] * 256 * 20 < 0.6e9          # what the fluid actually holds: active tiles + their rim
+    g = sim.read_grid()
+    mass = 0.0
+    for s in range(0, g.shape[0], CHUNK):
+        mass += float(g[s:s + CHUNK, 3].astype(np.float64).sum())
+    assert abs(mass - sc.n) / sc.n < 1e-6
+    assert sim.particle_counts() == dict(active=sc.n, frozen=0, outside=0, dropped=0)
+    sim.close()

@@ -16,8 +16,10 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-5
 
 
-def build_pair(pkg, orc, cfg, records, rect_min, rect_max, ids=None):
+def build_pair(pkg, orc, cfg, records, rect_min, rect_max, ids=None, sparse_blocks=0):
     sim = pkg.Simulation.new(cfg, device=0)
+    if sparse_blocks:
+        sim.set_sparse(sparse_blocks)
     sim.add_particles(records, ids)
     sim.set_rect(rect_min, rect_max)
     ref = orc.OracleSim(cfg)
@@ -51,9 +53,9 @@ def randomised(scene, seed=5, vel=0.3, aff=0.05):
     return rec
 
 
-def check_one_substep(pkg, orc, scene, rec, mouse=None, deterministic=False):
+def check_one_substep(pkg, orc, scene, rec, mouse=None, deterministic=False, sparse_blocks=0):
     d = scene.dim
-    sim, ref = build_pair(pkg, orc, scene.cfg, rec, scene.rect_min, scene.rect_max)
+    sim, ref = build_pair(pkg, orc, scene.cfg, rec, scene.rect_min, scene.rect_max, sparse_blocks=sparse_blocks)
     if deterministic:
         sim.set_deterministic(True)
     g = sim.debug_substep(mouse)
@@ -223,6 +225,76 @@ def test_deterministic_mode_is_bit_reproducible(pkg, orc, scenes, dim, n):
         sim.close()
     assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))     # every bit of every field
     check_one_substep(pkg, orc, sc, rec, deterministic=True)
+
+
+# ---- block-sparse node storage (3d:52-55, 89-96, 136-146: cost follows the fluid, not the domain) ------
+
+@pytest.mark.parametrize("case", ["default", "dam", "res10", "ragged"])
+def test_block_sparse_grid_one_substep(pkg, orc, scenes, case):
+    """The parity bar of the dense grid, with the node arrays as a pool of 8x8x4 blocks behind the per-tile table."""
+    if case == "default":
+        sc = scenes.default_3d()
+        rec = randomised(sc)
+    elif case == "dam":
+        sc = scenes.dam_break_3d(48, 32, 40)
+        rec = sc.records()
+    elif case == "res10":
+        sc = scenes.default_3d(3000)
+        sc.cfg["grid_res"] = 10
+        rec = randomised(sc)
+    else:
+        sc = scenes.default_3d()
+        rng = np.random.default_rng(2)
+        rec = np.zeros((300, 16), dtype=np.float32)
+        rec[:, :3] = (30.0 + rng.uniform(0, 1, (300, 3))).astype(np.float32)
+        rec[:, -1] = 0.01
+    check_one_substep(pkg, orc, sc, rec, sparse_blocks=2048)
+
+
+def test_block_sparse_domain_8x_the_fluid(pkg, orc, scenes):
+    """A 24x16x16-cell column in a box eight times its extent on every axis: the dense node arrays take 150 MB,
+    the pool a few MB; blocks are recycled as the fluid moves; the run agrees with the dense one and with the
+    oracle."""
+    cfg = scenes.default_config(3)
+    box = [200.0, 136.0, 136.0]
+    cfg["clip_max"] = box
+    cfg["gravity"] = [0.0, 4.8 / 16, 0.0]
+    sc = scenes.Scene("sparse_8x", cfg, [0, 0, 0], box, 24 * 16 * 16, [3.0, box[1] - 19.0, 3.0], [27.0, box[1] - 3.0, 19.0])
+    rec = randomised(sc, vel=0.2)
+    check_one_substep(pkg, orc, sc, rec, sparse_blocks=1024)
+    outs, stats = [], None
+    for blocks in (1024, 0):
+        sim = pkg.Simulation.new(sc.cfg)
+        sim.set_sparse(blocks)
+        sim.add_particles(rec)
+        sim.set_rect(sc.rect_min, sc.rect_max)
+        used = []
+        for _ in range(8):
+            sim.substeps(31)
+            if blocks:
+                used.append(sim.memory_stats()["blocks_in_use"])
+        if blocks:
+            stats = sim.memory_stats()
+            tiles = sim.debug_tiles()
+            active = int((tiles[:, 2] > 0).sum())
+            # in use = the active tiles and their 3x3x3 rim, nothing left behind where the fluid has been
+            assert active <= stats["blocks_in_use"] <= 27 * active
+            assert max(used) < 1024 and not stats["pool_exhausted"]
+        r, i = sim.read_particles(sort_by_id=True)
+        outs.append(r)
+        sim.close()
+    assert stats["pool_blocks"] == 1024 and stats["node_bytes"] == 1024 * 256 * 20
+    assert stats["dense_node_bytes"] > 25 * stats["node_bytes"]
+    assert np.abs(outs[0][:, :3] - outs[1][:, :3]).max() < 5e-3      # 248 substeps: summation-order rounding only
+    # a pool that is too small is reported, not silently wrong
+    sim = pkg.Simulation.new(sc.cfg)
+    sim.set_sparse(30)
+    sim.add_particles(rec)
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    sim.substeps(2)
+    with pytest.raises(pkg.FluidError):
+        sim.memory_stats()
+    sim.close()
 
 
 # ---- golden fixtures (oracle self-goldens, committed) ----------------------------------------------
