@@ -113,7 +113,7 @@ struct fluid_sim {
     int barrier_epoch = 0;
     bool p2p = false;            // deposits into the shared node planes go to the neighbour directly
     int* gz = nullptr;           // per tile: substep number in which k_g2p_tiled zeroed its node-mass block
-    int epoch = 0;               // tiled substeps run so far (compared with gz)
+    int* d_epoch = nullptr;      // device: tiled substeps completed so far (compared with gz; advanced by k_tail)
     bool grid_clean = false;     // every node outside the dirty blocks is zero
     bool sorted_valid = false;   // arrays are in tile order for the current positions
     bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
@@ -142,7 +142,9 @@ struct fluid_sim {
     float* gmass = nullptr;      // node masses alone (p2g 1 output, read by p2g 2), same layout
     int64_t grid_nodes = 0;      // reference node count (without guards)
     bool tiled = true;           // 3D: tiled sm_100a kernels; FLUID_B200_GENERIC=1 forces the generic ones
-    float* d_mouse = nullptr;
+    float* d_mouse = nullptr;    // {x, y, present}
+    float h_mouse[4] = {0, 0, 0, 0};
+    bool mouse_on = false;
 
     float* d_stage = nullptr;    // staging for host<->device record copies
     int64_t stage_floats = 0;
@@ -170,12 +172,21 @@ struct fluid_sim {
     double prof_sum[N_EVENTS - 1] = {0, 0, 0, 0, 0};
     int64_t prof_substeps = 0;
 
+    // CUDA graphs of one steady-state substep, one per (particle buffer, dirty-flag buffer) parity
+    bool graphs_on = true;                  // FLUID_B200_GRAPH=0 launches every kernel individually
+    cudaGraphExec_t graph[4] = {nullptr, nullptr, nullptr, nullptr};
+    int graph_nodes[4] = {0, 0, 0, 0};      // kernels per graph (launch accounting)
+    int64_t graph_n = -1;                   // the particle count the graphs were captured for
+    int64_t graph_min = 0;                  // (scenes of at most resident_max particles take the resident kernel instead)
+
     int64_t launches = 0;
     int32_t next_id = 0;
     int64_t dropped_total = 0;
 };
 
 namespace {
+
+void graphs_drop(fluid_sim* s);   // (defined with the substep)
 
 void free_particles(Particles& p) {
     cudaFree(p.P);
@@ -226,6 +237,7 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
         (void)cudaGetLastError();
         return st;
     }
+    graphs_drop(s);   // the captured launches hold the old pointers
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->gcell);
     cudaFree(s->rank);
@@ -470,7 +482,7 @@ fluid_status clear_mass_rim(fluid_sim* s, bool fused) {
                                                                         s->scal + SCAL_N_DIRTY2, false);
     k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                       static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-        s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY2, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, fused, 2, nullptr);
+        s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY2, s->grid, s->gmass, s->tile_base, s->gz, s->d_epoch, fused, 2, nullptr);
     s->launches += 2;
     CU_TRY(cudaGetLastError());
     return FLUID_OK;
@@ -581,13 +593,12 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                     s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY, true);
                 k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                                   static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-                    s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, s->epoch, true,
+                    s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, s->d_epoch, true,
                     s->p2p ? 1 : 3,    // peer-halo runs clear the node masses at the end of the substep instead
                     s->dirty[s->dirty_cur]);
                 s->launches += 2;
             }
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-            ++s->epoch;
             if (s->p2p)
                 k_mass_tiled<true><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
                                                                                             s->gmass, s->grid, s->peer);
@@ -654,14 +665,14 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             sb.cap = s->mig_cap;
             if (s->tma)
                 k_g2p_tiled<true, true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch, s->tm_grid);
+                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid);
             else
                 k_g2p_tiled<true, false><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->epoch, s->tm_grid);
+                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid);
             // ignored (and, outside slab runs, dropped) particles sit behind the tiles: carried over
             // and counted here; a slab run ends dropped / migrated particles at this point
             const int* n_end = s->geo.slab_on ? s->tile_base + s->geo.n_tiles + 1 : nullptr;
-            k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, q, qn, s->src, n_dep, n_end, n, sort_tables(s));
+            k_tail<DIM><<<s->sm_count, 256, 0, s->stream>>>(s->geo, q, qn, s->src, n_dep, n_end, n, sort_tables(s), s->d_epoch);
             s->launches += 2;
             if (s->p2p) ST_TRY(clear_mass_rim(s, true));
             s->cur ^= 1;
@@ -688,11 +699,77 @@ fluid_status substep(fluid_sim* s, const float* d_mouse, bool timed, const Debug
     return s->dim == 3 ? substep_impl<3>(s, d_mouse, timed, dbg) : substep_impl<2>(s, d_mouse, timed, dbg);
 }
 
+// ---- CUDA graphs: a steady-state tiled substep is the same dozen launches every time ---------------------
+// (same grids, same pointers up to the two buffer parities; the substep number and the mouse position live
+// in device memory).  The graph removes the launch gaps between its small sort / clear kernels.
+void graphs_drop(fluid_sim* s) {
+    for (int k = 0; k < 4; ++k) {
+        if (s->graph[k]) cudaGraphExecDestroy(s->graph[k]);
+        s->graph[k] = nullptr;
+        s->graph_nodes[k] = 0;
+    }
+    s->graph_n = -1;
+}
+
+bool graph_eligible(const fluid_sim* s) {
+    return s->graphs_on && s->dim == 3 && s->tiled && s->rect_set && s->n >= s->graph_min && s->sorted_valid &&
+           s->counts_pending && s->grid_clean && !s->profiling && !s->geo.slab_on;
+}
+
+// one untimed steady-state substep through the graph of the current parity (captured on first use)
+fluid_status substep_graphed(fluid_sim* s, const float* d_mouse) {
+    if (s->graph_n != s->n) graphs_drop(s);   // launch geometry depends on the particle count
+    s->graph_n = s->n;
+    const int key = s->cur * 2 + s->dirty_cur;
+    if (!s->graph[key]) {
+        const int64_t before = s->launches;
+        cudaGraph_t g = nullptr;
+        CU_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        const fluid_status st = substep_impl<3>(s, d_mouse, false, nullptr);   // records the launches, flips the host state
+        const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+        if (st != FLUID_OK || ce != cudaSuccess || !g) {
+            if (g) cudaGraphDestroy(g);
+            (void)cudaGetLastError();
+            s->graphs_on = false;                     // fall back to plain launches for good
+            s->sorted_valid = s->counts_pending = false;   // the captured substep never ran: re-sort from the positions
+            return st != FLUID_OK ? st : fail(FLUID_ERR_CUDA, "CUDA graph capture of the substep failed");
+        }
+        cudaGraphExec_t ge = nullptr;
+        const cudaError_t ci = cudaGraphInstantiate(&ge, g, 0);
+        cudaGraphDestroy(g);
+        if (ci != cudaSuccess) {
+            (void)cudaGetLastError();
+            s->graphs_on = false;
+            s->sorted_valid = s->counts_pending = false;
+            return fail(FLUID_ERR_CUDA, "cudaGraphInstantiate failed");
+        }
+        s->graph[key] = ge;
+        s->graph_nodes[key] = static_cast<int>(s->launches - before);
+        CU_TRY(cudaGraphLaunch(ge, s->stream));       // the capture did not execute anything
+        return FLUID_OK;
+    }
+    CU_TRY(cudaGraphLaunch(s->graph[key], s->stream));
+    // what substep_impl does to the host state
+    s->dirty_cur ^= 1;
+    s->cur ^= 1;
+    s->sorted_valid = true;
+    s->counts_pending = true;
+    s->launches += s->graph_nodes[key];
+    return FLUID_OK;
+}
+
+// The device copy is {x, y, present}: kernels always get the same pointer (a captured CUDA graph keeps working
+// whether or not the caller passes a mouse position) and test the flag.
 fluid_status upload_mouse(fluid_sim* s, const float* mouse_xy, const float** d_mouse) {
-    *d_mouse = nullptr;
-    if (!mouse_xy) return FLUID_OK;
-    CU_TRY(cudaMemcpyAsync(s->d_mouse, mouse_xy, 2 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
     *d_mouse = s->d_mouse;
+    const bool on = mouse_xy != nullptr;
+    if (!on && !s->mouse_on) return FLUID_OK;   // already {., ., 0} on the device
+    s->h_mouse[0] = on ? mouse_xy[0] : 0.0f;
+    s->h_mouse[1] = on ? mouse_xy[1] : 0.0f;
+    s->h_mouse[2] = on ? 1.0f : 0.0f;
+    // (pageable source: the runtime stages the 12 bytes before the call returns, so h_mouse may be reused at once)
+    CU_TRY(cudaMemcpyAsync(s->d_mouse, s->h_mouse, 3 * sizeof(float), cudaMemcpyHostToDevice, s->stream));
+    s->mouse_on = on;
     return FLUID_OK;
 }
 
@@ -782,6 +859,8 @@ __global__ void k_append_migrants(const __grid_constant__ Geo g, const float* __
     if (count) count_global(t, d, bucket, valid);   // `count` is uniform over the grid
 }
 }  // namespace
+
+__global__ void k_bump(int* counter) { *counter += 1; }
 
 // block-sparse pool: every tile without storage, blocks 1 .. n-1 on the free list (block 0 = overflow block)
 __global__ void k_pool_init(SparsePool sp, int n_tiles, int n_blocks) {
@@ -883,7 +962,10 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     s->dim = cfg->dim;
     s->device = device;
     cudaError_t ce = cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking);
-    if (ce == cudaSuccess) ce = cudaMalloc(&s->d_mouse, 2 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->d_mouse, 4 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMemset(s->d_mouse, 0, 4 * sizeof(float));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->d_epoch, sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemset(s->d_epoch, 0, sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->class_count, 4 * sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->d_counter, sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->scal, 8 * sizeof(int));
@@ -896,6 +978,7 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     s->stream = s->own_stream;
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
+    if (const char* e = std::getenv("FLUID_B200_GRAPH")) s->graphs_on = e[0] != '0';
     if (const char* e = std::getenv("FLUID_B200_SPARSE_BLOCKS")) {
         if (cfg->dim == 3) s->sparse_blocks = std::max<long long>(std::atoll(e), 0);
     }
@@ -957,6 +1040,7 @@ fluid_status fluid_destroy(fluid_sim* s) {
     if (!s) return FLUID_OK;
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
+    graphs_drop(s);
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->gcell);
     cudaFree(s->rank);
@@ -999,6 +1083,7 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaFree(s->fx[1]);
     cudaFree(s->d_stamps);
     cudaFree(s->d_mouse);
+    cudaFree(s->d_epoch);
     cudaFree(s->d_stage);
     cudaFree(s->d_stage_ids);
     cudaFree(s->d_counter);
@@ -1015,6 +1100,7 @@ fluid_status fluid_set_stream(fluid_sim* s, void* cuda_stream) {
     if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_set_stream: null handle");
     CU_TRY(cudaSetDevice(s->device));
     CU_TRY(cudaStreamSynchronize(s->stream));
+    graphs_drop(s);
     s->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : s->own_stream;
     return FLUID_OK;
 }
@@ -1142,6 +1228,7 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     }
 
     CU_TRY(cudaStreamSynchronize(s->stream));
+    graphs_drop(s);
     cudaFree(s->grid);
     cudaFree(s->grid2);
     cudaFree(s->fx[0]);
@@ -1210,7 +1297,7 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     CU_TRY(cudaMalloc(&s->dirty_list, (n_pt + 8) * sizeof(int)));
     CU_TRY(cudaMalloc(&s->gz, (n_pt + 8) * sizeof(int)));
     CU_TRY(cudaMemsetAsync(s->gz, 0, (n_pt + 8) * sizeof(int), s->stream));
-    s->epoch = 0;
+    CU_TRY(cudaMemsetAsync(s->d_epoch, 0, sizeof(int), s->stream));
     CU_TRY(cudaMalloc(&s->tile_info, (n_pt + 8) * sizeof(int2)));
     CU_TRY(cudaMalloc(&s->tab, (n_pt + 8) * TAB_BYTES));
     for (int b = 0; b < 2; ++b) {
@@ -1304,8 +1391,11 @@ fluid_status fluid_substeps(fluid_sim* s, int32_t n_substeps, const float* mouse
     const float* d_mouse = nullptr;
     ST_TRY(upload_mouse(s, mouse_xy, &d_mouse));
     if (resident_eligible(s)) return substeps_resident(s, d_mouse, n_substeps);
-    for (int32_t i = 0; i < n_substeps; ++i)
-        ST_TRY(substep(s, d_mouse, /*timed=*/i == n_substeps - 1, nullptr));
+    for (int32_t i = 0; i < n_substeps; ++i) {
+        const bool timed = i == n_substeps - 1;       // the reference's phase timers show the last substep (3d:112)
+        if (!timed && graph_eligible(s)) ST_TRY(substep_graphed(s, d_mouse));
+        else ST_TRY(substep(s, d_mouse, timed, nullptr));
+    }
     return FLUID_OK;
 }
 
@@ -1667,6 +1757,7 @@ fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t ha
     if ((has_lower && lo < 2) || (has_upper && hi > s->geo.size[2] - 2))
         return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_set: an interface needs a node plane on either side");
     CU_TRY(cudaStreamSynchronize(s->stream));
+    graphs_drop(s);
     s->geo.slab_on = 1;
     s->geo.slab_lo = lo;
     s->geo.slab_hi = hi;
@@ -1738,9 +1829,9 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
                 s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY, true);
             k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),
                                               static_cast<unsigned>(s->sm_count * 16)), 128, 0, s->stream>>>(
-                s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, 0, false,
+                s->geo, s->dirty_list, s->scal + SCAL_N_DIRTY, s->grid, s->gmass, s->tile_base, s->gz, s->d_epoch, false,
                 s->p2p ? 1 : 3, nullptr);
-            ++s->epoch;   // no g2p ran: no stamp of an earlier substep may match the next clear
+            k_bump<<<1, 1, 0, s->stream>>>(s->d_epoch);   // no g2p ran: no stamp of an earlier substep may match the next clear
             s->dirty_cur ^= 1;
         } else if (phase == 2 && s->p2p) {
             ST_TRY(clear_mass_rim(s, false));   // the neighbours' "p2g 1" deposits of this substep

@@ -293,6 +293,7 @@ k_g2p_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict_
               const int* __restrict__ n_deposit, NodeGrid ng, const float* __restrict__ mouse) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= *n_deposit) return;
+    if (mouse && mouse[2] == 0.0f) mouse = nullptr;   // {x, y, present}
     const int i = src[d];
     float4 p = q.P[i];
     float pos[3] = {p.x, p.y, p.z};
@@ -329,6 +330,7 @@ k_substeps_resident(const __grid_constant__ Geo g, Particles q, int n, NodeGrid 
                     const float* __restrict__ mouse, int n_substeps, unsigned long long* __restrict__ stamps) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
+    if (mouse && mouse[2] == 0.0f) mouse = nullptr;   // {x, y, present}
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     const bool mine = i < n;
     float pos[3] = {0.f, 0.f, 0.f}, vel[3] = {0.f, 0.f, 0.f}, C[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};

@@ -257,8 +257,9 @@ k_dirty_list(const __grid_constant__ Geo g, const unsigned char* __restrict__ di
 __global__ void __launch_bounds__(128)
 k_clear_tiles(const __grid_constant__ Geo g, const int* __restrict__ list, const int* __restrict__ n_list,
               float4* __restrict__ grid, float* __restrict__ gmass, const int* __restrict__ tile_base,
-              const int* __restrict__ gz, int epoch_prev, bool fused, int what,
+              const int* __restrict__ gz, const int* __restrict__ epoch_dev, bool fused, int what,
               const unsigned char* __restrict__ dirty_now) {
+    const int epoch_prev = *epoch_dev;   // tiled substeps completed so far = the stamp k_g2p_tiled left in the last one
     const int lane = threadIdx.x & 31;
     const int n = *n_list;
     const int n_warps = (gridDim.x * blockDim.x) >> 5;
@@ -686,7 +687,10 @@ __global__ void __launch_bounds__(T3::THREADS, 4)
 k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb,
-            float* __restrict__ gmass, int* __restrict__ gz, int epoch, const __grid_constant__ CUtensorMap tm_grid) {
+            float* __restrict__ gmass, int* __restrict__ gz, const int* __restrict__ epoch_dev,
+            const __grid_constant__ CUtensorMap tm_grid) {
+    const int epoch = *epoch_dev + 1;   // this substep's number (k_tail advances the counter after this kernel)
+    if (mouse && mouse[2] == 0.0f) mouse = nullptr;   // {x, y, present}: the pointer itself never changes (CUDA graphs)
     __shared__ __align__(128) float4 sm[T3::WARPS * T3::SLOTS];
     __shared__ int scnt_all[T3::WARPS * TILE_CELLS];
     __shared__ __align__(8) unsigned long long bars[T3::WARPS];

@@ -150,7 +150,9 @@ k_immigrants(SortTables t, const int4* __restrict__ tiles, int n_tiles_listed_ma
 template <int DIM>
 __global__ void __launch_bounds__(256)
 k_tail(const __grid_constant__ Geo g, Particles from, Particles to, const int* __restrict__ src,
-       const int* __restrict__ n_deposit, const int* __restrict__ n_end, int n, SortTables t) {
+       const int* __restrict__ n_deposit, const int* __restrict__ n_end, int n, SortTables t, int* __restrict__ epoch_dev) {
+    // runs right after k_g2p_tiled: the substep counter both compare their block stamps with moves on
+    if (epoch_dev && blockIdx.x == 0 && threadIdx.x == 0) *epoch_dev += 1;
     const int first = *n_deposit;
     // slab runs carry only the ignored particles over: dropped and migrated ones end here
     if (n_end) n = min(n, *n_end);

@@ -618,6 +618,31 @@ def test_tiled_and_generic_paths_agree(pkg, scenes, monkeypatch):
     assert np.abs(out[0] - out[1]).max() < 1e-4
 
 
+def test_graphed_substeps_match_plain_launches(pkg, scenes, monkeypatch):
+    """Steady-state substeps replay a captured CUDA graph (one per buffer parity); the same kernels, the same
+    launch count, the same results up to the float reductions' order."""
+    sc = scenes.dam_break_3d(48, 32, 40)
+    rec = randomised(sc)
+    out, launches = [], []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("FLUID_B200_GRAPH", flag)       # read by fluid_create
+        sim = pkg.Simulation.new(sc.cfg)
+        sim.add_particles(rec)
+        sim.set_rect(sc.rect_min, sc.rect_max)
+        n0 = sim.launch_count()
+        sim.substeps(12)
+        sim.substeps(7, mouse_pos=[20.0, 40.0])            # the graph reads the mouse position from device memory
+        sim.substeps(5)
+        launches.append(sim.launch_count() - n0)
+        r, _ = sim.read_particles(sort_by_id=True)
+        out.append(r)
+        assert sim.particle_counts()["active"] == sc.n
+        sim.close()
+    assert launches[0] == launches[1]
+    assert np.abs(out[0][:, :6] - out[1][:, :6]).max() < 2e-4
+    assert np.abs(out[0][:, 3:6]).max() > 0.5               # (the mouse push really happened in both)
+
+
 def test_fast_key_matches_exact_key(pkg, orc, scenes):
     """The hot kernels classify particles from the integer cell (shift / integer floor division)
     instead of f32 div_euclid.  Put particles one ulp either side of every block face, including the
