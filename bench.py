@@ -323,34 +323,46 @@ def run_ours(args):
     sim.synchronize()
 
     # ---- device-resident timing -------------------------------------------------------------
-    for _ in range(args.warmup):
-        sim.step()
-    torch.cuda.synchronize()
+    # The timed region runs the way a caller runs it: no per-phase event brackets, so steady-state substeps replay
+    # the engine's CUDA graph (scenes of at most 16,384 particles: one cooperative launch per step()).  The
+    # per-kernel durations the roofline needs come from a REPLAY of the same region — same initial state, same
+    # warm-up, same K steps — with CUDA-event brackets around every phase (plain launches: a bracket would split
+    # the graph; scenes on the resident kernel report its own %globaltimer stamps of the last substep instead).
+    resident = sc.n <= 16384
+
+    def region(profiled: bool):
+        sim.clear_particles()
+        sim.add_particles_pinned(host.data_ptr(), sc.n)
+        for _ in range(args.warmup):
+            sim.step()
+        torch.cuda.synchronize()
+        if profiled:
+            sim.profile(True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        l0 = sim.launch_count()
+        torch.cuda.synchronize()
+        ev[0].record(stream)
+        for k in range(args.steps):
+            sim.step()
+            ev[k + 1].record(stream)   # an event record costs nothing on the stream; no sync inside the timed region
+        torch.cuda.synchronize()
+        total = ev[0].elapsed_time(ev[-1])
+        by_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+        pr = None
+        if profiled:
+            pr = sim.profile_read()
+            sim.profile(False)
+        return total, by_step, sim.launch_count() - l0, pr
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = sim.launch_count()
-    # Scenes of at most 16,384 particles (the reference's default scenes) run step() as ONE cooperative launch
-    # with grid-wide barriers between the phases: there are no kernel boundaries to bracket with events, so the
-    # per-phase times of those lines are the kernel's own %globaltimer stamps of the step's last substep.
-    resident = sc.n <= 16384
-    if not resident:
-        sim.profile(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    torch.cuda.synchronize()
-    ev[0].record(stream)
-    for k in range(args.steps):
-        sim.step()
-        ev[k + 1].record(stream)       # an event record costs nothing on the stream; no sync inside the timed region
-    torch.cuda.synchronize()
-    ms = ev[0].elapsed_time(ev[-1])
-    ms_by_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
+    ms, ms_by_step, launches, _ = region(False)
+    clocks = sampler.stop()
     if resident:
         prof = dict(sim.phase_times(), substeps=1)
+        ms_profiled = None
     else:
-        prof = sim.profile_read()
-        sim.profile(False)
-    launches = sim.launch_count() - launches0
-    clocks = sampler.stop()
+        ms_profiled, _, _, prof = region(True)
     # occupancy of the last timed substep (from the engine's tile list; outside the timed region)
     tiles_now = sim.debug_tiles()
     tiles_now = tiles_now[tiles_now[:, 2] > 0]
@@ -452,6 +464,10 @@ def run_ours(args):
                        parallelism=f"z-slabs x{args.gpus}" if args.gpus > 1 else "single GPU"),
         "value_by_step": value_by_step,
         "step_latency_ms": ms / args.steps,
+        "timing": {"timed_region": "plain step() calls (CUDA-graph replay of steady-state substeps / resident kernel)",
+                   "per_phase": "the kernel's %globaltimer stamps of the last substep" if resident else
+                                "replay of the timed region (same state, warm-up and steps) with CUDA-event brackets per phase",
+                   "ms_per_step_with_phase_brackets": None if ms_profiled is None else ms_profiled / args.steps},
         "memory": sim.memory_stats(),
         "roofline": roofline,
         "cpu_baseline": cpu,
@@ -519,35 +535,47 @@ def run_slabs(args, pkg, world, rank, local_rank):
                                    C.cast(C.c_void_p(ids.data_ptr()), C.POINTER(C.c_int32)), n_local)
         assert st == 0, L.fluid_last_error()
 
-    load()
     stream = sim.stream
-    for _ in range(args.warmup):
-        sim.step()
-    torch.cuda.synchronize()
-    dist.barrier()
+
+    def region(profiled: bool):
+        """warm-up + the K timed steps from the initial state; `profiled` adds CUDA-event brackets per phase."""
+        load()
+        sim.driver.migrated_out = sim.driver.migrated_in = 0
+        for _ in range(args.warmup):
+            sim.step()
+        torch.cuda.synchronize()
+        dist.barrier()
+        l0 = sim.sim.launch_count()
+        if profiled:
+            sim.sim.profile(True)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        torch.cuda.synchronize()
+        dist.barrier()
+        ev[0].record(stream)
+        for k in range(args.steps):
+            sim.step()
+            ev[k + 1].record(stream)
+        torch.cuda.synchronize()
+        dist.barrier()
+        t = torch.tensor([ev[0].elapsed_time(ev[-1])] + [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # the slowest rank, per step and in total
+        pr = None
+        if profiled:
+            pr = sim.sim.profile_read()
+            sim.sim.profile(False)
+        return t, sim.sim.launch_count() - l0, pr
+
     sampler = ClockSampler(local_rank)
     sampler.start()
-    launches0 = sim.sim.launch_count()
-    sim.sim.profile(True)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    torch.cuda.synchronize()
-    dist.barrier()
-    ev[0].record(stream)
-    for k in range(args.steps):
-        sim.step()
-        ev[k + 1].record(stream)
-    torch.cuda.synchronize()
-    dist.barrier()
-    ms_t = torch.tensor([ev[0].elapsed_time(ev[-1])] + [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)], device="cuda")
-    dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms_t, my_launches, _ = region(False)                # the timed region: no per-phase brackets
+    clocks = sampler.stop()
     ms = float(ms_t[0].item())
     value_by_step = [sc.n * iters / (float(m) * 1e-3) for m in ms_t[1:].tolist()]
-    prof = sim.sim.profile_read()
-    sim.sim.profile(False)
-    launches_t = torch.tensor([sim.sim.launch_count() - launches0], device="cuda", dtype=torch.int64)
+    launches_t = torch.tensor([my_launches], device="cuda", dtype=torch.int64)
     dist.all_reduce(launches_t)
-    clocks = sampler.stop()
-    cnt = torch.tensor([sim.sim.particle_counts()["active"], sim.driver.migrated_out], device="cuda", dtype=torch.int64)
+    migrated_timed = sim.driver.migrated_out
+    ms_prof_t, _, prof = region(True)                   # its replay with CUDA-event brackets per phase (roofline)
+    cnt = torch.tensor([sim.sim.particle_counts()["active"], migrated_timed], device="cuda", dtype=torch.int64)
     dist.all_reduce(cnt)
     assert int(cnt[0].item()) == sc.n, (int(cnt[0].item()), sc.n)
     value = sc.n * iters * args.steps / (ms * 1e-3)
@@ -618,6 +646,9 @@ def run_slabs(args, pkg, world, rank, local_rank):
                        parallelism=f"z-slabs x{world}", particles_per_gpu=n_rank,
                        slabs=[list(x) for x in slabs]),
         "value_by_step": value_by_step,
+        "timing": {"timed_region": "plain step() calls on every rank, max over ranks",
+                   "per_phase": "replay of the timed region (same state, warm-up and steps) with CUDA-event brackets per phase",
+                   "ms_per_step_with_phase_brackets": float(ms_prof_t[0].item()) / args.steps},
         "roofline": roofline, "cpu_baseline": None, "parity_check": parity,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": rec_bytes, "d2h_bytes_per_step": rec_bytes,
                 "steps": e2e_steps, "what": "per rank: clear + add_particles(pinned host records) + step() + "

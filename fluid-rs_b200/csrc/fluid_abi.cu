@@ -66,7 +66,7 @@ int host_block_key(float p, float res) {
 }
 
 constexpr int N_EVENTS = 6;   // sort | clear | p2g1 | p2g2 | g2p | end
-constexpr int PROFILE_POOL = 256;
+constexpr int PROFILE_POOL = 1024;   // substeps between two drains (a drain waits for the stream: keep it out of short timed regions)
 
 }  // namespace
 
