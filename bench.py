@@ -388,7 +388,7 @@ def run_ours(args):
     if sc.dim == 2:      # SURVEY.md 8(d), 2D, A/N = 0.25: 121 B per particle-substep; the 2D path = particle-per-thread kernels
         alg = {"clear": 3.0, "p2g 1": 36.0 + 6.0, "p2g 2": 28.0 + 5.0, "update": 0.0, "g2p": 40.0 + 3.0}
         alg_step = 121.0
-        kernel_of = {"clear": "memset", "p2g 1": "k_p2g1_generic", "p2g 2": "k_p2g2_generic", "g2p": "k_g2p_generic"}
+        kernel_of = {"clear": "k_clear_tiles", "p2g 1": "k_mass_tiled2", "p2g 2": "k_p2g_tiled2", "g2p": "k_g2p_tiled2"}
     if resident:
         kernel_of = {k: "k_substeps_resident" for k in kernel_of}
     achieved = alg[dom] * sc.n / (per_phase_ms[dom] * 1e-3) / 1e9

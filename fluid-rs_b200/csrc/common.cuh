@@ -11,11 +11,13 @@
 
 namespace fluid {
 
-// Tile of cells that one warp owns in the tiled kernels and that defines the sort order.
-// 3D: 8 x 8 x 4 cells, 2D: 16 x 16 cells — 256 cells either way.
+// Tile of cells that one warp owns in the tiled kernels and that defines the sort order: 8 x 8 (x, y) columns,
+// 4 cells deep in 3D, 1 in 2D.  A tile always owns 256 buckets (8 bank classes x 8 columns x 4 depth slots); in 2D
+// only depth slot 0 of a column is used, so the 2D scenes (4 particles per cell, 2d:24) put about as many
+// particles into a tile as the 3D ones (1 per cell) and the sort tables and window order are the same code.
 template <int DIM> struct Tile;
 template <> struct Tile<3> { static constexpr int X = 8, Y = 8, Z = 4, CELLS = 256; };
-template <> struct Tile<2> { static constexpr int X = 16, Y = 16, Z = 1, CELLS = 256; };
+template <> struct Tile<2> { static constexpr int X = 8, Y = 8, Z = 1, CELLS = 256; };
 
 // Block-sparse node storage (the reference keeps a hash map of blocks and a touched list so that cost follows
 // the fluid, not the domain: 3d:52-55, 89-96, 136-146).  With `blk` set, the node arrays are a POOL of 8x8x4
@@ -137,7 +139,7 @@ __device__ __forceinline__ int tiled_cell_index(const Geo& g, const int* rel) {
     int tx = rel[0] / T::X, lx = rel[0] - tx * T::X;
     int ty = rel[1] / T::Y, ly = rel[1] - ty * T::Y;
     if (DIM == 2) {
-        return (ty * g.tdim[0] + tx) * T::CELLS + ly * T::X + lx;
+        return (ty * g.tdim[0] + tx) * T::CELLS + local_cell_3d(lx, ly, 0);
     }
     int tz = rel[2] / T::Z, lz = rel[2] - tz * T::Z;
     return ((tz * g.tdim[1] + ty) * g.tdim[0] + tx) * T::CELLS + local_cell_3d(lx, ly, lz);

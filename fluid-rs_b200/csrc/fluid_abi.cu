@@ -20,6 +20,7 @@
 #include "common.cuh"
 #include "phases_generic.cuh"
 #include "phases_tiled.cuh"
+#include "phases_tiled2d.cuh"
 #include "sort.cuh"
 
 using namespace fluid;
@@ -120,6 +121,7 @@ struct fluid_sim {
     int tile_order = ORDER_CLASS_RR;
     int sm_count = 148;
     unsigned grid_mass = 0, grid_p2g = 0, grid_g2p = 0;   // persistent grids: SMs x resident CTAs
+    unsigned grid2_mass = 0, grid2_p2g = 0, grid2_g2p = 0;   // ... of the 2D tile kernels
 
     int* count = nullptr;    // per bucket, (n_tiles + 2) * 256; all zero outside a sort
     int* block_sums = nullptr;
@@ -407,7 +409,7 @@ fluid_status sort_finish(fluid_sim* s) {
     // persistent warps over the candidate list: one resident wave of small CTAs
     const unsigned pb = std::min<unsigned>(blocks_for(static_cast<int64_t>(m) * 32, PERM_WARPS * 32),
                                            static_cast<unsigned>(s->sm_count * 16));
-    if (DIM == 3) {
+    if (DIM == 3 || s->tiled) {   // (2D tiles are 8 x 8 columns of depth 1: the same order and tables)
         s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
         k_tile_tables<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
                                                                             s->tiles, s->scal, s->dirty[s->dirty_cur], s->cand, s->peer);
@@ -548,8 +550,9 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     if (!s->rect_set || s->n == 0) return FLUID_OK;   // no blocks to walk (3d:149 over an empty rect)
     const int n = static_cast<int>(s->n);
     const int* n_dep = s->tile_base + s->geo.n_tiles;
-    const bool tiled = DIM == 3 && s->tiled;
-    if (!tiled && phases != 7) return fail(FLUID_ERR_STATE, "split substeps need the tiled 3D path");
+    const bool tiled = s->tiled;   // 3D: phases_tiled.cuh, 2D: phases_tiled2d.cuh
+    if ((!tiled || DIM != 3) && phases != 7) return fail(FLUID_ERR_STATE, "split substeps need the tiled 3D path");
+    const unsigned tb2 = blocks_for(s->geo.n_tiles, T2::WARPS);
     if (phases & 1) {
         s->cur_ev = s->ev;
         s->cur_timed = timed;
@@ -599,7 +602,10 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                 s->launches += 2;
             }
             if (timed) CU_TRY(cudaEventRecord(ev[2], s->stream));
-            if (s->p2p)
+            if (DIM == 2)
+                k_mass_tiled2<<<std::min(tb2, s->grid2_mass), T2::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act, s->gmass,
+                                                                                          s->grid);
+            else if (s->p2p)
                 k_mass_tiled<true><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
                                                                                             s->gmass, s->grid, s->peer);
             else
@@ -626,7 +632,11 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     }
     if (phases & 2) {
         Particles q = s->buf[s->cur];
-        if (tiled) {
+        if (tiled && DIM == 2) {
+            k_p2g_tiled2<<<std::min(tb2, s->grid2_p2g), T2::THREADS, 0, s->stream>>>(s->geo, q, s->src, s->tiles, n_act, s->gmass, s->grid,
+                                                                                    dbg ? dbg->density : nullptr,
+                                                                                    dbg ? dbg->pressure : nullptr);
+        } else if (tiled) {
             const unsigned gp = std::min(tb, s->grid_p2g);
             float* dd = dbg ? dbg->density : nullptr;
             float* dp = dbg ? dbg->pressure : nullptr;
@@ -663,7 +673,10 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                 sb.rec[sd] = dst ? dst + MIG_WORDS : nullptr;
             }
             sb.cap = s->mig_cap;
-            if (s->tma)
+            if (DIM == 2)
+                k_g2p_tiled2<<<std::min(tb2, s->grid2_g2p), T2::THREADS, 0, s->stream>>>(s->geo, q, qn, s->src, s->tiles, n_act, s->grid,
+                                                                                        d_mouse, sort_tables(s), s->gmass, s->gz, s->d_epoch);
+            else if (s->tma)
                 k_g2p_tiled<true, true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
                     s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid);
             else
@@ -712,7 +725,7 @@ void graphs_drop(fluid_sim* s) {
 }
 
 bool graph_eligible(const fluid_sim* s) {
-    return s->graphs_on && s->dim == 3 && s->tiled && s->rect_set && s->n >= s->graph_min && s->sorted_valid &&
+    return s->graphs_on && s->tiled && s->rect_set && s->n >= s->graph_min && s->sorted_valid &&
            s->counts_pending && s->grid_clean && !s->profiling && !s->geo.slab_on;
 }
 
@@ -725,7 +738,7 @@ fluid_status substep_graphed(fluid_sim* s, const float* d_mouse) {
         const int64_t before = s->launches;
         cudaGraph_t g = nullptr;
         CU_TRY(cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-        const fluid_status st = substep_impl<3>(s, d_mouse, false, nullptr);   // records the launches, flips the host state
+        const fluid_status st = substep(s, d_mouse, false, nullptr);   // records the launches, flips the host state
         const cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
         if (st != FLUID_OK || ce != cudaSuccess || !g) {
             if (g) cudaGraphDestroy(g);
@@ -1007,6 +1020,12 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
         s->grid_p2g = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled<true, true>, T3::THREADS, 0);
         s->grid_g2p = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_mass_tiled2, T2::THREADS, 0);
+        s->grid2_mass = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_p2g_tiled2, T2::THREADS, 0);
+        s->grid2_p2g = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_g2p_tiled2, T2::THREADS, 0);
+        s->grid2_g2p = static_cast<unsigned>(s->sm_count * std::max(occ, 1));
         // a cooperative launch needs every CTA resident: one particle per thread
         int occ_r = 1;
         if (cfg->dim == 3) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_r, k_substeps_resident<3, true>, 128, 0);
@@ -1275,7 +1294,7 @@ fluid_status fluid_set_rect(fluid_sim* s, const float* mn, const float* mx) {
     if (s->pool_blocks > 0 && s->pool_blocks < 28) s->pool_blocks = 28;   // one tile's 3x3x3 neighbourhood + the overflow block
     s->node_alloc = s->pool_blocks ? s->pool_blocks * TILE_CELLS : nodes + 2 * g.guard;
     CU_TRY(cudaMalloc(&s->grid, s->node_alloc * sizeof(float4)));
-    if (D == 3) CU_TRY(cudaMalloc(&s->gmass, s->node_alloc * sizeof(float)));
+    CU_TRY(cudaMalloc(&s->gmass, s->node_alloc * sizeof(float)));
     if (s->pool_blocks) {
         CU_TRY(cudaMalloc(&g.sp.blk, (tiles + 8) * sizeof(int)));
         CU_TRY(cudaMalloc(&g.sp.free_list, s->pool_blocks * sizeof(int)));

@@ -66,8 +66,12 @@ constexpr int FOOT_STEPS = FOOT_ROWS / 3;            // a warp takes 3 rows (30 
 
 // ---- TMA (cp.async.bulk.tensor) helpers: the node grid as a 4-D tensor {4 floats, x, y, z}; one box =
 // one 10x10 plane of a tile's footprint, dense in shared memory (1600 B at a 128-byte aligned address).
-// The copies do not go through the LSU pipe, which is what binds the tile kernels.  Used for the tiles whose
-// footprint lies inside the grid (a box that started at coordinate -1 raised "illegal instruction" on B200).
+// The copies do not go through the LSU pipe, which is what binds the tile kernels.  What a box may do at the rim of
+// the tensor was measured on B200 (tools/tma_probe.cu, profiles/r02_tma_probe.log): LOADS take any start
+// coordinate, negative ones included, and zero-fill what lies outside; a box may overhang the far end for loads
+// and reductions alike; but a REDUCTION whose box starts at a negative coordinate, and any box whose negative
+// start is not 16-byte aligned (the 4-byte node-mass tensor at x = -1), raise "illegal instruction".  So g2p
+// loads every tile's footprint by TMA, and p2g flushes by TMA unless the tile touches the low rim of the grid.
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(static_cast<unsigned>(__cvta_generic_to_shared(bar))), "r"(count) : "memory");
 }
@@ -113,6 +117,7 @@ struct TileCtx {
     int windows;   // W
     int per, extra;
     bool edge;     // the footprint sticks out of the p_rect grid
+    bool low_rim;  // ... at the low end of an axis: its boxes start at coordinate -1 (no TMA reduction there)
 };
 
 // Active tiles, listed by k_tile_tables: {tile id, first slot, count, windows}.  The tile kernels
@@ -132,8 +137,9 @@ __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileC
     tc.c0[0] = tx * T3::X;
     tc.c0[1] = ty * T3::Y;
     tc.c0[2] = tz * T3::Z;
-    tc.edge = tc.c0[0] == 0 || tc.c0[1] == 0 || tc.c0[2] == 0 || tc.c0[0] + T3::X + 1 > g.size[0] ||
-              tc.c0[1] + T3::Y + 1 > g.size[1] || tc.c0[2] + T3::Z + 1 > g.size[2];
+    tc.low_rim = tc.c0[0] == 0 || tc.c0[1] == 0 || tc.c0[2] == 0;
+    tc.edge = tc.low_rim || tc.c0[0] + T3::X + 1 > g.size[0] || tc.c0[1] + T3::Y + 1 > g.size[1] ||
+              tc.c0[2] + T3::Z + 1 > g.size[2];
 }
 
 // window w of the tile: first slot (relative to tc.base) and length
@@ -481,7 +487,8 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         const FootLane fl = foot_lane(lane);
         // the node masses of the footprint as ONE tensor copy (box 12 x 10 x 6 floats) into the accumulator
         // tile, which is idle until the first window; unpacked into z quads below
-        const bool tma_load = TMA && tma_mass && !tc.edge && tc.c0[0] + MBOX_X <= g.size[0];
+        // (y / z may start at -1: loads zero-fill; x starts at c0[0] >= 0; the tensor ends one node early in x)
+        const bool tma_load = TMA && tma_mass && tc.c0[0] + MBOX_X <= g.size[0];
         if (tma_load) {
             fence_proxy_async();
             __syncwarp();
@@ -625,7 +632,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
                 }
             }
         }
-        if (TMA && !tc.edge) {   // (tiles on the rim of the grid keep the per-node path: their boxes stick out of the tensor)
+        if (TMA && !tc.low_rim) {   // (a reduction box must not start at a negative coordinate; overhang at the far end is fine)
             // six 10x10 planes as tensor reductions (cp.reduce.async.bulk.tensor .add, SASS UTMAREDG): no LDS, no
             // per-node REDG, no index arithmetic.  Every lane orders its own accumulator stores (generic proxy)
             // before the async proxy, then the warp meets, then one lane issues.
@@ -737,7 +744,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         // node records of the footprint: cp.async (LDGSTS) straight into shared memory, all 19 per
         // lane in flight, zero-filled outside the p_rect grid; then update_grid in place
         const FootLane fl = foot_lane(lane);
-        if (TMA && !tc.edge) {   // (tiles on the rim of the grid keep the per-node path: their boxes stick out of the tensor)
+        if (TMA) {   // every tile, the rim included: loads zero-fill whatever lies outside the tensor
             // six 10x10 planes by the tensor memory accelerator (SASS UTMALDG): no LSU wavefronts; every
             // lane orders its previous reads and writes of the tile before the async proxy, then the warp meets
             fence_proxy_async();

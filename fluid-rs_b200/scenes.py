@@ -121,6 +121,21 @@ def dam_break_3d(cx: int, cy: int, cz: int, name: str | None = None) -> Scene:
     return Scene(name or f"dam_break_3d_{cx}x{cy}x{cz}", cfg, [0, 0, 0], [bx, by, bz], n, lo, hi)
 
 
+def dam_break_2d(cells: int, name: str | None = None) -> Scene:
+    """2D dam break: a cells x cells column at the 2D scene's density (4 particles per cell, 2d:24,502-511) resting
+    on the +y wall of a 3x wider box; gravity rescaled to the default scene's hydrostatic load (32 cells at 0.3)."""
+    cfg = default_config(2)
+    bx, by = 3.0 * cells, cells + 32.0
+    cfg["clip_max"] = [bx, by, 64.0]
+    cfg["gravity"] = [0.0, 0.3 * 32.0 / cells, 0.0]
+    n = cells * cells * 4
+    return Scene(name or f"dam_break_2d_{cells}x{cells}", cfg, [0, 0], [bx, by], n, [3.0, by - 3.0 - cells], [3.0 + cells, by - 3.0])
+
+
+def dam_break_2d_1m() -> Scene:   # the 2D tiled path at scale (not a BASELINE config): 2^20 particles
+    return dam_break_2d(512, "dam_break_2d_1M")
+
+
 def dam_break_1m() -> Scene:      # BASELINE config 3
     return dam_break_3d(128, 64, 128, "dam_break_3d_1M")
 

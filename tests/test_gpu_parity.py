@@ -227,6 +227,83 @@ def test_deterministic_mode_is_bit_reproducible(pkg, orc, scenes, dim, n):
     check_one_substep(pkg, orc, sc, rec, deterministic=True)
 
 
+# ---- the tiled 2D path (phases_tiled2d.cuh) -----------------------------------------------------------
+
+def big_2d(scenes, cells=192, per_cell=4):
+    """A 2D dam of cells x cells cells, 4 particles per cell (2d:24), resting on the +y wall of a 3x wider box."""
+    cfg = scenes.default_config(2)
+    box = [3.0 * cells, cells + 32.0]
+    cfg["clip_max"] = [box[0], box[1], 64.0]
+    cfg["gravity"] = [0.0, 0.3 * 32.0 / cells, 0.0]
+    n = cells * cells * per_cell
+    return scenes.Scene(f"dam_break_2d_{cells}", cfg, [0, 0], box, n, [3.0, box[1] - 3.0 - cells], [3.0 + cells, box[1] - 3.0])
+
+
+def test_tiled_2d_one_substep_large(pkg, orc, scenes):
+    """147,456 particles: far above the resident kernel's range, many tiles, rim tiles, 8 windows per tile."""
+    sc = big_2d(scenes)
+    check_one_substep(pkg, orc, sc, randomised(sc, vel=0.2, aff=0.03))
+
+
+def test_generic_2d_path_one_substep(pkg, orc, scenes, monkeypatch):
+    monkeypatch.setenv("FLUID_B200_GENERIC", "1")       # the particle-per-thread kernels stay correct in 2D too
+    sc = scenes.default_2d()
+    check_one_substep(pkg, orc, sc, randomised(sc))
+
+
+def test_tiled_2d_steps_match_generic_and_keep_invariants(pkg, orc, scenes, monkeypatch):
+    """62 substeps of a 36,864-particle 2D dam on the tiled path (CUDA-graph replay included) against the
+    particle-per-thread kernels and, in aggregate, against the oracle."""
+    sc = big_2d(scenes, cells=96)
+    rec = randomised(sc, vel=0.2, aff=0.03)
+    outs = []
+    for flag in ("0", "1"):
+        monkeypatch.setenv("FLUID_B200_GENERIC", flag)
+        sim = pkg.Simulation.new(sc.cfg)
+        sim.set_resident_max(0)
+        sim.add_particles(rec)
+        sim.set_rect(sc.rect_min, sc.rect_max)
+        sim.substeps(62)
+        assert sim.particle_counts() == dict(active=sc.n, frozen=0, outside=0, dropped=0)
+        r, _ = sim.read_particles(sort_by_id=True)
+        outs.append(r)
+        sim.close()
+    assert np.abs(outs[0][:, :2] - outs[1][:, :2]).max() < 5e-3
+    ref = orc.OracleSim(sc.cfg)
+    ref.add_particles(rec)
+    ref.set_rect(sc.rect_min, sc.rect_max)
+    ref.substeps(62)
+    r, _ = ref.read()
+    ke = lambda a: 0.5 * float((a[:, -1].astype(np.float64) * (a[:, 2:4].astype(np.float64) ** 2).sum(axis=1)).sum())
+    assert abs(ke(outs[0]) - ke(r)) < 0.02 * max(ke(r), 1.0)
+    assert abs(float(outs[0][:, 1].mean()) - float(r[:, 1].mean())) < 0.01
+    ref.close()
+
+
+def test_windows_hold_distinct_cells_2d(pkg, scenes):
+    """2D tiles: inside one window no two particles share a cell; windows cover the tile's slots exactly."""
+    sc = big_2d(scenes, cells=64)
+    sim = pkg.Simulation.new(sc.cfg)
+    sim.add_particles(randomised(sc, vel=0.5))
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    sim.set_resident_max(0)
+    for _ in range(3):
+        ids, cidx = sim.neighbour_table()
+        seen = 0
+        for t, first, n, w in sim.debug_tiles().tolist():
+            per, extra = divmod(n, w)
+            off = first
+            for k in range(w):
+                ln = per + (1 if k < extra else 0)
+                assert ln <= 32 and len(np.unique(cidx[off:off + ln])) == ln, (t, k)
+                off += ln
+            assert off == first + n
+            seen += n
+        assert seen == len(ids)
+        sim.substeps(9)
+    sim.close()
+
+
 # ---- block-sparse node storage (3d:52-55, 89-96, 136-146: cost follows the fluid, not the domain) ------
 
 @pytest.mark.parametrize("case", ["default", "dam", "res10", "ragged"])
@@ -356,9 +433,8 @@ def test_neighbour_sets_bit_exact(pkg, orc, scenes, dim):
             assert (np.diff(tile) >= 0).all()
         else:
             x, y = cidx % sz[0], cidx // sz[0]
-            tile = (y // 16) * (-(-sz[0] // 16)) + x // 16
-            local = (y % 16) * 16 + x % 16
-            assert (np.diff(tile * 256 + local) >= 0).all()   # 2D: plain tiled cell order
+            tile = (y // 8) * (-(-sz[0] // 8)) + x // 8       # 2D tiles: 8 x 8 cells, same window order as 3D
+            assert (np.diff(tile) >= 0).all()
         sim.substeps(7)
         ref.substeps(7)
     sim.close()
