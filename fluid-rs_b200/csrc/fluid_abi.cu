@@ -167,6 +167,7 @@ struct fluid_sim {
     bool has_nb[2] = {false, false};
     float* halo_mass_recv[2] = {nullptr, nullptr};
     float4* halo_node_recv[2] = {nullptr, nullptr};
+    long long* halo_fx_recv[2] = {nullptr, nullptr};   // deterministic mode: the neighbour's fixed-point planes
     // profile mode: a pool of event sets, drained into sums when full or when read
     bool profiling = false;
     std::vector<cudaEvent_t> pool;     // PROFILE_POOL * N_EVENTS
@@ -551,7 +552,11 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
     const int n = static_cast<int>(s->n);
     const int* n_dep = s->tile_base + s->geo.n_tiles;
     const bool tiled = s->tiled;   // 3D: phases_tiled.cuh, 2D: phases_tiled2d.cuh
-    if ((!tiled || DIM != 3) && phases != 7) return fail(FLUID_ERR_STATE, "split substeps need the tiled 3D path");
+    // slab runs split the substep at the halo exchanges: the tiled 3D path, or (deterministic mode) the
+    // particle-per-thread kernels with fixed-point node sums
+    const bool slab_generic = DIM == 3 && !tiled && s->det && s->geo.slab_on;
+    if (phases != 7 && !(tiled && DIM == 3) && !slab_generic)
+        return fail(FLUID_ERR_STATE, "split substeps need the tiled 3D path or the deterministic mode");
     const unsigned tb2 = blocks_for(s->geo.n_tiles, T2::WARPS);
     if (phases & 1) {
         s->cur_ev = s->ev;
@@ -615,8 +620,9 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
             if (s->det) {
-                ST_TRY(ensure_fixed(s, 1));
+                ST_TRY(ensure_fixed(s, slab_generic ? 2 : 1));
                 CU_TRY(cudaMemsetAsync(s->fx[0], 0, n_alloc * 4 * sizeof(long long), s->stream));
+                if (slab_generic) CU_TRY(cudaMemsetAsync(s->fx[1], 0, n_alloc * 4 * sizeof(long long), s->stream));
             } else {
                 CU_TRY(cudaMemsetAsync(s->grid, 0, n_alloc * sizeof(float4), s->stream));
             }
@@ -652,10 +658,13 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
         }
         else {
             const NodeGrid ng{s->grid, s->fx[0]};
+            // slab runs: the force deposits go to a buffer of their own, so that the second halo exchange carries
+            // this phase's deposits only (the first one already completed the mass / momentum planes)
+            const NodeGrid ng_out{s->grid, slab_generic ? s->fx[1] : s->fx[0]};
             float* dd = dbg ? dbg->density : nullptr;
             float* dp = dbg ? dbg->pressure : nullptr;
-            if (s->det) k_p2g2_generic<DIM, true><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, dd, dp);
-            else k_p2g2_generic<DIM, false><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, dd, dp);
+            if (s->det) k_p2g2_generic<DIM, true><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, ng_out, dd, dp);
+            else k_p2g2_generic<DIM, false><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, ng_out, dd, dp);
         }
         ++s->launches;
         if (timed) CU_TRY(cudaEventRecord(ev[4], s->stream));
@@ -692,9 +701,16 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             s->counts_pending = true;
         } else {
             const NodeGrid ng{s->grid, s->fx[0]};
-            if (s->det) k_g2p_generic<DIM, true><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, d_mouse);
-            else k_g2p_generic<DIM, false><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, d_mouse);
+            const long long* more = slab_generic ? s->fx[1] : nullptr;
+            if (s->det) k_g2p_generic<DIM, true><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, more, d_mouse);
+            else k_g2p_generic<DIM, false><<<blocks_for(n, 128), 128, 0, s->stream>>>(s->geo, q, s->src, n_dep, ng, more, d_mouse);
             ++s->launches;
+            if (slab_generic) {   // hand the particles that left the slab to the neighbours (behind the header records)
+                k_pack_migrants_generic<<<blocks_for(n, 256), 256, 0, s->stream>>>(
+                    s->geo, q, s->src, n_dep, s->mig_rec[0] ? s->mig_rec[0] + MIG_WORDS : nullptr,
+                    s->mig_rec[1] ? s->mig_rec[1] + MIG_WORDS : nullptr, s->mig_cap, s->scal);
+                ++s->launches;
+            }
             s->sorted_valid = false;   // positions moved; the generic path re-sorts from scratch
         }
         if (timed) {
@@ -1090,6 +1106,7 @@ fluid_status fluid_destroy(fluid_sim* s) {
         cudaFree(s->mig_rec[sd]);
         cudaFree(s->halo_mass_recv[sd]);
         cudaFree(s->halo_node_recv[sd]);
+        cudaFree(s->halo_fx_recv[sd]);
     }
     cudaFree(s->class_count);
     cudaFree(s->geo.sp.blk);
@@ -1766,7 +1783,8 @@ fluid_status fluid_reserve(fluid_sim* s, int64_t capacity) {
 
 fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t has_lower, int32_t has_upper) {
     if (!s) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_set: null handle");
-    if (s->dim != 3 || !s->tiled) return fail(FLUID_ERR_STATE, "fluid_slab_set: needs the tiled 3D path");
+    if (s->dim != 3 || (!s->tiled && !s->det))
+        return fail(FLUID_ERR_STATE, "fluid_slab_set: needs the tiled 3D path (or the deterministic mode)");
     if (!s->rect_set) return fail(FLUID_ERR_STATE, "fluid_slab_set: call set_rect first");
     if (s->pool_blocks) return fail(FLUID_ERR_STATE, "fluid_slab_set: block-sparse node storage is single-GPU (the neighbours index each other's dense planes)");
     CU_TRY(cudaSetDevice(s->device));
@@ -1804,6 +1822,9 @@ fluid_status fluid_slab_set(fluid_sim* s, int32_t z_lo, int32_t z_hi, int32_t ha
         CU_TRY(cudaMemsetAsync(s->mig_recv[sd], 0, MIG_WORDS * sizeof(float), s->stream));
         CU_TRY(cudaMalloc(&s->halo_mass_recv[sd], plane2 * sizeof(float)));
         CU_TRY(cudaMalloc(&s->halo_node_recv[sd], plane2 * sizeof(float4)));
+        cudaFree(s->halo_fx_recv[sd]);
+        s->halo_fx_recv[sd] = nullptr;
+        if (s->det) CU_TRY(cudaMalloc(&s->halo_fx_recv[sd], plane2 * 4 * sizeof(long long)));
     }
     s->sorted_valid = s->counts_pending = false;
     return FLUID_OK;
@@ -1817,6 +1838,16 @@ fluid_status fluid_slab_planes(fluid_sim* s, int32_t side, int32_t kind, void** 
     const int64_t plane = static_cast<int64_t>(s->geo.size[0]) * s->geo.size[1];
     const int64_t first = s->geo.guard + (zb - 1) * plane;          // node planes zb-1 and zb
     *n_elems = 2 * plane;
+    if (s->det) {
+        // deterministic mode: kind 0 = the fixed-point sums after "p2g 1" (mass + momentum), kind 1 = the force
+        // deposits of "p2g 2" (their own buffer); 32 bytes per node either way, so n_elems is scaled to what the
+        // caller multiplies it with (4 bytes for kind 0, 16 for kind 1)
+        ST_TRY(ensure_fixed(s, 2));
+        *d_own = s->fx[kind] + first * 4;
+        *d_recv = s->halo_fx_recv[side];
+        *n_elems = kind == 0 ? 2 * plane * 8 : 2 * plane * 2;
+        return FLUID_OK;
+    }
     if (kind == 0) {
         *d_own = s->gmass + first;
         *d_recv = s->halo_mass_recv[side];
@@ -1833,6 +1864,15 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
     CU_TRY(cudaSetDevice(s->device));
     const float* d_mouse = nullptr;
     if (phase == 2) ST_TRY(upload_mouse(s, mouse_xy, &d_mouse));
+    if (s->n == 0 && !s->tiled) {   // deterministic mode, empty rank: its planes must still be zero for the exchanges
+        if (phase == 0) {
+            ST_TRY(ensure_fixed(s, 2));
+            CU_TRY(cudaMemsetAsync(s->fx[0], 0, s->node_alloc * 4 * sizeof(long long), s->stream));
+            CU_TRY(cudaMemsetAsync(s->fx[1], 0, s->node_alloc * 4 * sizeof(long long), s->stream));
+            CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
+        }
+        return FLUID_OK;
+    }
     if (s->n == 0) {
         // a rank may hold no particles yet still has to take part in the exchanges: its planes must be zero
         if (phase == 0 && !s->grid_clean) {
@@ -1868,6 +1908,12 @@ fluid_status fluid_slab_accumulate(fluid_sim* s, int32_t side, int32_t kind) {
     const int64_t plane = static_cast<int64_t>(s->geo.size[0]) * s->geo.size[1];
     const int64_t first = s->geo.guard + (zb - 1) * plane;
     const int64_t n = 2 * plane;
+    if (s->det) {
+        k_accumulate_fixed<<<blocks_for(n * 4, 256), 256, 0, s->stream>>>(s->fx[kind] + first * 4, s->halo_fx_recv[side], n * 4);
+        ++s->launches;
+        CU_TRY(cudaGetLastError());
+        return FLUID_OK;
+    }
     unsigned char* dirty = s->dirty[s->dirty_cur];
     if (kind == 0)
         k_accumulate_planes<float><<<blocks_for(n, 256), 256, 0, s->stream>>>(s->geo, s->gmass + first, s->halo_mass_recv[side], n, zb - 1, dirty);
@@ -1936,6 +1982,24 @@ fluid_status fluid_slab_migrants_end(fluid_sim* s, const void* d_recv_lower, con
         // the buffer g2p + k_tail just wrote ends where this substep's sort put the dropped bucket
         s->dropped_total += h[8 + 2] - h[8 + 1];
         s->n = h[8 + 1];
+    }
+    if (!s->tiled && s->n > 0 && (n_out[0] + n_out[1]) > 0) {
+        // particle-per-thread path (deterministic mode): the particles that left the slab are dead entries in
+        // storage; sort by the new positions and keep what lies before the "dropped" bucket
+        ST_TRY(sort_cold<3>(s));
+        int tail[4];
+        CU_TRY(cudaMemcpyAsync(tail, s->tile_base + s->geo.n_tiles, sizeof(tail), cudaMemcpyDeviceToHost, s->stream));
+        CU_TRY(cudaStreamSynchronize(s->stream));
+        const int keep = tail[1];
+        if (keep > 0) {
+            k_gather_range<3><<<blocks_for(keep, 256), 256, 0, s->stream>>>(s->buf[s->cur], s->buf[s->cur ^ 1], s->src, 0, keep);
+            ++s->launches;
+            CU_TRY(cudaGetLastError());
+            s->cur ^= 1;
+        }
+        s->dropped_total += tail[2] - tail[1];
+        s->n = keep;
+        s->sorted_valid = false;
     }
     return FLUID_OK;
 }
@@ -2013,6 +2077,8 @@ fluid_status fluid_slab_ipc_export(fluid_sim* s, void* handles) {
 fluid_status fluid_slab_ipc_import(fluid_sim* s, int32_t side, const void* handles) {
     if (!s || side < 0 || side > 1) return fail(FLUID_ERR_INVALID_ARG, "fluid_slab_ipc_import: bad argument");
     if (!s->geo.slab_on) return fail(FLUID_ERR_STATE, "fluid_slab_ipc_import: fluid_slab_set has not been called");
+    if (s->det && handles)
+        return fail(FLUID_ERR_STATE, "fluid_slab_ipc_import: the deterministic mode exchanges its fixed-point planes (no peer-memory halo)");
     CU_TRY(cudaSetDevice(s->device));
     close_peer(s, side);
     if (!handles) {   // back to plane exchanges on this side

@@ -66,11 +66,19 @@ __device__ __forceinline__ float node_mass(const NodeGrid& ng, int idx) {
     if (!DET) return __ldcg(reinterpret_cast<const float*>(&ng.f[idx]) + 3);   // .w lane only: others are being written
     return from_fixed(__ldcg(ng.fx + 4 * static_cast<size_t>(idx) + 3));
 }
+// `more`: a second fixed-point buffer whose sums belong to the same nodes (slab runs keep the force deposits of
+// "p2g 2" apart so that each halo exchange carries one phase's deposits): added as INTEGERS, then converted, so
+// the result equals the single-buffer sum bit for bit.
 template <bool DET>
-__device__ __forceinline__ float4 node_load(const NodeGrid& ng, int idx) {
+__device__ __forceinline__ float4 node_load(const NodeGrid& ng, int idx, const long long* more = nullptr) {
     if (!DET) return __ldcg(&ng.f[idx]);
     const longlong2* p = reinterpret_cast<const longlong2*>(ng.fx + 4 * static_cast<size_t>(idx));
-    const longlong2 a = __ldcg(p), b = __ldcg(p + 1);
+    longlong2 a = __ldcg(p), b = __ldcg(p + 1);
+    if (more) {
+        const longlong2* p2 = reinterpret_cast<const longlong2*>(more + 4 * static_cast<size_t>(idx));
+        const longlong2 a2 = __ldcg(p2), b2 = __ldcg(p2 + 1);
+        a.x += a2.x; a.y += a2.y; b.x += b2.x; b.y += b2.y;
+    }
     return make_float4(from_fixed(a.x), from_fixed(a.y), from_fixed(b.x), from_fixed(b.y));
 }
 template <bool DET>
@@ -126,7 +134,7 @@ __device__ __forceinline__ void p2g1_particle(const Geo& g, const NodeGrid& ng, 
 
 // p2g_2 (3d:185-247): density from node masses, Tait pressure, stress, force scatter.
 template <int DIM, bool DET>
-__device__ __forceinline__ void p2g2_particle(const Geo& g, const NodeGrid& ng, const Stencil<DIM>& s,
+__device__ __forceinline__ void p2g2_particle(const Geo& g, const NodeGrid& ng, const NodeGrid& ng_out, const Stencil<DIM>& s,
                                               const float* C, float m, float& density, float& pressure) {
     constexpr int NZ = DIM == 3 ? 3 : 1;
     density = 0.0f;
@@ -171,7 +179,7 @@ __device__ __forceinline__ void p2g2_particle(const Geo& g, const NodeGrid& ng, 
                     for (int c = 0; c < DIM; ++c) acc += T[DIM * c + r] * d[c];
                     f[r] = w * acc;
                 }
-                node_add<DET>(ng, node_index<DIM>(g, s, ox, oy, oz), make_float4(f[0], f[1], f[2], 0.0f));
+                node_add<DET>(ng_out, node_index<DIM>(g, s, ox, oy, oz), make_float4(f[0], f[1], f[2], 0.0f));
             }
 }
 
@@ -214,7 +222,8 @@ __device__ __forceinline__ bool left_p_rect(const Geo& g, const float* pos) {
 // update_grid + g2p (3d:249-343) for one particle: new velocity, B (C = 4B), new position.
 template <int DIM, bool DET>
 __device__ __forceinline__ void g2p_particle(const Geo& g, const NodeGrid& ng, const Stencil<DIM>& s,
-                                             const float* mouse, float* pos, float* vel, float* B) {
+                                             const float* mouse, float* pos, float* vel, float* B,
+                                             const long long* more = nullptr) {
     constexpr int NZ = DIM == 3 ? 3 : 1;
 #pragma unroll
     for (int a = 0; a < 3; ++a) vel[a] = 0.0f;
@@ -229,7 +238,7 @@ __device__ __forceinline__ void g2p_particle(const Geo& g, const NodeGrid& ng, c
                 float w = s.w[0][ox] * s.w[1][oy];
                 if (DIM == 3) w *= s.w[2][oz];
                 float d[3] = {s.d[0][ox], s.d[1][oy], DIM == 3 ? s.d[2][oz] : 0.0f};
-                float4 nd = node_load<DET>(ng, node_index<DIM>(g, s, ox, oy, oz));
+                float4 nd = node_load<DET>(ng, node_index<DIM>(g, s, ox, oy, oz), more);
                 float nv[3] = {nd.x, nd.y, nd.z};
                 if (nd.w > 0.0f) {   // update_grid (3d:253-256)
 #pragma unroll
@@ -270,7 +279,7 @@ k_p2g1_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict
 template <int DIM, bool DET>
 __global__ void __launch_bounds__(128)
 k_p2g2_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
-               const int* __restrict__ n_deposit, NodeGrid ng,
+               const int* __restrict__ n_deposit, NodeGrid ng, NodeGrid ng_out,
                float* __restrict__ dbg_density, float* __restrict__ dbg_pressure) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= *n_deposit) return;
@@ -282,7 +291,7 @@ k_p2g2_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict
     Stencil<DIM> s;
     make_stencil<DIM>(g, pos, s);
     float density, pressure;
-    p2g2_particle<DIM, DET>(g, ng, s, C, p.w, density, pressure);
+    p2g2_particle<DIM, DET>(g, ng, ng_out, s, C, p.w, density, pressure);
     if (dbg_density) dbg_density[d] = density;
     if (dbg_pressure) dbg_pressure[d] = pressure;
 }
@@ -290,7 +299,8 @@ k_p2g2_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict
 template <int DIM, bool DET>
 __global__ void __launch_bounds__(128)
 k_g2p_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
-              const int* __restrict__ n_deposit, NodeGrid ng, const float* __restrict__ mouse) {
+              const int* __restrict__ n_deposit, NodeGrid ng, const long long* __restrict__ more,
+              const float* __restrict__ mouse) {
     int d = blockIdx.x * blockDim.x + threadIdx.x;
     if (d >= *n_deposit) return;
     if (mouse && mouse[2] == 0.0f) mouse = nullptr;   // {x, y, present}
@@ -301,7 +311,7 @@ k_g2p_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict_
     Stencil<DIM> s;
     make_stencil<DIM>(g, pos, s);
     float vel[3], B[9];
-    g2p_particle<DIM, DET>(g, ng, s, mouse, pos, vel, B);
+    g2p_particle<DIM, DET>(g, ng, s, mouse, pos, vel, B, more);
     float4 v_old = q.V[i];
     q.P[i] = make_float4(pos[0], pos[1], DIM == 3 ? pos[2] : 0.0f, p.w);
     q.V[i] = make_float4(vel[0], vel[1], DIM == 3 ? vel[2] : 0.0f, v_old.w);
@@ -374,7 +384,7 @@ k_substeps_resident(const __grid_constant__ Geo g, Particles q, int n, NodeGrid 
         if (clock && last) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamps[2]));
         if (deposits) {
             float density, pressure;
-            p2g2_particle<DIM, DET>(g, G, s, C, m, density, pressure);
+            p2g2_particle<DIM, DET>(g, G, G, s, C, m, density, pressure);
         }
         grid.sync();
         if (clock && last) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(stamps[3]));
@@ -396,6 +406,45 @@ k_substeps_resident(const __grid_constant__ Geo g, Particles q, int n, NodeGrid 
             q.CC[i] = C[8];
         }
     }
+}
+
+// Slab runs on the particle-per-thread path (deterministic mode): after g2p, the particles whose cell left this
+// rank's z slab are packed for the neighbour (17 words: 16 f32 + id, as k_g2p_tiled packs them).  They stay in
+// storage as dead entries (the next sort files them under "migrated") until the host compacts them away.
+__global__ void __launch_bounds__(256)
+k_pack_migrants_generic(const __grid_constant__ Geo g, Particles q, const int* __restrict__ src,
+                        const int* __restrict__ n_deposit, float* rec_lo, float* rec_hi, int cap, int* __restrict__ scal) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= *n_deposit) return;
+    const int i = src[d];
+    const float4 a = q.P[i];
+    if (is_tombstone(a.x)) return;
+    const int rz = rust_as_i32(floorf(a.z)) - g.org[2];
+    if (rz >= g.slab_lo && rz < g.slab_hi) return;
+    float pos[3] = {a.x, a.y, a.z};
+    if (classify_pos<3>(g, pos) == CLS_LIMBO) return;   // left p_rect altogether: not the neighbour's either
+    const int side = rz < g.slab_lo ? 0 : 1;
+    float* rec = side == 0 ? rec_lo : rec_hi;
+    const int slot = atomicAdd(&scal[SCAL_MIG_LO + side], 1);
+    if (!rec || slot >= cap) {
+        scal[SCAL_MIG_OVERFLOW] = 1;
+        return;
+    }
+    float* r = rec + static_cast<size_t>(slot) * MIG_WORDS;
+    const float4 v = q.V[i], ca = q.CA[i], cb = q.CB[i];
+    r[0] = a.x; r[1] = a.y; r[2] = a.z;
+    r[3] = v.x; r[4] = v.y; r[5] = v.z;
+    r[6] = ca.x; r[7] = ca.y; r[8] = ca.z; r[9] = ca.w;
+    r[10] = cb.x; r[11] = cb.y; r[12] = cb.z; r[13] = cb.w;
+    r[14] = q.CC[i];
+    r[15] = a.w;
+    r[16] = v.w;   // id bits
+}
+
+// own fixed-point planes += the neighbour's (integer addition: both ranks end with the same bits, in any order)
+__global__ void k_accumulate_fixed(long long* __restrict__ own, const long long* __restrict__ recv, int64_t n) {
+    const int64_t e = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (e < n) own[e] += recv[e];
 }
 
 // DET: the float view of the fixed-point grid (read-backs and parity taps read float4 records)

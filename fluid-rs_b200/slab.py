@@ -391,14 +391,22 @@ class SlabSimulation:
         self.sim.close()
 
 
-def parity_check(pkg, dist, rank: int, world: int, device: int, substeps: int = 60, tol: float = 2e-4) -> dict:
+def parity_check(pkg, dist, rank: int, world: int, device: int, substeps: int = 60, tol: float = 2e-4,
+                 deterministic: bool = False) -> dict:
     """N-rank z-slab run against the single-GPU run of the same sloshing scene (81,920 particles, every
     rank crosses its faces).  Collective: every rank of `dist` must call it.  Rank 0 returns the verdict
     {ok, ranks, particles, substeps, max_dpos, max_dvel, tol, migrated_out, migrated_in, ids_once, halo};
     the other ranks return {ok} only.  Bars: every id present exactly once over the ranks, particles sent ==
     particles received (> 0), and |dpos|, |dvel| < tol against the one-GPU run (the node sums of the shared
-    planes are float reductions in a different order, so the last bits differ; measured 5e-5 / 3e-5)."""
+    planes are float reductions in a different order, so the last bits differ; measured 5e-5 / 3e-5).
+    deterministic=True runs both sides in the deterministic mode (64-bit fixed-point node sums, planes exchanged
+    and added as integers): the bar becomes BIT-FOR-BIT equality of every field of every particle."""
+    import os
     import torch
+    old_env = os.environ.get("FLUID_B200_DETERMINISTIC")
+    if deterministic:
+        os.environ["FLUID_B200_DETERMINISTIC"] = "1"      # read by fluid_create
+        tol = 0.0
     sc = pkg.scenes.dam_break_3d(40, 32, 64)
     rec = sc.records()
     rng = np.random.default_rng(3)
@@ -418,6 +426,7 @@ def parity_check(pkg, dist, rank: int, world: int, device: int, substeps: int = 
         one = pkg.Simulation.new(sc.cfg, device=device)
         one.add_particles(rec, ids)
         one.set_rect(sc.rect_min, sc.rect_max)
+        one.set_resident_max(0)
         one.substeps(substeps)
         ref, rid = one.read_particles(sort_by_id=True)
         one.close()
@@ -429,13 +438,20 @@ def parity_check(pkg, dist, rank: int, world: int, device: int, substeps: int = 
         ids_once = bool(np.array_equal(allid, rid))
         dp = float(np.abs(allrec[:, :3] - ref[:, :3]).max()) if ids_once else float("inf")
         dv = float(np.abs(allrec[:, 3:6] - ref[:, 3:6]).max()) if ids_once else float("inf")
-        res = {"ok": bool(ids_once and dp < tol and dv < tol and sent > 0 and sent == got),
+        bitwise = bool(ids_once and np.array_equal(allrec.view(np.uint32), ref.view(np.uint32)))
+        close = bitwise if deterministic else (dp < tol and dv < tol)
+        res = {"ok": bool(ids_once and close and sent > 0 and sent == got), "deterministic": deterministic, "bitwise_equal": bitwise,
                "ranks": world, "particles": int(sc.n), "substeps": int(substeps), "max_dpos": dp, "max_dvel": dv,
                "tol": tol, "migrated_out": int(sent), "migrated_in": int(got), "ids_once": ids_once,
                "halo": "peer memory (P2P deposits)" if sim.p2p else "plane exchange",
                "slabs": [list(g[5]) for g in gathered], "start": [int(g[2]) for g in gathered],
                "end": [int(len(g[1])) for g in gathered]}
     sim.close()
+    if deterministic:
+        if old_env is None:
+            os.environ.pop("FLUID_B200_DETERMINISTIC", None)
+        else:
+            os.environ["FLUID_B200_DETERMINISTIC"] = old_env
     flag = torch.tensor([1 if res["ok"] else 0], device=f"cuda:{device}")
     dist.broadcast(flag, 0)
     if rank != 0:

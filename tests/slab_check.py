@@ -24,9 +24,13 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = fluidpkg.load()
     res = pkg.slab.parity_check(pkg, dist, rank, world, local, substeps=substeps)
+    # the same scene in the deterministic mode: the N-rank run must equal the one-GPU run BIT FOR BIT
+    det = pkg.slab.parity_check(pkg, dist, rank, world, local, substeps=substeps, deterministic=True)
     if rank == 0:
         print(json.dumps(res))
-        print("SLAB CHECK", "OK" if res["ok"] else "FAILED")
+        print(json.dumps(det))
+        print("SLAB CHECK", "OK" if res["ok"] and det["ok"] else "FAILED")
+    res["ok"] = res["ok"] and det["ok"]
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if res["ok"] else 1)
