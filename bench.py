@@ -497,6 +497,10 @@ def run_slabs(args, pkg, world, rank, local_rank):
     # Parity first, outside every timed region: the N-rank slab run of a small sloshing scene against the one-GPU
     # run of the same scene (ids exactly once, sent == received, |dpos|, |dvel| under the stated bound).
     parity = pkg.slab.parity_check(pkg, dist, rank, world, local_rank)
+    # ... and the same scene in the deterministic mode (fixed-point node sums, planes added as integers): BIT-FOR-BIT
+    det = pkg.slab.parity_check(pkg, dist, rank, world, local_rank, deterministic=True)
+    parity = dict(parity, ok=bool(parity["ok"] and det["ok"]), float_path_ok=parity["ok"],
+                  deterministic_mode={k: det.get(k) for k in ("ok", "bitwise_equal", "migrated_out", "migrated_in", "halo")})
     sc = scenes.dam_break_for_gpus(world)
     iters = sc.cfg["iterations"]
     rf = scenes.rec_floats(3)

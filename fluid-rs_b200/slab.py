@@ -391,14 +391,15 @@ class SlabSimulation:
         self.sim.close()
 
 
-def parity_check(pkg, dist, rank: int, world: int, device: int, substeps: int = 60, tol: float = 2e-4,
+def parity_check(pkg, dist, rank: int, world: int, device: int, substeps: int = 60, tol: float = 5e-4,
                  deterministic: bool = False) -> dict:
     """N-rank z-slab run against the single-GPU run of the same sloshing scene (81,920 particles, every
     rank crosses its faces).  Collective: every rank of `dist` must call it.  Rank 0 returns the verdict
     {ok, ranks, particles, substeps, max_dpos, max_dvel, tol, migrated_out, migrated_in, ids_once, halo};
     the other ranks return {ok} only.  Bars: every id present exactly once over the ranks, particles sent ==
     particles received (> 0), and |dpos|, |dvel| < tol against the one-GPU run (the node sums of the shared
-    planes are float reductions in a different order, so the last bits differ; measured 5e-5 / 3e-5).
+    planes are float reductions in a different order, so the last bits differ and 60 substeps of sloshing amplify
+    them: measured 4e-5 .. 1.1e-4 from run to run).
     deterministic=True runs both sides in the deterministic mode (64-bit fixed-point node sums, planes exchanged
     and added as integers): the bar becomes BIT-FOR-BIT equality of every field of every particle."""
     import os
