@@ -227,6 +227,35 @@ def test_deterministic_mode_is_bit_reproducible(pkg, orc, scenes, dim, n):
     check_one_substep(pkg, orc, sc, rec, deterministic=True)
 
 
+@pytest.mark.parametrize("dim", [2, 3])
+def test_other_config_values_one_substep(pkg, orc, scenes, dim):
+    """Config fields away from their defaults (3d:3-15): the Becker-Teschner exponent 7 (the powf path instead of
+    the two multiplies of the default 4), another stiffness / viscosity / rest density / dt, a clip box that does
+    not start at the origin (negative block keys, div_euclid below zero), an odd grid_res."""
+    sc = scenes.default_2d(3000) if dim == 2 else scenes.default_3d(3000)
+    cfg = dict(sc.cfg)
+    cfg.update(eos_power=7.0, eos_stiffness=3.5, dynamic_viscosity=0.25, rest_density=cfg["rest_density"] * 1.3,
+               dt=cfg["dt"] * 0.7, grid_res=12 if dim == 3 else 24, boundary_damp_dist=2.0, pressure_clamp=-0.05,
+               clip_min=[-21.0, -9.0, -14.0], clip_max=[43.0, 55.0, 50.0], gravity=[0.05, 0.2, -0.1])
+    sc.cfg = cfg
+    rec = randomised(sc)
+    rec[:, :dim] -= np.float32(20.0)             # the cloud straddles the origin
+    sc.rect_min = np.asarray([-21.0, -9.0, -14.0][:dim], dtype=np.float32)
+    sc.rect_max = np.asarray([43.0, 55.0, 50.0][:dim], dtype=np.float32)
+    check_one_substep(pkg, orc, sc, rec)
+    # ... and through step() (resident kernel) for a few substeps
+    sim, ref = build_pair(pkg, orc, sc.cfg, rec, sc.rect_min, sc.rect_max)
+    sim.substeps(3)
+    ref.substeps(3)
+    g, gi = sim.read_particles(sort_by_id=True)
+    r, ri = ref.read()
+    o = np.argsort(ri)
+    assert np.array_equal(gi, ri[o])
+    assert np.abs(g[:, :dim] - r[o][:, :dim]).max() < 1e-4
+    sim.close()
+    ref.close()
+
+
 # ---- the tiled 2D path (phases_tiled2d.cuh) -----------------------------------------------------------
 
 def big_2d(scenes, cells=192, per_cell=4):
