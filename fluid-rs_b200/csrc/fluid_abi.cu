@@ -84,6 +84,8 @@ struct fluid_sim {
     int64_t n = 0;          // particle slots in use (live + not yet compacted tombstones)
     int64_t cap = 0;
     Particles buf[2]{};
+    ParticleTex tex[2]{};    // the same arrays (and src) as linear textures: gathers through the TEX pipe (sort.cuh)
+    bool tex_on = true;      // FLUID_B200_TEX=0 keeps the gathers on __ldg
     int cur = 0;
     // neighbour search (sort.cuh)
     int* gcell = nullptr;    // per particle: bucket (tile * 256 + cell in tile)
@@ -209,6 +211,61 @@ fluid_status alloc_particles(Particles& p, int64_t cap) {
     return FLUID_OK;
 }
 
+void free_textures(fluid_sim* s) {
+    for (int b = 0; b < 2; ++b) {
+        cudaTextureObject_t* t[6] = {&s->tex[b].P, &s->tex[b].V, &s->tex[b].CA, &s->tex[b].CB, &s->tex[b].CC, &s->tex[b].src};
+        for (int k = 0; k < 6; ++k) {
+            if (*t[k] && !(b == 1 && k == 5)) cudaDestroyTextureObject(*t[k]);   // (src is one object, held by both)
+            *t[k] = 0;
+        }
+    }
+    (void)cudaGetLastError();
+}
+
+template <typename T>
+cudaTextureObject_t linear_texture(const T* ptr, int64_t n, int device) {
+    const cudaChannelFormatDesc fmt = cudaCreateChannelDesc<T>();
+    size_t max_elems = 0;
+    if (cudaDeviceGetTexture1DLinearMaxWidth(&max_elems, &fmt, device) != cudaSuccess || static_cast<size_t>(n) > max_elems) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeLinear;
+    rd.res.linear.devPtr = const_cast<T*>(ptr);
+    rd.res.linear.desc = fmt;
+    rd.res.linear.sizeInBytes = static_cast<size_t>(n) * sizeof(T);
+    cudaTextureDesc td{};
+    td.readMode = cudaReadModeElementType;
+    cudaTextureObject_t t = 0;
+    if (cudaCreateTextureObject(&t, &rd, &td, nullptr) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return 0;
+    }
+    return t;
+}
+
+// all or nothing: the kernels test one handle per stream, but a partial set would only complicate the fallback
+void make_textures(fluid_sim* s) {
+    free_textures(s);
+    if (!s->tex_on || s->dim != 3 || s->cap <= 0) return;
+    const cudaTextureObject_t ts = linear_texture(s->src, s->cap, s->device);
+    bool ok = ts != 0;
+    for (int b = 0; b < 2 && ok; ++b) {
+        s->tex[b].P = linear_texture(s->buf[b].P, s->cap, s->device);
+        s->tex[b].V = linear_texture(s->buf[b].V, s->cap, s->device);
+        s->tex[b].CA = linear_texture(s->buf[b].CA, s->cap, s->device);
+        s->tex[b].CB = linear_texture(s->buf[b].CB, s->cap, s->device);
+        s->tex[b].CC = linear_texture(s->buf[b].CC, s->cap, s->device);
+        s->tex[b].src = ts;
+        ok = s->tex[b].P && s->tex[b].V && s->tex[b].CA && s->tex[b].CB && s->tex[b].CC;
+    }
+    if (!ok) {
+        if (ts && !s->tex[0].src) cudaDestroyTextureObject(ts);
+        free_textures(s);
+    }
+}
+
 fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     if (want <= s->cap) return FLUID_OK;
     if (want > INT_MAX - 1024) return fail(FLUID_ERR_INVALID_ARG, "more than 2^31 particles per handle");
@@ -241,6 +298,7 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
         return st;
     }
     graphs_drop(s);   // the captured launches hold the old pointers
+    free_textures(s);
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->gcell);
     cudaFree(s->rank);
@@ -255,6 +313,7 @@ fluid_status ensure_capacity(fluid_sim* s, int64_t want) {
     s->src = tabs[3];
     s->sorted_valid = s->counts_pending = false;
     s->cap = cap;
+    make_textures(s);
     return FLUID_OK;
 }
 
@@ -612,10 +671,10 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                                                                                           s->grid);
             else if (s->p2p)
                 k_mass_tiled<true><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                            s->gmass, s->grid, s->peer);
+                                                                                            s->gmass, s->grid, s->peer, s->tex[s->cur]);
             else
                 k_mass_tiled<false><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                             s->gmass, s->grid, s->peer);
+                                                                                             s->gmass, s->grid, s->peer, s->tex[s->cur]);
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
@@ -649,7 +708,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
 #define P2G_LAUNCH(PEER, TMA)                                                                                       \
     k_p2g_tiled<PEER, TMA><<<gp, T3::THREADS, sizeof(P2GSmem), s->stream>>>(s->geo, q, s->src, s->tiles, n_act, s->gmass, \
                                                                            s->grid, dd, dp, s->peer, s->tm_grid, s->tm_mass,     \
-                                                                           s->tma_mass ? 1 : 0)
+                                                                           s->tma_mass ? 1 : 0, s->tex[s->cur])
             if (s->p2p && s->tma) P2G_LAUNCH(true, true);
             else if (s->p2p) P2G_LAUNCH(true, false);
             else if (s->tma) P2G_LAUNCH(false, true);
@@ -687,10 +746,12 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                                                                                         d_mouse, sort_tables(s), s->gmass, s->gz, s->d_epoch);
             else if (s->tma)
                 k_g2p_tiled<true, true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid);
+                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid,
+                    s->tex[s->cur]);
             else
                 k_g2p_tiled<true, false><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid);
+                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid,
+                    s->tex[s->cur]);
             // ignored (and, outside slab runs, dropped) particles sit behind the tiles: carried over
             // and counted here; a slab run ends dropped / migrated particles at this point
             const int* n_end = s->geo.slab_on ? s->tile_base + s->geo.n_tiles + 1 : nullptr;
@@ -1008,6 +1069,7 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     const char* force_generic = std::getenv("FLUID_B200_GENERIC");
     s->tiled = !(force_generic && force_generic[0] == '1');
     if (const char* e = std::getenv("FLUID_B200_GRAPH")) s->graphs_on = e[0] != '0';
+    if (const char* e = std::getenv("FLUID_B200_TEX")) s->tex_on = e[0] != '0';
     if (const char* e = std::getenv("FLUID_B200_SPARSE_BLOCKS")) {
         if (cfg->dim == 3) s->sparse_blocks = std::max<long long>(std::atoll(e), 0);
     }
@@ -1076,6 +1138,7 @@ fluid_status fluid_destroy(fluid_sim* s) {
     cudaSetDevice(s->device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     graphs_drop(s);
+    free_textures(s);
     for (int b = 0; b < 2; ++b) free_particles(s->buf[b]);
     cudaFree(s->gcell);
     cudaFree(s->rank);

@@ -334,7 +334,8 @@ template <bool PEER>   // PEER: slab run with the neighbours' arrays mapped (dep
 __global__ void __launch_bounds__(T3::THREADS)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
-             const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid, PeerHalo ph) {
+             const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid, PeerHalo ph,
+             ParticleTex tq) {
     __shared__ float4 sm[T3::WARPS * T3::QSLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* tile = sm + warp * T3::QSLOTS;
@@ -355,18 +356,18 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
         int off, len;
         window_range(tc, 0, off, len);
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < len) p_next = __ldg(&P[__ldg(&src[tc.base + off + lane])]);
+        if (lane < len) p_next = fetch_f4(tq.P, P, fetch_i(tq.src, src, tc.base + off + lane));
         window_range(tc, 1, off, len);
-        int i_next = lane < len ? __ldg(&src[tc.base + off + lane]) : 0;
+        int i_next = lane < len ? fetch_i(tq.src, src, tc.base + off + lane) : 0;
         for (int w = 0; w < tc.windows; ++w) {
             window_range(tc, w, off, len);
             const bool active = lane < len;
             const int len_w = len;
             const float4 p = p_next;
             window_range(tc, w + 1, off, len);
-            if (lane < len) p_next = __ldg(&P[i_next]);
+            if (lane < len) p_next = fetch_f4(tq.P, P, i_next);
             window_range(tc, w + 2, off, len);
-            if (lane < len) i_next = __ldg(&src[tc.base + off + lane]);
+            if (lane < len) i_next = fetch_i(tq.src, src, tc.base + off + lane);
             TStencil s;
             tile_stencil(g, tc, p.x, p.y, p.z, s);
             const float wqm[4] = {s.wq[0] * p.w, s.wq[1] * p.w, s.wq[2] * p.w, s.wq[3] * p.w};
@@ -437,13 +438,13 @@ struct PRec {   // one particle's streams
     float cc;
 };
 
-__device__ __forceinline__ void load_prec(const Particles& q, int i, bool ok, PRec& r) {
+__device__ __forceinline__ void load_prec(const Particles& q, const ParticleTex& tq, int i, bool ok, PRec& r) {
     if (ok) {
-        r.p = __ldg(&q.P[i]);
-        r.v = __ldg(&q.V[i]);
-        r.ca = __ldg(&q.CA[i]);
-        r.cb = __ldg(&q.CB[i]);
-        r.cc = __ldg(&q.CC[i]);
+        r.p = fetch_f4(tq.P, q.P, i);
+        r.v = fetch_f4(tq.V, q.V, i);
+        r.ca = fetch_f4(tq.CA, q.CA, i);
+        r.cb = fetch_f4(tq.CB, q.CB, i);
+        r.cc = fetch_f(tq.CC, q.CC, i);
     }
 }
 
@@ -453,7 +454,8 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float* __restrict__ gmass, float4* __restrict__ grid,
             float* __restrict__ dbg_density, float* __restrict__ dbg_pressure, PeerHalo ph,
-            const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_mass, int tma_mass) {
+            const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_mass, int tma_mass,
+            ParticleTex tq) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     __shared__ __align__(8) unsigned long long bars[T3::WARPS];
@@ -481,9 +483,9 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         PRec nxt;
         nxt.p = nxt.v = nxt.ca = nxt.cb = make_float4(0.f, 0.f, 0.f, 0.f);
         nxt.cc = 0.0f;
-        load_prec(q, lane < len ? __ldg(&src[tc.base + off + lane]) : 0, lane < len, nxt);
+        load_prec(q, tq, lane < len ? fetch_i(tq.src, src, tc.base + off + lane) : 0, lane < len, nxt);
         window_range(tc, 1, off, len);
-        int i_next = lane < len ? __ldg(&src[tc.base + off + lane]) : 0;
+        int i_next = lane < len ? fetch_i(tq.src, src, tc.base + off + lane) : 0;
         const FootLane fl = foot_lane(lane);
         // the node masses of the footprint as ONE tensor copy (box 12 x 10 x 6 floats) into the accumulator
         // tile, which is idle until the first window; unpacked into z quads below
@@ -551,9 +553,9 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             const int d = tc.base + off + lane;   // sorted slot
             const PRec cur = nxt;
             window_range(tc, w + 1, off, len);
-            load_prec(q, i_next, lane < len, nxt);            // prefetch the next window
+            load_prec(q, tq, i_next, lane < len, nxt);        // prefetch the next window
             window_range(tc, w + 2, off, len);
-            if (lane < len) i_next = __ldg(&src[tc.base + off + lane]);
+            if (lane < len) i_next = fetch_i(tq.src, src, tc.base + off + lane);
             TStencil s;
             tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
             // idle lanes read where the first lane of their quarter warp reads (128-bit accesses are served
@@ -695,7 +697,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb,
             float* __restrict__ gmass, int* __restrict__ gz, const int* __restrict__ epoch_dev,
-            const __grid_constant__ CUtensorMap tm_grid) {
+            const __grid_constant__ CUtensorMap tm_grid, ParticleTex tq) {
     const int epoch = *epoch_dev + 1;   // this substep's number (k_tail advances the counter after this kernel)
     if (mouse && mouse[2] == 0.0f) mouse = nullptr;   // {x, y, present}: the pointer itself never changes (CUDA graphs)
     __shared__ __align__(128) float4 sm[T3::WARPS * T3::SLOTS];
@@ -724,14 +726,14 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         // q = state before this substep (storage order, read through src);
         // qn = state after it, written at the sorted slot.  g2p has no write conflicts, so it walks
         // the tile's slots 32 at a time regardless of the window structure.
-        int i_cur = lane < tc.count ? __ldg(&src[tc.base + lane]) : 0;
+        int i_cur = lane < tc.count ? fetch_i(tq.src, src, tc.base + lane) : 0;
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
         float id_next = 0.0f;            // the particle id travels in V.w: fetched with the position, a window ahead
         if (lane < tc.count) {
-            p_next = __ldg(&q.P[i_cur]);
-            id_next = __ldg(&q.V[i_cur].w);
+            p_next = fetch_f4(tq.P, q.P, i_cur);
+            id_next = tq.V ? tex1Dfetch<float4>(tq.V, i_cur).w : __ldg(&q.V[i_cur].w);
         }
-        int i_next = 32 + lane < tc.count ? __ldg(&src[tc.base + 32 + lane]) : 0;
+        int i_next = 32 + lane < tc.count ? fetch_i(tq.src, src, tc.base + 32 + lane) : 0;
         int n_leave = 0;
         if (COUNT) {
 #pragma unroll
@@ -798,10 +800,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             const float idw = id_next;
             i_cur = i_next;
             if (it + 32 + lane < tc.count) {   // prefetch the next window
-                p_next = __ldg(&q.P[i_next]);
-                id_next = __ldg(&q.V[i_next].w);
+                p_next = fetch_f4(tq.P, q.P, i_next);
+                id_next = tq.V ? tex1Dfetch<float4>(tq.V, i_next).w : __ldg(&q.V[i_next].w);
             }
-            if (it + 64 + lane < tc.count) i_next = __ldg(&src[d + 64]);
+            if (it + 64 + lane < tc.count) i_next = fetch_i(tq.src, src, d + 64);
             float pos[3] = {p.x, p.y, p.z};
             const bool advance = active && classify_pos<3>(g, pos) == CLS_ACTIVE;   // g2p walks a_rect blocks only
             if (advance) {

@@ -34,6 +34,23 @@ struct Particles {
     float*  CC;   // C[8]      (3D only)
 };
 
+// The same streams (and src[]) as linear TEXTURES.  The tile kernels gather particle records through src[]: 32
+// lanes hit ~17 different 128-byte lines per 128-bit load, and every line is a wavefront of the LSU pipe — the
+// pipe that binds those kernels (20 % of k_p2g_tiled's LSU wavefronts were these gathers).  A texture fetch takes
+// the TEX pipe instead, which the kernels leave idle.  All zero = not available (the kernels use __ldg then).
+struct ParticleTex {
+    cudaTextureObject_t P, V, CA, CB, CC, src;
+};
+__device__ __forceinline__ float4 fetch_f4(cudaTextureObject_t t, const float4* __restrict__ p, int i) {
+    return t ? tex1Dfetch<float4>(t, i) : __ldg(&p[i]);
+}
+__device__ __forceinline__ float fetch_f(cudaTextureObject_t t, const float* __restrict__ p, int i) {
+    return t ? tex1Dfetch<float>(t, i) : __ldg(&p[i]);
+}
+__device__ __forceinline__ int fetch_i(cudaTextureObject_t t, const int* __restrict__ p, int i) {
+    return t ? tex1Dfetch<int>(t, i) : __ldg(&p[i]);
+}
+
 // Everything the counting kernels write.
 struct SortTables {
     int* gcell;        // per particle: bucket
