@@ -142,6 +142,20 @@ __device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileC
               tc.c0[2] + T3::Z + 1 > g.size[2];
 }
 
+// Every cell of the tile lies in an a_rect block: then every particle the sort put into the tile is advanced by g2p
+// (3d:263) and the per-particle block-key classification can be skipped (the tile's cells are the particles' cells).
+__device__ __forceinline__ bool tile_all_active(const Geo& g, const TileCtx& tc) {
+    bool ok = true;
+    const int ext[3] = {T3::X, T3::Y, T3::Z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const int k0 = block_key_of_cell(tc.c0[a] + g.org[a], g.res_i, g.res_shift);
+        const int k1 = block_key_of_cell(tc.c0[a] + ext[a] - 1 + g.org[a], g.res_i, g.res_shift);
+        ok = ok && k0 >= g.a_lo[a] && k1 < g.a_hi[a];
+    }
+    return ok;
+}
+
 // window w of the tile: first slot (relative to tc.base) and length
 __device__ __forceinline__ void window_range(const TileCtx& tc, int w, int& off, int& len) {
     off = w * tc.per + min(w, tc.extra);
@@ -726,6 +740,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         // q = state before this substep (storage order, read through src);
         // qn = state after it, written at the sorted slot.  g2p has no write conflicts, so it walks
         // the tile's slots 32 at a time regardless of the window structure.
+        const bool all_active = tile_all_active(g, tc);
         int i_cur = lane < tc.count ? fetch_i(tq.src, src, tc.base + lane) : 0;
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
         float id_next = 0.0f;            // the particle id travels in V.w: fetched with the position, a window ahead
@@ -775,19 +790,17 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
+        // update_grid in place (3d:253-256): a linear sweep over the tile's 624 slots — no footprint index arithmetic;
+        // the four pad slots behind each plane are never gathered, whatever they hold
 #pragma unroll 4
-        for (int it = 0; it < FOOT_STEPS; ++it) {
-            int gi;
-            const int sl = foot_step(g, tc, fl, it, gi);
-            if (fl.rsub < 3) {
-                float4 nd = vt[sl];
-                if (nd.w > 0.0f) {   // update_grid (3d:253-256); one IEEE reciprocal, three multiplies
-                    const float inv = __frcp_rn(nd.w);
-                    nd.x = nd.x * inv + g.dtg[0];
-                    nd.y = nd.y * inv + g.dtg[1];
-                    nd.z = nd.z * inv + g.dtg[2];
-                    vt[sl] = nd;
-                }
+        for (int k = lane; k < T3::SLOTS; k += 32) {
+            float4 nd = vt[k];
+            if (nd.w > 0.0f) {   // one reciprocal (MUFU.RCP, 1 ulp), three multiplies
+                const float inv = __fdividef(1.0f, nd.w);
+                nd.x = nd.x * inv + g.dtg[0];
+                nd.y = nd.y * inv + g.dtg[1];
+                nd.z = nd.z * inv + g.dtg[2];
+                vt[k] = nd;
             }
         }
         __syncwarp();
@@ -805,7 +818,8 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             }
             if (it + 64 + lane < tc.count) i_next = fetch_i(tq.src, src, d + 64);
             float pos[3] = {p.x, p.y, p.z};
-            const bool advance = active && classify_pos<3>(g, pos) == CLS_ACTIVE;   // g2p walks a_rect blocks only
+            // g2p walks a_rect blocks only (3d:263); warp-uniform short cut for tiles that lie inside a_rect
+            const bool advance = active && (all_active || classify_pos<3>(g, pos) == CLS_ACTIVE);
             if (advance) {
                 TStencil s;
                 tile_stencil(g, tc, p.x, p.y, p.z, s);
@@ -866,7 +880,20 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             if (COUNT) {
                 // bucket of the (possibly moved) particle; frozen halo particles keep theirs
                 int cls = -1, bucket = 0;
-                if (active) bucket = bucket_of<3>(g, make_float4(pos[0], pos[1], pos[2], 0.f), cls);
+                if (active) {
+                    // most particles stay inside their tile: inside an a_rect tile the new bucket is just the cell's
+                    // place in the tile (no block keys, no rect tests); everything else takes the general rule
+                    const int lx = rust_as_i32(floorf(pos[0])) - g.org[0] - tc.c0[0];
+                    const int ly = rust_as_i32(floorf(pos[1])) - g.org[1] - tc.c0[1];
+                    const int lz = rust_as_i32(floorf(pos[2])) - g.org[2] - tc.c0[2];
+                    if (all_active && static_cast<unsigned>(lx) < static_cast<unsigned>(T3::X) &&
+                        static_cast<unsigned>(ly) < static_cast<unsigned>(T3::Y) && static_cast<unsigned>(lz) < static_cast<unsigned>(T3::Z)) {
+                        bucket = (tc.tile << 8) + local_cell_3d(lx, ly, lz);
+                        cls = CLS_ACTIVE;
+                    } else {
+                        bucket = bucket_of<3>(g, make_float4(pos[0], pos[1], pos[2], 0.f), cls);
+                    }
+                }
                 const bool stays = active && (bucket >> 8) == tc.tile;
                 const bool leaves = active && !stays;
                 if (active) st.gcell[d] = bucket;

@@ -112,6 +112,20 @@ def test_small_div_is_exact():
             assert small_div(v, w) == v // w
 
 
+def test_small_div_tolerates_an_approximate_reciprocal():
+    """k_build_src takes 1/W from MUFU.RCP (1 ulp off at most): the floor stays exact with a reciprocal that is
+    off by up to 2 ulp either way, for every W <= 32 and every x < 8192."""
+    for w in range(1, 33):
+        inv = np.float32(1.0) / np.float32(w)
+        for d in (-2, -1, 1, 2):
+            iv = inv
+            for _ in range(abs(d)):
+                iv = np.nextafter(iv, np.float32(np.inf if d > 0 else -np.inf))
+            x = np.arange(8192, dtype=np.float32)
+            got = np.trunc((x + np.float32(0.5)) * iv).astype(np.int64)
+            assert np.array_equal(got, np.arange(8192) // w), (w, d)
+
+
 @pytest.mark.parametrize("kind", ["poisson1", "sparse", "one_column", "one_class", "dense"])
 def test_closed_form_matches_definition(kind):
     rng = np.random.default_rng(hash(kind) % 1000)
