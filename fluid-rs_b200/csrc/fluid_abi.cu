@@ -479,7 +479,7 @@ fluid_status sort_finish(fluid_sim* s) {
     }
     s->launches += 4;
     if (n > 0) {
-        k_build_src<<<blocks_for(n, 256), 256, 0, s->stream>>>(n, s->gcell, s->rank, s->cell_off, s->tile_base, s->tile_info, s->tab, s->src);
+        k_build_src<<<blocks_for(n, 256 * BUILD_SRC_PER_THREAD), 256, 0, s->stream>>>(n, s->gcell, s->rank, s->cell_off, s->tile_base, s->tile_info, s->tab, s->src);
         ++s->launches;
     }
     CU_TRY(cudaGetLastError());

@@ -156,6 +156,22 @@ __device__ __forceinline__ bool tile_all_active(const Geo& g, const TileCtx& tc)
     return ok;
 }
 
+// 1 / x as one MUFU.RCP (1 ulp); x > 0 and far from the denormal range here (node masses)
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// floor(pos) is one of the tile's cells
+__device__ __forceinline__ bool in_tile(const Geo& g, const TileCtx& tc, const float* pos) {
+    const int lx = rust_as_i32(floorf(pos[0])) - g.org[0] - tc.c0[0];
+    const int ly = rust_as_i32(floorf(pos[1])) - g.org[1] - tc.c0[1];
+    const int lz = rust_as_i32(floorf(pos[2])) - g.org[2] - tc.c0[2];
+    return static_cast<unsigned>(lx) < static_cast<unsigned>(T3::X) && static_cast<unsigned>(ly) < static_cast<unsigned>(T3::Y) &&
+           static_cast<unsigned>(lz) < static_cast<unsigned>(T3::Z);
+}
+
 // window w of the tile: first slot (relative to tc.base) and length
 __device__ __forceinline__ void window_range(const TileCtx& tc, int w, int& off, int& len) {
     off = w * tc.per + min(w, tc.extra);
@@ -796,7 +812,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         for (int k = lane; k < T3::SLOTS; k += 32) {
             float4 nd = vt[k];
             if (nd.w > 0.0f) {   // one reciprocal (MUFU.RCP, 1 ulp), three multiplies
-                const float inv = __fdividef(1.0f, nd.w);
+                const float inv = rcp_approx(nd.w);
                 nd.x = nd.x * inv + g.dtg[0];
                 nd.y = nd.y * inv + g.dtg[1];
                 nd.z = nd.z * inv + g.dtg[2];
@@ -864,7 +880,8 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
                     B[6 + r] = Dz[r] - S[r] * s.cz;
                 }
                 integrate_particle<3>(g, pos, vel, mouse);
-                if (left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
+                // a particle that is still in a cell of this (a_rect) tile cannot have left p_rect (3d:356-366)
+                if (!(all_active && in_tile(g, tc, pos)) && left_p_rect<3>(g, pos)) pos[0] = __int_as_float(0x7f800000);   // dropped: tombstone
                 qn.P[d] = make_float4(pos[0], pos[1], pos[2], p.w);
                 qn.V[d] = make_float4(vel[0], vel[1], vel[2], idw);
                 qn.CA[d] = make_float4(4.0f * B[0], 4.0f * B[1], 4.0f * B[2], 4.0f * B[3]);

@@ -483,53 +483,69 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
 // position in the tile's class-major cell order; window w = q mod W; inside the window the classes are
 // merged round robin (ORDER_CLASS_RR above): with k = my index among my class's members of the window,
 //     pos = sum_b min(n_b, k) + #{b < my class : n_b > k},   n_b = tab[w][b].
-__global__ void __launch_bounds__(256)
-k_build_src(int n, const int* __restrict__ gcell, const int* __restrict__ rank,
-            const int* __restrict__ cell_off, const int* __restrict__ tile_base,
-            const int2* __restrict__ tile_info, const unsigned char* __restrict__ tab, int* __restrict__ src) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const int bucket = gcell[i];
+// Slot of one particle from its bucket, cellStart[bucket] + rank and its tile's {W, list entry} (formulas above).
+__device__ __forceinline__ int build_src_slot(int bucket, int q_abs, int2 info, const int* __restrict__ cell_off,
+                                              const int* __restrict__ tile_base, const unsigned char* __restrict__ tab) {
+    if (info.x == 0) return q_abs;   // plain cell order (pseudo tiles, 2D particle-per-thread path)
     const int t = bucket >> 8;
-    const int q_abs = cell_off[bucket] + rank[i];
-    const int2 info = __ldg(&tile_info[t]);
-    if (info.x == 0) {   // plain cell order (2D, pseudo tiles)
-        src[q_abs] = i;
-        return;
-    }
     const int base = __ldg(&tile_base[t]);
     const int n_t = __ldg(&tile_base[t + 1]) - base;
     const int q = q_abs - base;
-    int slot;
     if (info.x < 0) {    // too many windows for the merge table: round robin only
         const int w_count = -info.x;
         const int per = n_t / w_count, extra = n_t - per * w_count;
         const int pos = q / w_count, w = q - pos * w_count;
-        slot = base + w * per + min(w, extra) + pos;
-    } else {
-        const int w_count = info.x;
-        // (MUFU.RCP: 1 ulp off at most, far inside small_div's margin of 0.5/32 on a quotient below 8192)
-        const float inv_w = __fdividef(1.0f, static_cast<float>(w_count));
-        const int per = small_div(n_t, inv_w), extra = n_t - per * w_count;
-        const int w = q - small_div(q, inv_w) * w_count;
-        const int cls = (bucket & (TILE_CELLS - 1)) >> 5;
-        const int s_cls = __ldg(&cell_off[(t << 8) + (cls << 5)]) - base;
-        const int s_mod = s_cls - small_div(s_cls, inv_w) * w_count;
-        int off = w - s_mod;
-        if (off < 0) off += w_count;
-        const int k = small_div(q - (s_cls + off), inv_w);   // my index among my class in window w
-        const uint2 row = __ldg(reinterpret_cast<const uint2*>(tab + static_cast<size_t>(info.y) * TAB_BYTES + w * 8));
-        const unsigned kk = static_cast<unsigned>(min(k, 255)) * 0x01010101u;
-        // sum_b min(n_b, k): per-byte minimum, then the byte sum
-        int pos = __vsadu4(__vminu4(row.x, kk), 0u) + __vsadu4(__vminu4(row.y, kk), 0u);
-        // #{b < cls : n_b > k}
-        const unsigned gx = __vcmpgtu4(row.x, kk), gy = __vcmpgtu4(row.y, kk);   // 0xff per byte where n_b > k
-        const unsigned long long gt = (static_cast<unsigned long long>(gy) << 32) | gx;
-        const unsigned long long below = cls == 0 ? 0ull : (~0ull >> (64 - 8 * cls));
-        pos += __popcll(gt & below) >> 3;
-        slot = base + w * per + min(w, extra) + pos;
+        return base + w * per + min(w, extra) + pos;
     }
-    src[slot] = i;
+    const int w_count = info.x;
+    // (MUFU.RCP: 1 ulp off at most, far inside small_div's margin of 0.5/32 on a quotient below 8192)
+    const float inv_w = __fdividef(1.0f, static_cast<float>(w_count));
+    const int per = small_div(n_t, inv_w), extra = n_t - per * w_count;
+    const int w = q - small_div(q, inv_w) * w_count;
+    const int cls = (bucket & (TILE_CELLS - 1)) >> 5;
+    const int s_cls = __ldg(&cell_off[(t << 8) + (cls << 5)]) - base;
+    const int s_mod = s_cls - small_div(s_cls, inv_w) * w_count;
+    int off = w - s_mod;
+    if (off < 0) off += w_count;
+    const int k = small_div(q - (s_cls + off), inv_w);   // my index among my class in window w
+    const uint2 row = __ldg(reinterpret_cast<const uint2*>(tab + static_cast<size_t>(info.y) * TAB_BYTES + w * 8));
+    const unsigned kk = static_cast<unsigned>(min(k, 255)) * 0x01010101u;
+    // sum_b min(n_b, k): per-byte minimum, then the byte sum
+    int pos = __vsadu4(__vminu4(row.x, kk), 0u) + __vsadu4(__vminu4(row.y, kk), 0u);
+    // #{b < cls : n_b > k}
+    const unsigned gx = __vcmpgtu4(row.x, kk), gy = __vcmpgtu4(row.y, kk);   // 0xff per byte where n_b > k
+    const unsigned long long gt = (static_cast<unsigned long long>(gy) << 32) | gx;
+    const unsigned long long below = cls == 0 ? 0ull : (~0ull >> (64 - 8 * cls));
+    pos += __popcll(gt & below) >> 3;
+    return base + w * per + min(w, extra) + pos;
+}
+
+// BUILD_SRC_PER_THREAD particles per thread: the kernel is a chain of dependent table look-ups (bucket -> cellStart ->
+// tile entry -> class start -> window row), so independent chains in one thread are what hides their latency.
+constexpr int BUILD_SRC_PER_THREAD = 4;
+__global__ void __launch_bounds__(256)
+k_build_src(int n, const int* __restrict__ gcell, const int* __restrict__ rank,
+            const int* __restrict__ cell_off, const int* __restrict__ tile_base,
+            const int2* __restrict__ tile_info, const unsigned char* __restrict__ tab, int* __restrict__ src) {
+    const int i0 = blockIdx.x * (256 * BUILD_SRC_PER_THREAD) + threadIdx.x;
+    int bucket[BUILD_SRC_PER_THREAD], q_abs[BUILD_SRC_PER_THREAD];
+    int2 info[BUILD_SRC_PER_THREAD];
+#pragma unroll
+    for (int k = 0; k < BUILD_SRC_PER_THREAD; ++k) {
+        const int i = i0 + 256 * k;
+        bucket[k] = i < n ? gcell[i] : 0;
+        q_abs[k] = i < n ? rank[i] : 0;
+    }
+#pragma unroll
+    for (int k = 0; k < BUILD_SRC_PER_THREAD; ++k) {
+        q_abs[k] += __ldg(&cell_off[bucket[k]]);            // (bucket 0 for the lanes behind the end: a valid address)
+        info[k] = __ldg(&tile_info[bucket[k] >> 8]);
+    }
+#pragma unroll
+    for (int k = 0; k < BUILD_SRC_PER_THREAD; ++k) {
+        const int i = i0 + 256 * k;
+        if (i < n) src[build_src_slot(bucket[k], q_abs[k], info[k], cell_off, tile_base, tab)] = i;
+    }
 }
 
 // Physical gather (only used to compact dropped particles away and for the steady-state tail).
