@@ -27,6 +27,8 @@ def main():
         print(f"after {k} steps: tiles {len(t)} particles {n.sum()} mean N {n.mean():.1f} "
               f"fill {n.sum() / (32.0 * w.sum()):.3f} fill_if_no_column_rule {n.sum() / (32.0 * need.sum()):.3f} "
               f"mean W {w.mean():.2f} mean ceil(N/32) {need.mean():.2f} W>need in {np.mean(w > need):.3f}", flush=True)
+        hist = [(lim, float(np.mean(n < lim)), float(n[n < lim].sum() / n.sum())) for lim in (16, 32, 64, 128, 192)]
+        print("    tiles / particles below N: " + "  ".join(f"<{lim}: {a:.3f}/{b:.3f}" for lim, a, b in hist), flush=True)
         if k < steps:
             sim.step()
     sim.close()
