@@ -42,6 +42,9 @@ extern "C" {
     fn fluid_step(sim: *mut FluidSim, mouse_xy: *const f32) -> c_int; // step, 3d:110
     fn fluid_particle_count(sim: *mut FluidSim, n: *mut i64) -> c_int;
     fn fluid_slot_count(sim: *const FluidSim, n: *mut i64) -> c_int;
+    fn fluid_set_deterministic(sim: *mut FluidSim, on: i32) -> c_int; // fixed-order node sums (grid_search, 3d:403-408)
+    fn fluid_set_sparse(sim: *mut FluidSim, max_blocks: i64) -> c_int; // block-sparse node storage (3d:52-55, 89-96)
+    fn fluid_memory_stats(sim: *mut FluidSim, out: *mut i64) -> c_int;
     fn fluid_read_particles(sim: *mut FluidSim, rec: *mut f32, ids: *mut i32, cap: i64, n: *mut i64) -> c_int; // iter_particle, 3d:383
     fn fluid_get_phase_times(sim: *mut FluidSim, sec: *mut f64, sort: *mut f64) -> c_int; // debug_elapseds, 3d:502
     fn fluid_render_frame(sim: *mut FluidSim, viewport_xy: *const f32, cols: i32, rows: i32, counts: *mut i32) -> c_int; // draw's binning, 3d:469-486
@@ -176,6 +179,20 @@ pub mod d3 {
         }
         pub fn frame(&mut self, viewport: Vec2, cols: i32, rows: i32) -> String {
             self.inner.frame(viewport.to_array(), cols, rows)
+        }
+        /// Bit-reproducible node sums (64-bit fixed point), from run to run and across GPU counts.
+        pub fn set_deterministic(&mut self, on: bool) {
+            check(unsafe { fluid_set_deterministic(self.inner.h, on as i32) });
+        }
+        /// Block-sparse node storage with a pool of `max_blocks` 8x8x4 blocks (call before `set_rect`).
+        pub fn set_sparse(&mut self, max_blocks: i64) {
+            check(unsafe { fluid_set_sparse(self.inner.h, max_blocks) });
+        }
+        /// [bytes allocated, dense equivalent, pool blocks, blocks in use, dense nodes, pool ever exhausted]
+        pub fn memory_stats(&mut self) -> [i64; 6] {
+            let mut o = [0i64; 6];
+            check(unsafe { fluid_memory_stats(self.inner.h, o.as_mut_ptr()) });
+            o
         }
     }
 }

@@ -1481,6 +1481,20 @@ fluid_status fluid_clear_particles(fluid_sim* s) {
     s->next_id = 0;
     s->dropped_total = 0;
     s->sorted_valid = s->counts_pending = false;
+    if (s->pool_blocks && s->rect_set) {
+        // block-sparse: no particle, no block.  Otherwise the blocks of the old positions would stay allocated until
+        // the next clear releases them, and re-seeding a scene would need a pool of old + new blocks for a moment.
+        CU_TRY(cudaSetDevice(s->device));
+        const int64_t m_init = std::max<int64_t>(s->geo.n_tiles, s->pool_blocks);
+        k_pool_init<<<blocks_for(m_init, 256), 256, 0, s->stream>>>(s->geo.sp, s->geo.n_tiles, static_cast<int>(s->pool_blocks));
+        ++s->launches;
+        CU_TRY(cudaMemsetAsync(s->grid, 0, s->node_alloc * sizeof(float4), s->stream));
+        CU_TRY(cudaMemsetAsync(s->gmass, 0, s->node_alloc * sizeof(float), s->stream));
+        CU_TRY(cudaMemsetAsync(s->dirty[0], 0, s->geo.n_tiles, s->stream));
+        CU_TRY(cudaMemsetAsync(s->dirty[1], 0, s->geo.n_tiles, s->stream));
+        CU_TRY(cudaGetLastError());
+        s->grid_clean = true;
+    }
     return FLUID_OK;
 }
 

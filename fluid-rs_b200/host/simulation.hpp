@@ -82,6 +82,16 @@ class Simulation {
     }
     float dt() const { return config.dt; }   // sim.config.dt (3d:541)
 
+    // beyond the reference's six: bit-reproducible node sums (the reference fixes every sum's order, 3d:403-408),
+    // block-sparse node storage (its hash map of blocks, 3d:52-55), and what that storage takes
+    void set_deterministic(bool on) { check(fluid_set_deterministic(h_, on ? 1 : 0)); }
+    void set_sparse(int64_t max_blocks) { check(fluid_set_sparse(h_, max_blocks)); }   // before set_rect
+    std::array<int64_t, 6> memory_stats() {
+        std::array<int64_t, 6> o{};
+        check(fluid_memory_stats(h_, o.data()));
+        return o;
+    }
+
     fluid_config config;
     std::vector<std::pair<std::string, double>> debug_elapseds;   // (label, seconds), 3d:60,112-132
 

@@ -388,6 +388,14 @@ def test_block_sparse_domain_8x_the_fluid(pkg, orc, scenes):
             assert max(used) < 1024 and not stats["pool_exhausted"]
         r, i = sim.read_particles(sort_by_id=True)
         outs.append(r)
+        if blocks:                                   # no particle, no block: re-seeding needs no second pool
+            sim.clear_particles()
+            assert sim.memory_stats()["blocks_in_use"] == 0
+            sim.add_particles(rec)
+            sim.substeps(3)
+            again = sim.memory_stats()
+            assert 0 < again["blocks_in_use"] <= used[0] and not again["pool_exhausted"]
+            assert sim.particle_counts()["active"] == sc.n
         sim.close()
     assert stats["pool_blocks"] == 1024 and stats["node_bytes"] == 1024 * 256 * 20
     assert stats["dense_node_bytes"] > 25 * stats["node_bytes"]
