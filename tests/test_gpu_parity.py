@@ -90,7 +90,9 @@ def check_one_substep(pkg, orc, scene, rec, mouse=None, deterministic=False, spa
     assert scaled_err(gg[:, -1], rg[:, -1], ms) < TOL
     live = rg[:, -1] > 1e-4 * ms      # node velocity = mom/mass is ill-conditioned where mass ~ 0
     gs = max(float(np.abs(rg[live, :d]).max()), 1e-3)
-    assert scaled_err(gg[live, :d], rg[live, :d], gs) < 5 * TOL
+    # float reductions: 5 x TOL (the sums run in another order than the oracle's); the deterministic mode's
+    # fixed-point sums are exact to 3e-11 per deposit, so there the plain bound holds
+    assert scaled_err(gg[live, :d], rg[live, :d], gs) < (TOL if deterministic else 5 * TOL)
     sim.close()
     ref.close()
 

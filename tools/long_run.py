@@ -1,7 +1,9 @@
 """Long single-GPU run of the bench scene with aggregate checks (GPU box only):
-particle count constant, every position finite and inside the clip box, kinetic energy bounded.
+particle count constant, every position finite and inside the clip box, kinetic energy bounded; and the
+throughput of every step against simulated time (the rate falls as the dam spreads over more, emptier tiles).
 usage: python tools/long_run.py [16M|1M] [steps]"""
 import sys
+import time
 from pathlib import Path
 import numpy as np
 ROOT = Path(__file__).resolve().parent.parent
@@ -21,8 +23,17 @@ def main():
     for s in range(0, sc.n, chunk):
         sim.add_particles(sc.records(s, min(chunk, sc.n - s)))
     lo, hi = np.asarray(sc.cfg["clip_min"][:3]), np.asarray(sc.cfg["clip_max"][:3])
+    iters = sc.cfg["iterations"]
     for k in range(steps):
+        sim.synchronize()
+        t0 = time.perf_counter()
         sim.step()
+        sim.synchronize()
+        dt = time.perf_counter() - t0
+        tiles = sim.debug_tiles()
+        tiles = tiles[tiles[:, 2] > 0]
+        print(f"step {k + 1}: {sc.n * iters / dt / 1e9:.3f} G updates/s  ({dt * 1e3 / iters:.3f} ms per substep)  "
+              f"active tiles {len(tiles)}  particles per tile {tiles[:, 2].mean():.1f}", flush=True)
         if (k + 1) % 10 == 0 or k + 1 == steps:
             c = sim.particle_counts()
             rec, ids = sim.read_particles()
