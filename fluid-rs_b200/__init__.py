@@ -99,6 +99,7 @@ SIGNATURES = {
     "fluid_render_frame": (C.c_int, [C.c_void_p, _fp, C.c_int32, C.c_int32, _ip]),
     "fluid_frame_char": (C.c_char, [C.c_int32]),
     "fluid_debug_tiles": (C.c_int, [C.c_void_p, C.c_int64, _ip, _i64p]),
+    "fluid_debug_windows": (C.c_int, [C.c_void_p, C.c_int64, _ip, _i64p]),
     "fluid_read_grid": (C.c_int, [C.c_void_p, _fp, C.c_int64, _i64p]),
     "fluid_launch_count": (C.c_int, [C.c_void_p, _i64p]),
     "fluid_slab_set": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32]),
@@ -411,6 +412,14 @@ class Simulation:
         out = np.empty((max(n.value, 1), 4), dtype=np.int32)
         _check(lib().fluid_debug_tiles(self._h, n.value, out.ctypes.data_as(_ip), C.byref(n)))
         return out[: n.value]
+
+    def debug_windows(self):
+        """Per sorted slot: window * 32 + lane of the tile kernels' walk (after neighbour_table())."""
+        cap = self.slot_count()    # (no count query here: that would re-run the neighbour search)
+        out = np.empty(max(cap, 1), dtype=np.int32)
+        w = C.c_int64()
+        _check(lib().fluid_debug_windows(self._h, cap, out.ctypes.data_as(_ip), C.byref(w)))
+        return out[: w.value]
 
     def neighbour_table(self):
         c = self.particle_counts()

@@ -120,7 +120,8 @@ struct fluid_sim {
     bool grid_clean = false;     // every node outside the dirty blocks is zero
     bool sorted_valid = false;   // arrays are in tile order for the current positions
     bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
-    int tile_order = ORDER_CLASS_RR;
+    int tile_order = ORDER_CLASS_RR;  // window order of the 3D tiled path (FLUID_B200_ORDER=q: ORDER_CLASS_Q, sort.cuh)
+    int dyn_tiles = 6;                // tile kernels that take their tiles from a ticket counter: 1 k_mass_tiled, 2 k_p2g_tiled, 4 k_g2p_tiled (FLUID_B200_DYN=mask; 0: fixed stride)
     int sm_count = 148;
     unsigned grid_mass = 0, grid_p2g = 0, grid_g2p = 0;   // persistent grids: SMs x resident CTAs
     unsigned grid2_mass = 0, grid2_p2g = 0, grid2_g2p = 0;   // ... of the 2D tile kernels
@@ -461,7 +462,7 @@ fluid_status sort_finish(fluid_sim* s) {
     const int n = static_cast<int>(s->n);
     const int m = s->geo.n_tiles + N_PSEUDO;
     const unsigned nb = static_cast<unsigned>(s->n_scan_blocks);
-    CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
+    CU_TRY(cudaMemsetAsync(s->scal, 0, SCAL_COUNT * sizeof(int), s->stream));
     k_scan_partial<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums);
     k_scan_sums<<<1, 1024, 0, s->stream>>>(s->block_sums, static_cast<int>(nb));
     k_scan_final<<<nb, SCAN_THREADS, 0, s->stream>>>(s->tile_total, m, s->block_sums, s->tile_base, s->cand,
@@ -471,8 +472,12 @@ fluid_status sort_finish(fluid_sim* s) {
                                            static_cast<unsigned>(s->sm_count * 16));
     if (DIM == 3 || s->tiled) {   // (2D tiles are 8 x 8 columns of depth 1: the same order and tables)
         s->dirty_cur ^= 1;   // the buffer k_clear_tiles emptied last substep
-        k_tile_tables<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
-                                                                            s->tiles, s->scal, s->dirty[s->dirty_cur], s->cand, s->peer);
+        if (DIM == 3 && s->tile_order == ORDER_CLASS_Q)
+            k_tile_tables<ORDER_CLASS_Q><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
+                                                                               s->tiles, s->scal, s->dirty[s->dirty_cur], s->cand, s->peer);
+        else
+            k_tile_tables<ORDER_CLASS_RR><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
+                                                                                s->tiles, s->scal, s->dirty[s->dirty_cur], s->cand, s->peer);
     } else {
         k_tile_tables<ORDER_CELL><<<pb, PERM_WARPS * 32, 0, s->stream>>>(s->geo, s->count, s->tile_base, s->cell_off, s->tile_info, s->tab,
                                                                         s->tiles, s->scal, nullptr, s->cand, PeerHalo{});
@@ -671,10 +676,10 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                                                                                           s->grid);
             else if (s->p2p)
                 k_mass_tiled<true><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                            s->gmass, s->grid, s->peer, s->tex[s->cur]);
+                                                                                            s->gmass, s->grid, s->peer, s->tex[s->cur], s->tab, (s->dyn_tiles & 1) ? s->scal + SCAL_TICKET : nullptr);
             else
                 k_mass_tiled<false><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                             s->gmass, s->grid, s->peer, s->tex[s->cur]);
+                                                                                             s->gmass, s->grid, s->peer, s->tex[s->cur], s->tab, (s->dyn_tiles & 1) ? s->scal + SCAL_TICKET : nullptr);
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
@@ -708,7 +713,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
 #define P2G_LAUNCH(PEER, TMA)                                                                                       \
     k_p2g_tiled<PEER, TMA><<<gp, T3::THREADS, sizeof(P2GSmem), s->stream>>>(s->geo, q, s->src, s->tiles, n_act, s->gmass, \
                                                                            s->grid, dd, dp, s->peer, s->tm_grid, s->tm_mass,     \
-                                                                           s->tma_mass ? 1 : 0, s->tex[s->cur])
+                                                                           s->tma_mass ? 1 : 0, s->tex[s->cur], s->tab, (s->dyn_tiles & 2) ? s->scal + SCAL_TICKET + 1 : nullptr)
             if (s->p2p && s->tma) P2G_LAUNCH(true, true);
             else if (s->p2p) P2G_LAUNCH(true, false);
             else if (s->tma) P2G_LAUNCH(false, true);
@@ -744,14 +749,15 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
             if (DIM == 2)
                 k_g2p_tiled2<<<std::min(tb2, s->grid2_g2p), T2::THREADS, 0, s->stream>>>(s->geo, q, qn, s->src, s->tiles, n_act, s->grid,
                                                                                         d_mouse, sort_tables(s), s->gmass, s->gz, s->d_epoch);
-            else if (s->tma)
-                k_g2p_tiled<true, true><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid,
-                    s->tex[s->cur]);
-            else
-                k_g2p_tiled<true, false><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(
-                    s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid,
-                    s->tex[s->cur]);
+            else {
+#define G2P_LAUNCH(TMA)                                                                                                       \
+    k_g2p_tiled<true, TMA><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(                                          \
+        s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid, \
+        s->tex[s->cur], (s->dyn_tiles & 4) ? s->scal + SCAL_TICKET + 2 : nullptr)
+                if (s->tma) G2P_LAUNCH(true);
+                else G2P_LAUNCH(false);
+#undef G2P_LAUNCH
+            }
             // ignored (and, outside slab runs, dropped) particles sit behind the tiles: carried over
             // and counted here; a slab run ends dropped / migrated particles at this point
             const int* n_end = s->geo.slab_on ? s->tile_base + s->geo.n_tiles + 1 : nullptr;
@@ -1058,8 +1064,8 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     if (ce == cudaSuccess) ce = cudaMemset(s->d_epoch, 0, sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->class_count, 4 * sizeof(int));
     if (ce == cudaSuccess) ce = cudaMalloc(&s->d_counter, sizeof(int));
-    if (ce == cudaSuccess) ce = cudaMalloc(&s->scal, 8 * sizeof(int));
-    if (ce == cudaSuccess) ce = cudaMemset(s->scal, 0, 8 * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMalloc(&s->scal, SCAL_COUNT * sizeof(int));
+    if (ce == cudaSuccess) ce = cudaMemset(s->scal, 0, SCAL_COUNT * sizeof(int));
     for (int i = 0; i < N_EVENTS && ce == cudaSuccess; ++i) ce = cudaEventCreate(&s->ev[i]);
     if (ce != cudaSuccess) {
         fluid_destroy(s);
@@ -1070,6 +1076,8 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     s->tiled = !(force_generic && force_generic[0] == '1');
     if (const char* e = std::getenv("FLUID_B200_GRAPH")) s->graphs_on = e[0] != '0';
     if (const char* e = std::getenv("FLUID_B200_TEX")) s->tex_on = e[0] != '0';
+    if (const char* e = std::getenv("FLUID_B200_ORDER")) s->tile_order = (e[0] == 'q') ? ORDER_CLASS_Q : ORDER_CLASS_RR;
+    if (const char* e = std::getenv("FLUID_B200_DYN")) s->dyn_tiles = std::atoi(e) & 7;
     if (const char* e = std::getenv("FLUID_B200_SPARSE_BLOCKS")) {
         if (cfg->dim == 3) s->sparse_blocks = std::max<long long>(std::atoll(e), 0);
     }
@@ -1814,6 +1822,32 @@ fluid_status fluid_debug_tiles(fluid_sim* s, int64_t capacity_tiles, int32_t* ti
     if (!tiles4) return FLUID_OK;
     if (h > capacity_tiles) return fail(FLUID_ERR_TOO_SMALL, "fluid_debug_tiles: capacity too small");
     if (h > 0) CU_TRY(cudaMemcpy(tiles4, s->tiles, static_cast<size_t>(h) * sizeof(int4), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < h; ++k) tiles4[4 * k + 3] &= ORDER_Q_FLAG - 1;   // W without the order flag
+    return FLUID_OK;
+}
+
+fluid_status fluid_debug_windows(fluid_sim* s, int64_t capacity, int32_t* window_lane, int64_t* n_written) {
+    if (!s || capacity < 0 || !window_lane || !n_written) return fail(FLUID_ERR_INVALID_ARG, "fluid_debug_windows: bad argument");
+    CU_TRY(cudaSetDevice(s->device));
+    *n_written = 0;
+    if (!s->rect_set || !s->sorted_valid || !s->tiled) return FLUID_OK;
+    int h = 0;
+    CU_TRY(cudaMemcpyAsync(&h, s->tile_base + s->geo.n_tiles, sizeof(int), cudaMemcpyDeviceToHost, s->stream));
+    CU_TRY(cudaStreamSynchronize(s->stream));
+    if (h > capacity) return fail(FLUID_ERR_TOO_SMALL, "fluid_debug_windows: capacity too small");
+    if (h == 0) return FLUID_OK;
+    int* d_out = nullptr;
+    CU_TRY(cudaMalloc(&d_out, static_cast<size_t>(h) * sizeof(int)));
+    cudaError_t ce = cudaMemsetAsync(d_out, 0xff, static_cast<size_t>(h) * sizeof(int), s->stream);   // -1 = no window claimed the slot
+    if (ce == cudaSuccess) {
+        k_debug_windows<<<s->sm_count * 4, 128, 0, s->stream>>>(s->geo, s->tiles, s->scal + SCAL_N_ACTIVE, s->tab, d_out);
+        ++s->launches;
+        ce = cudaMemcpyAsync(window_lane, d_out, static_cast<size_t>(h) * sizeof(int), cudaMemcpyDeviceToHost, s->stream);
+    }
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(s->stream);
+    cudaFree(d_out);
+    if (ce != cudaSuccess) return fail(FLUID_ERR_CUDA, cudaGetErrorString(ce));
+    *n_written = h;
     return FLUID_OK;
 }
 
@@ -1946,7 +1980,7 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
             ST_TRY(ensure_fixed(s, 2));
             CU_TRY(cudaMemsetAsync(s->fx[0], 0, s->node_alloc * 4 * sizeof(long long), s->stream));
             CU_TRY(cudaMemsetAsync(s->fx[1], 0, s->node_alloc * 4 * sizeof(long long), s->stream));
-            CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
+            CU_TRY(cudaMemsetAsync(s->scal, 0, SCAL_COUNT * sizeof(int), s->stream));
         }
         return FLUID_OK;
     }
@@ -1960,7 +1994,7 @@ fluid_status fluid_slab_phase(fluid_sim* s, int32_t phase, const float* mouse_xy
             CU_TRY(cudaMemsetAsync(s->dirty[1], 0, s->geo.n_tiles, s->stream));
             s->grid_clean = true;
         } else if (phase == 0) {
-            CU_TRY(cudaMemsetAsync(s->scal, 0, 8 * sizeof(int), s->stream));
+            CU_TRY(cudaMemsetAsync(s->scal, 0, SCAL_COUNT * sizeof(int), s->stream));
             k_dirty_list<<<blocks_for(s->geo.n_tiles, 256), 256, 0, s->stream>>>(
                 s->geo, s->dirty[s->dirty_cur], s->dirty[s->dirty_cur ^ 1], s->dirty_list, s->scal + SCAL_N_DIRTY, true);
             k_clear_tiles<<<std::min<unsigned>(blocks_for(static_cast<int64_t>(s->geo.n_tiles) * 32, 128),

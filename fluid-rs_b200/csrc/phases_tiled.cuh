@@ -1,13 +1,16 @@
 // phases_tiled.cuh — the 3D hot path: warp-private shared-memory node tiles, sm_100a.
 //
 // One warp owns one tile of 8x8x4 cells (Tile<3>) and the 10x10x6 nodes its particles can touch
-// (3^3 stencil reach, 3d:157-158).  The sort (sort.cuh, ORDER_CLASS_RR) deals the tile's
+// (3^3 stencil reach, 3d:157-158).  The sort (sort.cuh, ORDER_CLASS_RR or ORDER_CLASS_Q) deals the tile's
 // particles into windows of <= 32 in which no two particles share an (x,y) column.  A warp
 // processes one window per iteration, one particle per lane: for a fixed stencil offset (ox,oy)
 // the 32 lanes touch 32 different node columns and the three nodes along z belong to the lane
 // alone, so the read-modify-writes into the shared-memory tile are plain LDS / FFMA / STS — three
-// independent chains in flight per lane, one __syncwarp per (ox,oy) — with no atomics (shared
-// float atomics are a CAS loop on sm_100a, ATOMS.CAST.SPIN) and no conflict passes.
+// independent chains in flight per lane, one warp barrier per (ox,oy) — with no atomics (shared
+// float atomics are a CAS loop on sm_100a, ATOMS.CAST.SPIN) and no conflict passes.  Lanes without a
+// particle skip the window's shared-memory work (a quarter warp none of whose lanes takes part in a
+// 128-bit access costs no wavefront).  The tiles of the active-tile list are handed to the resident warps
+// through a ticket counter (k_p2g_tiled, k_g2p_tiled), so a warp that drew light tiles takes more of them.
 // Tiles move between HBM and shared memory through the tensor memory accelerator where their
 // footprint lies inside the grid: k_p2g_tiled flushes its accumulators with six tensor reductions
 // (cp.reduce.async.bulk.tensor.4d .add, SASS UTMAREDG.4D.ADD), k_g2p_tiled loads its footprint with
@@ -116,20 +119,30 @@ struct TileCtx {
     int count;     // particles in the tile
     int windows;   // W
     int per, extra;
+    bool quart;          // ORDER_CLASS_Q (sort.cuh): a window's rounds sit on quarter-warp boundaries
+    unsigned nlo, nhi;   // ... its class totals N_b, one byte each (classes 0..3 | 4..7)
     bool edge;     // the footprint sticks out of the p_rect grid
     bool low_rim;  // ... at the low end of an axis: its boxes start at coordinate -1 (no TMA reduction there)
 };
 
 // Active tiles, listed by k_tile_tables: {tile id, first slot, count, windows}.  The tile kernels
 // run persistent warps that stride over this list, so empty tiles cost nothing.
-__device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileCtx& tc) {
+__device__ __forceinline__ void tile_from_list(const Geo& g, const int4 e, TileCtx& tc, const unsigned char* __restrict__ tab = nullptr,
+                                               int a = 0) {
     const int t = e.x;
     tc.tile = t;
     tc.base = e.y;
     tc.count = e.z;
-    tc.windows = e.w;
-    tc.per = e.z / e.w;
-    tc.extra = e.z - tc.per * e.w;
+    tc.quart = (e.w & ORDER_Q_FLAG) != 0;
+    tc.windows = e.w & (ORDER_Q_FLAG - 1);
+    tc.per = e.z / tc.windows;
+    tc.extra = e.z - tc.per * tc.windows;
+    tc.nlo = tc.nhi = 0u;
+    if (tc.quart && tab) {   // (the kernels that walk windows pass the table; g2p's compact walk does not need it)
+        const uint2 nb = __ldg(reinterpret_cast<const uint2*>(tab + static_cast<size_t>(a) * TAB_BYTES));
+        tc.nlo = nb.x;
+        tc.nhi = nb.y;
+    }
     int tx = t % g.tdim[0];
     int r = t / g.tdim[0];
     int ty = r % g.tdim[1];
@@ -172,10 +185,71 @@ __device__ __forceinline__ bool in_tile(const Geo& g, const TileCtx& tc, const f
            static_cast<unsigned>(lz) < static_cast<unsigned>(T3::Z);
 }
 
-// window w of the tile: first slot (relative to tc.base) and length
-__device__ __forceinline__ void window_range(const TileCtx& tc, int w, int& off, int& len) {
-    off = w * tc.per + min(w, tc.extra);
-    len = w < tc.windows ? tc.per + (w < tc.extra ? 1 : 0) : 0;
+// The tile kernels run one wave of resident warps over the active-tile list.  With a ticket counter (zeroed by the
+// sort) a warp takes the next tile when it is done with one, so a warp that drew light tiles does more of them;
+// without one the list is dealt out with a fixed stride.
+// The ticket is drawn at the START of a tile and looked at when the tile is done: the atomic's round trip (which
+// queues behind the reductions the warp's previous flush still has in flight) is hidden behind the tile's work.
+__device__ __forceinline__ int tile_ticket(int* __restrict__ ticket, int lane, int a, int stride) {
+    if (!ticket) return a + stride;
+    return lane == 0 ? atomicAdd(ticket, 1) : 0;      // lane 0 holds the value
+}
+__device__ __forceinline__ int tile_of_ticket(int* __restrict__ ticket, int raw) {
+    return ticket ? __shfl_sync(0xffffffffu, raw, 0) : raw;
+}
+
+// A lane's place in window w of its tile: `active` and the slot (relative to the tile's first).  `first` = slots of
+// the windows before w; it is advanced to window w + 1, so the windows have to be visited in order (one call per
+// window, w = 0, 1, ...).
+//   ORDER_CLASS_Q: quarter warp k = round k of the window = the classes with N_b > w + k W, ascending, from lane 8k on
+//   otherwise:     the window is the slot range [w per + min(w, extra), + per + (w < extra)), lane by lane
+struct WinLane {
+    bool active;
+    int slot;
+};
+__device__ __forceinline__ int round_members(const TileCtx& tc, int thr) {   // #{b : N_b > thr}, thr < 128
+    const unsigned t4 = static_cast<unsigned>(thr) * 0x01010101u;
+    return (__popc(__vcmpgtu4(tc.nlo, t4)) + __popc(__vcmpgtu4(tc.nhi, t4))) >> 3;
+}
+__device__ __forceinline__ WinLane window_lane(const TileCtx& tc, int w, int lane, int& first) {
+    WinLane r;
+    r.active = false;
+    r.slot = 0;
+    if (w >= tc.windows) return r;
+    if (tc.quart) {
+        const int m0 = round_members(tc, w), m1 = round_members(tc, w + tc.windows),
+                  m2 = round_members(tc, w + 2 * tc.windows), m3 = round_members(tc, w + 3 * tc.windows);
+        const int k = lane >> 3, j = lane & 7;
+        const int mk = k == 0 ? m0 : (k == 1 ? m1 : (k == 2 ? m2 : m3));
+        const int before = k == 0 ? 0 : (k == 1 ? m0 : (k == 2 ? m0 + m1 : m0 + m1 + m2));
+        r.active = j < mk;
+        r.slot = first + before + j;
+        first += m0 + m1 + m2 + m3;
+    } else {
+        const int len = tc.per + (w < tc.extra ? 1 : 0);
+        r.active = lane < len;
+        r.slot = first + lane;
+        first += len;
+    }
+    return r;
+}
+
+// Parity tap: window * 32 + lane of every sorted slot, from the same window_lane() the tile kernels walk with.
+__global__ void __launch_bounds__(128)
+k_debug_windows(const __grid_constant__ Geo g, const int4* __restrict__ tiles, const int* __restrict__ n_active,
+                const unsigned char* __restrict__ tab, int* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int n_warps = (gridDim.x * blockDim.x) >> 5;
+    for (int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; a < *n_active; a += n_warps) {
+        TileCtx tc;
+        tile_from_list(g, tiles[a], tc, tab, a);
+        if (tc.count == 0) continue;
+        int first = 0;
+        for (int w = 0; w < tc.windows; ++w) {
+            const WinLane wl = window_lane(tc, w, lane, first);
+            if (wl.active) out[tc.base + wl.slot] = w * 32 + lane;
+        }
+    }
 }
 
 // Footprint node k (0..599): shared-memory slot and global node index (-1 outside the grid).
@@ -361,19 +435,21 @@ __device__ __forceinline__ void zero_own_block(const Geo& g, const TileCtx& tc, 
 // ---- p2g 1: node masses ---------------------------------------------------------------------
 
 template <bool PEER>   // PEER: slab run with the neighbours' arrays mapped (deposits into the shared planes go there too)
-__global__ void __launch_bounds__(T3::THREADS)
+__global__ void __launch_bounds__(T3::THREADS, 12)   // 40 registers: 12 CTAs per SM (at 48 registers / 10 CTAs: +6 % time)
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
              const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid, PeerHalo ph,
-             ParticleTex tq) {
+             ParticleTex tq, const unsigned char* __restrict__ tab, int* __restrict__ ticket) {
     __shared__ float4 sm[T3::WARPS * T3::QSLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* tile = sm + warp * T3::QSLOTS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
-    for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
+    int a_raw = tile_ticket(ticket, lane, blockIdx.x * T3::WARPS + warp - n_warps, n_warps);
+    for (int a = tile_of_ticket(ticket, a_raw); a < n_act; a = tile_of_ticket(ticket, a_raw)) {
+        a_raw = tile_ticket(ticket, lane, a, n_warps);   // the next tile's ticket: needed only when this one is done
         TileCtx tc;
-        tile_from_list(g, __ldg(&tiles[a]), tc);
+        tile_from_list(g, __ldg(&tiles[a]), tc, tab, a);
         if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
             continue;
         }
@@ -383,46 +459,45 @@ k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
         // kernel; "p2g 2" deposits into it next)
         zero_own_block(g, tc, lane, grid);
         // software pipeline: record one window ahead, index two windows ahead
-        int off, len;
-        window_range(tc, 0, off, len);
+        int first = 0;
+        WinLane wl0 = window_lane(tc, 0, lane, first);
+        WinLane wl1 = window_lane(tc, 1, lane, first);
         float4 p_next = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (lane < len) p_next = fetch_f4(tq.P, P, fetch_i(tq.src, src, tc.base + off + lane));
-        window_range(tc, 1, off, len);
-        int i_next = lane < len ? fetch_i(tq.src, src, tc.base + off + lane) : 0;
+        if (wl0.active) p_next = fetch_f4(tq.P, P, fetch_i(tq.src, src, tc.base + wl0.slot));
+        int i_next = wl1.active ? fetch_i(tq.src, src, tc.base + wl1.slot) : 0;
         for (int w = 0; w < tc.windows; ++w) {
-            window_range(tc, w, off, len);
-            const bool active = lane < len;
-            const int len_w = len;
+            const bool active = wl0.active;
             const float4 p = p_next;
-            window_range(tc, w + 1, off, len);
-            if (lane < len) p_next = fetch_f4(tq.P, P, i_next);
-            window_range(tc, w + 2, off, len);
-            if (lane < len) i_next = fetch_i(tq.src, src, tc.base + off + lane);
-            TStencil s;
-            tile_stencil(g, tc, p.x, p.y, p.z, s);
-            const float wqm[4] = {s.wq[0] * p.w, s.wq[1] * p.w, s.wq[2] * p.w, s.wq[3] * p.w};
-            // an idle lane reads where the first lane of its quarter warp reads (128-bit accesses are
-            // served per quarter warp; same address = no extra wavefront), or lane 0 if the whole quarter
-            // is idle; its own stale address could sit in a bank group an active lane uses
-            const int q_lane = lane & ~7;
-            const int n0_q = __shfl_sync(0xffffffffu, s.node0q, q_lane < len_w ? q_lane : 0);   // every lane takes part
-            const int n0 = active ? s.node0q : n0_q;
+            if (wl1.active) p_next = fetch_f4(tq.P, P, i_next);
+            wl0 = wl1;
+            wl1 = window_lane(tc, w + 2, lane, first);
+            if (wl1.active) i_next = fetch_i(tq.src, src, tc.base + wl1.slot);
+            // Idle lanes skip the read-modify-writes altogether: a 128-bit access is served per quarter warp, and a
+            // quarter none of whose lanes takes part costs no wavefront (ncu: an LDS.128 executed by mirrored idle
+            // lanes always costs 4).  The lanes that do take part meet at a warp barrier of their own.
+            const unsigned amask = __ballot_sync(0xffffffffu, active);
+            if (active) {
+                TStencil s;
+                tile_stencil(g, tc, p.x, p.y, p.z, s);
+                const float wqm[4] = {s.wq[0] * p.w, s.wq[1] * p.w, s.wq[2] * p.w, s.wq[3] * p.w};
+                float4* n0 = tile + s.node0q;
 #pragma unroll
-            for (int oy = 0; oy < 3; ++oy)
+                for (int oy = 0; oy < 3; ++oy)
 #pragma unroll
-                for (int ox = 0; ox < 3; ++ox) {
-                    const float wxy = s.wx[ox] * s.wy[oy];
-                    float4* nd = tile + n0 + ox + T3::NX * oy;
-                    // the quad of this column: private to this lane within the window.  The load and
-                    // the math run for every lane, only the store is predicated: no branch in the chain.
-                    float4 q4 = *nd;
-                    q4.x += wxy * wqm[0];
-                    q4.y += wxy * wqm[1];
-                    q4.z += wxy * wqm[2];
-                    q4.w += wxy * wqm[3];
-                    if (active) *nd = q4;
-                    __syncwarp();
-                }
+                    for (int ox = 0; ox < 3; ++ox) {
+                        const float wxy = s.wx[ox] * s.wy[oy];
+                        float4* nd = n0 + ox + T3::NX * oy;
+                        // the quad of this column: private to this lane within the window
+                        float4 q4 = *nd;
+                        q4.x += wxy * wqm[0];
+                        q4.y += wxy * wqm[1];
+                        q4.z += wxy * wqm[2];
+                        q4.w += wxy * wqm[3];
+                        *nd = q4;
+                        __syncwarp(amask);
+                    }
+            }
+            __syncwarp();
         }
         // flush: lane -> footprint column c = lane + 32*it (100 columns), six nodes along z
         float* peer_lo = (PEER && tc.c0[2] == g.slab_lo) ? ph.gmass[0] : nullptr;              // warp-uniform
@@ -485,7 +560,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             const float* __restrict__ gmass, float4* __restrict__ grid,
             float* __restrict__ dbg_density, float* __restrict__ dbg_pressure, PeerHalo ph,
             const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_mass, int tma_mass,
-            ParticleTex tq) {
+            ParticleTex tq, const unsigned char* __restrict__ tab, int* __restrict__ ticket) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     __shared__ __align__(8) unsigned long long bars[T3::WARPS];
@@ -502,20 +577,22 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
     }
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
-    for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
+    int a_raw = tile_ticket(ticket, lane, blockIdx.x * T3::WARPS + warp - n_warps, n_warps);
+    for (int a = tile_of_ticket(ticket, a_raw); a < n_act; a = tile_of_ticket(ticket, a_raw)) {
+        a_raw = tile_ticket(ticket, lane, a, n_warps);   // the next tile's ticket: needed only when this one is done
         TileCtx tc;
-        tile_from_list(g, __ldg(&tiles[a]), tc);
+        tile_from_list(g, __ldg(&tiles[a]), tc, tab, a);
         if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
             continue;
         }
-        int off, len;
-        window_range(tc, 0, off, len);
+        int first = 0;
+        WinLane wl0 = window_lane(tc, 0, lane, first);
+        WinLane wl1 = window_lane(tc, 1, lane, first);
         PRec nxt;
         nxt.p = nxt.v = nxt.ca = nxt.cb = make_float4(0.f, 0.f, 0.f, 0.f);
         nxt.cc = 0.0f;
-        load_prec(q, tq, lane < len ? fetch_i(tq.src, src, tc.base + off + lane) : 0, lane < len, nxt);
-        window_range(tc, 1, off, len);
-        int i_next = lane < len ? fetch_i(tq.src, src, tc.base + off + lane) : 0;
+        load_prec(q, tq, wl0.active ? fetch_i(tq.src, src, tc.base + wl0.slot) : 0, wl0.active, nxt);
+        int i_next = wl1.active ? fetch_i(tq.src, src, tc.base + wl1.slot) : 0;
         const FootLane fl = foot_lane(lane);
         // the node masses of the footprint as ONE tensor copy (box 12 x 10 x 6 floats) into the accumulator
         // tile, which is idle until the first window; unpacked into z quads below
@@ -577,92 +654,85 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
         __syncwarp();
 
         for (int w = 0; w < tc.windows; ++w) {
-            window_range(tc, w, off, len);
-            const bool active = lane < len;
-            const int len_w = len;
-            const int d = tc.base + off + lane;   // sorted slot
+            const bool active = wl0.active;
+            const int d = tc.base + wl0.slot;   // sorted slot
             const PRec cur = nxt;
-            window_range(tc, w + 1, off, len);
-            load_prec(q, tq, i_next, lane < len, nxt);        // prefetch the next window
-            window_range(tc, w + 2, off, len);
-            if (lane < len) i_next = fetch_i(tq.src, src, tc.base + off + lane);
-            TStencil s;
-            tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
-            // idle lanes read where the first lane of their quarter warp reads (128-bit accesses are served
-            // per quarter warp; same address = no extra wavefront), or lane 0 if the whole quarter is idle;
-            // their own stale address could sit in a bank an active lane uses
-            const int q_lane = lane & ~7;
-            const int n0_q = __shfl_sync(0xffffffffu, s.node0, q_lane < len_w ? q_lane : 0);   // every lane takes part
-            const int n0q_q = __shfl_sync(0xffffffffu, s.node0q, q_lane < len_w ? q_lane : 0);
-            const int n0 = active ? s.node0 : n0_q;
-            const int n0q = active ? s.node0q : n0q_q;
-
-            // density = sum_i m_i w_ip (3d:198-215): one quad of node masses per stencil column,
-            // summed z -> x -> y
-            float density = 0.0f;
-#pragma unroll
-            for (int oy = 0; oy < 3; ++oy) {
-                const float4* row = ms + n0q + T3::NX * oy;
-                float rs = 0.0f;
-#pragma unroll
-                for (int ox = 0; ox < 3; ++ox) {
-                    const float4 q4 = row[ox];
-                    rs += (q4.x * s.wq[0] + q4.y * s.wq[1] + q4.z * s.wq[2] + q4.w * s.wq[3]) * s.wx[ox];
-                }
-                density += rs * s.wy[oy];
-            }
-            const float m = cur.p.w;
-            float volume = 0.0f, pressure = 0.0f;
+            load_prec(q, tq, i_next, wl1.active, nxt);        // prefetch the next window
+            wl0 = wl1;
+            wl1 = window_lane(tc, w + 2, lane, first);
+            if (wl1.active) i_next = fetch_i(tq.src, src, tc.base + wl1.slot);
+            // Idle lanes skip the shared-memory work altogether: a 128-bit access is served per quarter warp, and a
+            // quarter none of whose lanes takes part costs no wavefront (ncu: an LDS.128 executed by mirrored idle
+            // lanes always costs 4).  The lanes that do take part meet at a warp barrier of their own.
+            const unsigned amask = __ballot_sync(0xffffffffu, active);
             if (active) {
-                volume = m * __frcp_rn(density);
-                pressure = tait_pressure_fast(g, density);
+                TStencil s;
+                tile_stencil(g, tc, cur.p.x, cur.p.y, cur.p.z, s);
+                // density = sum_i m_i w_ip (3d:198-215): one quad of node masses per stencil column,
+                // summed z -> x -> y
+                float density = 0.0f;
+#pragma unroll
+                for (int oy = 0; oy < 3; ++oy) {
+                    const float4* row = ms + s.node0q + T3::NX * oy;
+                    float rs = 0.0f;
+#pragma unroll
+                    for (int ox = 0; ox < 3; ++ox) {
+                        const float4 q4 = row[ox];
+                        rs += (q4.x * s.wq[0] + q4.y * s.wq[1] + q4.z * s.wq[2] + q4.w * s.wq[3]) * s.wx[ox];
+                    }
+                    density += rs * s.wy[oy];
+                }
+                const float m = cur.p.w;
+                const float volume = m * __frcp_rn(density);
+                const float pressure = tait_pressure_fast(g, density);
                 if (dbg_density) dbg_density[d] = density;
                 if (dbg_pressure) dbg_pressure[d] = pressure;
-            }
-            // M = m C + T,  T = -4 V (-p I + mu (C + C^T)) dt   (3d:222-225), column-major
-            const float C[9] = {cur.ca.x, cur.ca.y, cur.ca.z, cur.ca.w, cur.cb.x, cur.cb.y, cur.cb.z, cur.cb.w, cur.cc};
-            const float s1 = -4.0f * volume * g.dt;
-            float M[9];
+                // M = m C + T,  T = -4 V (-p I + mu (C + C^T)) dt   (3d:222-225), column-major
+                const float C[9] = {cur.ca.x, cur.ca.y, cur.ca.z, cur.ca.w, cur.cb.x, cur.cb.y, cur.cb.z, cur.cb.w, cur.cc};
+                const float s1 = -4.0f * volume * g.dt;
+                float M[9];
 #pragma unroll
-            for (int c = 0; c < 3; ++c)
+                for (int c = 0; c < 3; ++c)
 #pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    float stress = g.mu * (C[3 * c + r] + C[3 * r + c]);
-                    if (c == r) stress -= pressure;
-                    M[3 * c + r] = m * C[3 * c + r] + s1 * stress;
+                    for (int r = 0; r < 3; ++r) {
+                        float stress = g.mu * (C[3 * c + r] + C[3 * r + c]);
+                        if (c == r) stress -= pressure;
+                        M[3 * c + r] = m * C[3 * c + r] + s1 * stress;
+                    }
+                // value at offset o: w * (b + ox*M0 + oy*M1 + oz*M2), b = m v + M * (-1 - c)
+                const float dx0 = -1.0f - s.cx, dy0 = -1.0f - s.cy, dz0 = -1.0f - s.cz;
+                float b[3];
+                b[0] = m * cur.v.x + M[0] * dx0 + M[3] * dy0 + M[6] * dz0;
+                b[1] = m * cur.v.y + M[1] * dx0 + M[4] * dy0 + M[7] * dz0;
+                b[2] = m * cur.v.z + M[2] * dx0 + M[5] * dy0 + M[8] * dz0;
+                // per-z factors: node k gets wz_k * A + (k * wz_k) * G with A = wxy*c, G = wxy*M2
+                const float q1 = s.wz[1], q2 = 2.0f * s.wz[2];
+                float4* n0 = acc + s.node0;
+#pragma unroll
+                for (int oy = 0; oy < 3; ++oy) {
+                    const float r0 = b[0] + oy * M[3], r1 = b[1] + oy * M[4], r2 = b[2] + oy * M[5];
+#pragma unroll
+                    for (int ox = 0; ox < 3; ++ox) {
+                        const float wxy = s.wx[ox] * s.wy[oy];
+                        const float A0 = wxy * (r0 + ox * M[0]), A1 = wxy * (r1 + ox * M[1]), A2 = wxy * (r2 + ox * M[2]);
+                        const float G0 = wxy * M[6], G1 = wxy * M[7], G2 = wxy * M[8];
+                        const float mw = wxy * m;
+                        float4* nd = n0 + ox + T3::NX * oy;
+                        // three nodes along z: private to this lane within the window
+                        float4 a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
+                        a0.x += s.wz[0] * A0;  a0.y += s.wz[0] * A1;  a0.z += s.wz[0] * A2;  a0.w += s.wz[0] * mw;
+                        a1.x += s.wz[1] * A0 + q1 * G0;  a1.y += s.wz[1] * A1 + q1 * G1;
+                        a1.z += s.wz[1] * A2 + q1 * G2;  a1.w += s.wz[1] * mw;
+                        a2.x += s.wz[2] * A0 + q2 * G0;  a2.y += s.wz[2] * A1 + q2 * G1;
+                        a2.z += s.wz[2] * A2 + q2 * G2;  a2.w += s.wz[2] * mw;
+                        nd[0] = a0;
+                        nd[T3::PLANE] = a1;
+                        nd[2 * T3::PLANE] = a2;
+                        __syncwarp(amask);
+                    }
                 }
-            // value at offset o: w * (b + ox*M0 + oy*M1 + oz*M2), b = m v + M * (-1 - c)
-            const float dx0 = -1.0f - s.cx, dy0 = -1.0f - s.cy, dz0 = -1.0f - s.cz;
-            float b[3];
-            b[0] = m * cur.v.x + M[0] * dx0 + M[3] * dy0 + M[6] * dz0;
-            b[1] = m * cur.v.y + M[1] * dx0 + M[4] * dy0 + M[7] * dz0;
-            b[2] = m * cur.v.z + M[2] * dx0 + M[5] * dy0 + M[8] * dz0;
-            // per-z factors: node k gets wz_k * A + (k * wz_k) * G with A = wxy*c, G = wxy*M2
-            const float q1 = s.wz[1], q2 = 2.0f * s.wz[2];
-#pragma unroll
-            for (int oy = 0; oy < 3; ++oy) {
-                const float r0 = b[0] + oy * M[3], r1 = b[1] + oy * M[4], r2 = b[2] + oy * M[5];
-#pragma unroll
-                for (int ox = 0; ox < 3; ++ox) {
-                    const float wxy = s.wx[ox] * s.wy[oy];
-                    const float A0 = wxy * (r0 + ox * M[0]), A1 = wxy * (r1 + ox * M[1]), A2 = wxy * (r2 + ox * M[2]);
-                    const float G0 = wxy * M[6], G1 = wxy * M[7], G2 = wxy * M[8];
-                    const float mw = wxy * m;
-                    float4* nd = acc + n0 + ox + T3::NX * oy;
-                    // three nodes along z: private to this lane within the window; loads and math are
-                    // unconditional, only the stores are predicated
-                    float4 a0 = nd[0], a1 = nd[T3::PLANE], a2 = nd[2 * T3::PLANE];
-                    a0.x += s.wz[0] * A0;  a0.y += s.wz[0] * A1;  a0.z += s.wz[0] * A2;  a0.w += s.wz[0] * mw;
-                    a1.x += s.wz[1] * A0 + q1 * G0;  a1.y += s.wz[1] * A1 + q1 * G1;
-                    a1.z += s.wz[1] * A2 + q1 * G2;  a1.w += s.wz[1] * mw;
-                    a2.x += s.wz[2] * A0 + q2 * G0;  a2.y += s.wz[2] * A1 + q2 * G1;
-                    a2.z += s.wz[2] * A2 + q2 * G2;  a2.w += s.wz[2] * mw;
-                    if (active) nd[0] = a0;
-                    if (active) nd[T3::PLANE] = a1;
-                    if (active) nd[2 * T3::PLANE] = a2;
-                    __syncwarp();
-                }
             }
+            __syncwarp();
         }
         if (TMA && !tc.low_rim) {   // (a reduction box must not start at a negative coordinate; overhang at the far end is fine)
             // six 10x10 planes as tensor reductions (cp.reduce.async.bulk.tensor .add, SASS UTMAREDG): no LDS, no
@@ -721,13 +791,16 @@ struct SlabBufs {
 // COUNT: also start the next substep's neighbour search (sort.cuh): every particle of the tile
 // gets its new bucket; the ones that stay in this tile are ranked with shared-memory integer
 // atomics (native ATOMS.ADD), the few that change tile or are dropped go to the immigrant list.
+// g2p has no write conflicts, so it walks the tile's slots 32 at a time, every lane busy, whatever the windows are.
+// (Measured, tools/experiments: walking window by window instead — no bank conflicts under ORDER_CLASS_Q, but a fifth
+// more iterations — costs 12 %; five CTAs per SM at 96 registers cost 10 %.)
 template <bool COUNT, bool TMA>   // TMA: the footprint is loaded by the tensor memory accelerator (tm_grid)
 __global__ void __launch_bounds__(T3::THREADS, 4)
 k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int* __restrict__ src,
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb,
             float* __restrict__ gmass, int* __restrict__ gz, const int* __restrict__ epoch_dev,
-            const __grid_constant__ CUtensorMap tm_grid, ParticleTex tq) {
+            const __grid_constant__ CUtensorMap tm_grid, ParticleTex tq, int* __restrict__ ticket) {
     const int epoch = *epoch_dev + 1;   // this substep's number (k_tail advances the counter after this kernel)
     if (mouse && mouse[2] == 0.0f) mouse = nullptr;   // {x, y, present}: the pointer itself never changes (CUDA graphs)
     __shared__ __align__(128) float4 sm[T3::WARPS * T3::SLOTS];
@@ -746,7 +819,9 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         }
         __syncwarp();
     }
-    for (int a = blockIdx.x * T3::WARPS + warp; a < n_act; a += n_warps) {
+    int a_raw = tile_ticket(ticket, lane, blockIdx.x * T3::WARPS + warp - n_warps, n_warps);
+    for (int a = tile_of_ticket(ticket, a_raw); a < n_act; a = tile_of_ticket(ticket, a_raw)) {
+        a_raw = tile_ticket(ticket, lane, a, n_warps);   // the next tile's ticket: needed only when this one is done
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
         if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)

@@ -77,6 +77,8 @@ constexpr int TILE_CELLS = 256;
 constexpr int N_PSEUDO = 3;   // pseudo tiles behind the real ones: ignored, dropped, migrated away
 constexpr int SCAL_N_ACTIVE = 0, SCAL_N_IMM = 1, SCAL_MIG_LO = 2, SCAL_MIG_HI = 3, SCAL_MIG_OVERFLOW = 4;
 constexpr int SCAL_N_CAND = 5, SCAL_N_DIRTY = 6, SCAL_N_DIRTY2 = 7;
+constexpr int SCAL_TICKET = 8;   // + 0, 1, 2: next list entry of k_mass_tiled / k_p2g_tiled / k_g2p_tiled (zeroed with the rest by the sort)
+constexpr int SCAL_COUNT = 16;
 constexpr int MIG_WORDS = 17;   // packed migrant record: 16 f32 + id
 
 __device__ __forceinline__ bool is_tombstone(float x) { return isinf(x) && x > 0.0f; }
@@ -315,7 +317,26 @@ k_scan_final(int* __restrict__ in, int m, const int* __restrict__ block_sums, in
 //                   quarter warp hit 8 different 16-byte bank groups of the float4 node tile.
 //                 The tile list carries W: {tile, first slot, N, W}; window w holds the slots
 //                 [w*(N/W) + min(w, N%W), + N/W + (w < N%W)).
-enum TileOrder : int { ORDER_CELL = 0, ORDER_CLASS_RR = 1 };
+//                 (2D tiled path; 3D tiles too crowded for ORDER_CLASS_Q.)
+// ORDER_CLASS_Q   3D tiled path.  A 128-bit shared-memory access is served per QUARTER warp, one wavefront per
+//                 distinct address in the quarter's fullest bank group, so what a tile costs per access is the
+//                 number of quarter warps it occupies plus their collisions, and no order can do with fewer
+//                 than max(ceil(N/8), N_max) of them, N_max = the fullest bank class (tools/order_lab.py).  This
+//                 order meets that bound with no collision at all: with q_b = a particle's place in its class's
+//                 (column, z) sequence and
+//                     W = max(fullest column, ceil(N_max / 4))  windows:
+//                     window = q_b mod W,   round = q_b div W (0..3),
+//                 round k of a window is quarter warp k, its members the classes with N_b > window + k*W in
+//                 ascending order, one lane each from lane 8k on.  So a quarter never holds two particles of one
+//                 class (8 different 16-byte bank groups, whatever the stencil offset), every class starts at
+//                 window 0 (the windows in which the fullest class has its ceil(N_b/W) members are the same for
+//                 all classes: sum over windows of the rounds in use = N_max), and two particles of a column are
+//                 still less than W apart in q_b: no two in one window.  Lanes behind a round's members idle
+//                 (an idle quarter costs no wavefront).  Slots stay compact: window after window, round after
+//                 round.  The tile list carries W | ORDER_Q_FLAG; the class totals N_b (one byte each, N_b <= 4W
+//                 <= 128), N_b div W and N_b mod W sit in the tile's table row.
+enum TileOrder : int { ORDER_CELL = 0, ORDER_CLASS_RR = 1, ORDER_CLASS_Q = 2 };
+constexpr int ORDER_Q_FLAG = 1 << 30;   // in tiles[a].w and tile_info[t].x beside W (<= 32; the other orders store any W > 0 or -W there)
 
 // floor(x / w) for 0 <= x < 8192, 1 <= w <= 32 without an integer division: (x + 0.5) / w is at least
 // 0.5/32 away from an integer while the float product is off by less than 2^-10.
@@ -446,8 +467,30 @@ k_tile_tables(const __grid_constant__ Geo g, int* __restrict__ count, const int*
             }
             continue;
         }
-        const int col_max = max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]);
-        const int w_count = max((n_t + 31) / 32, __reduce_max_sync(0xffffffffu, col_max));
+        const int col_max = __reduce_max_sync(0xffffffffu, max(cnt[0] + cnt[1] + cnt[2] + cnt[3], cnt[4] + cnt[5] + cnt[6] + cnt[7]));
+        if (ORDER == ORDER_CLASS_Q) {
+            int n_cls = mine;                       // class totals N_b (lanes 4b..4b+3 hold class b)
+            n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 1);
+            n_cls += __shfl_xor_sync(0xffffffffu, n_cls, 2);
+            const int n_max = __reduce_max_sync(0xffffffffu, n_cls);
+            const int w_q = max(col_max, (n_max + 3) >> 2);
+            const int nb = __shfl_sync(0xffffffffu, n_cls, 4 * (lane & 7));
+            if (w_q <= PERM_MAX_W) {                // (then N_b <= 128: one byte each; more crowded tiles get ORDER_CLASS_RR)
+                if (lane == 0) {
+                    tiles[a] = make_int4(t, base, n_t, w_q | ORDER_Q_FLAG);
+                    tile_info[t] = make_int2(w_q | ORDER_Q_FLAG, a);
+                }
+                if (lane < 8) {
+                    unsigned char* row = tab + static_cast<size_t>(a) * TAB_BYTES;
+                    const int d = small_div(nb, 1.0f / static_cast<float>(w_q));
+                    row[lane] = static_cast<unsigned char>(nb);
+                    row[8 + lane] = static_cast<unsigned char>(d);
+                    row[16 + lane] = static_cast<unsigned char>(nb - d * w_q);
+                }
+                continue;
+            }
+        }
+        const int w_count = max((n_t + 31) / 32, col_max);
         const bool merge = w_count <= PERM_MAX_W && n_t < 8192;
         if (lane == 0) {
             tiles[a] = make_int4(t, base, n_t, w_count);   // list slot = candidate index: no atomics
@@ -491,6 +534,33 @@ __device__ __forceinline__ int build_src_slot(int bucket, int q_abs, int2 info, 
     const int base = __ldg(&tile_base[t]);
     const int n_t = __ldg(&tile_base[t + 1]) - base;
     const int q = q_abs - base;
+    if (info.x > 0 && (info.x & ORDER_Q_FLAG)) {   // ORDER_CLASS_Q
+        const int w_count = info.x & 0xff;
+        const float inv_w = __fdividef(1.0f, static_cast<float>(w_count));
+        const int cls = (bucket & (TILE_CELLS - 1)) >> 5;
+        const int qb = q_abs - __ldg(&cell_off[(t << 8) + (cls << 5)]);   // place in my class's (column, z) sequence: < N_b <= 128
+        const int k = small_div(qb, inv_w);          // round
+        const int w = qb - k * w_count;              // window
+        const uint2* row = reinterpret_cast<const uint2*>(tab + static_cast<size_t>(info.y) * TAB_BYTES);
+        const uint2 nb = __ldg(&row[0]), db = __ldg(&row[1]), mb = __ldg(&row[2]);
+        // slots of the windows before w: sum_b (N_b div W) * w + min(N_b mod W, w)
+        const unsigned w4 = static_cast<unsigned>(w) * 0x01010101u;
+        int pos = w * static_cast<int>(__vsadu4(db.x, 0u) + __vsadu4(db.y, 0u)) +
+                  static_cast<int>(__vsadu4(__vminu4(mb.x, w4), 0u) + __vsadu4(__vminu4(mb.y, w4), 0u));
+        // rounds before mine in this window: #{b : N_b > w + k' W}, k' < k
+#pragma unroll
+        for (int kk = 0; kk < 3; ++kk)
+            if (kk < k) {
+                const unsigned t4 = static_cast<unsigned>(w + kk * w_count) * 0x01010101u;
+                pos += (__popc(__vcmpgtu4(nb.x, t4)) + __popc(__vcmpgtu4(nb.y, t4))) >> 3;
+            }
+        // my place in the round: the classes below mine that reach it
+        const unsigned q4 = static_cast<unsigned>(qb) * 0x01010101u;
+        const unsigned long long gt = (static_cast<unsigned long long>(__vcmpgtu4(nb.y, q4)) << 32) | __vcmpgtu4(nb.x, q4);
+        const unsigned long long below = cls == 0 ? 0ull : (~0ull >> (64 - 8 * cls));
+        pos += __popcll(gt & below) >> 3;
+        return base + pos;
+    }
     if (info.x < 0) {    // too many windows for the merge table: round robin only
         const int w_count = -info.x;
         const int per = n_t / w_count, extra = n_t - per * w_count;

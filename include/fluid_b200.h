@@ -184,12 +184,17 @@ fluid_status fluid_debug_substep(fluid_sim* sim, const float* mouse_xy, int64_t 
  * the engine's tiled cell order; `cell_index` lets a checker rebuild cellStart/cellEnd. */
 fluid_status fluid_debug_neighbour_table(fluid_sim* sim, int64_t capacity, int32_t* ids,
                                          int32_t* cell_index, int64_t* n_written);
-/* Active tile list of the current sort (3D tiled path): per tile {tile id, first sorted slot,
- * particles N, windows W}.  Window w of a tile holds the sorted slots
- * [first + w*(N/W) + min(w, N%W), + N/W + (w < N%W)).  With fluid_debug_neighbour_table this lets a
- * checker verify the invariant the shared-memory accumulation relies on: no two particles of one
- * window share an (x,y) cell column.  Call right after fluid_debug_neighbour_table. */
+/* Active tile list of the current sort (tiled paths): per tile {tile id, first sorted slot,
+ * particles N, windows W}; a tile's slots are [first, first + N).  Call right after
+ * fluid_debug_neighbour_table. */
 fluid_status fluid_debug_tiles(fluid_sim* sim, int64_t capacity_tiles, int32_t* tiles4, int64_t* n_tiles);
+/* Per sorted slot (same order as fluid_debug_neighbour_table): window * 32 + lane, i.e. the warp iteration
+ * and the lane in which the tile kernels process that particle (computed on the device by the kernels' own
+ * window walk).  With the cell indices of fluid_debug_neighbour_table a checker can verify the invariants
+ * the shared-memory accumulation relies on: every slot is claimed exactly once, no two particles of one
+ * window share an (x,y) cell column, and (3D, default order) no two particles of one quarter warp share a
+ * 16-byte bank class (x + 2y) mod 8.  capacity in slots. */
+fluid_status fluid_debug_windows(fluid_sim* sim, int64_t capacity, int32_t* window_lane, int64_t* n_written);
 /* Node grid after the last substep, reference layout: vel_or_momentum[dim] then mass, per
  * node, x fastest (3d:169-172).  `stage`: 0 = as left by the last substep (velocities after
  * update where mass>0). capacity in nodes. */

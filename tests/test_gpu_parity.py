@@ -719,6 +719,33 @@ def test_generic_3d_path_one_substep(pkg, orc, scenes, monkeypatch):
     check_one_substep(pkg, orc, sc, randomised(sc))
 
 
+@pytest.mark.parametrize("order,dyn", [("q", "6"), ("rr", "0"), ("rr", "7")])
+def test_window_order_and_tile_scheduling_variants_one_substep(pkg, orc, scenes, monkeypatch, order, dyn):
+    """The alternative window order (ORDER_CLASS_Q) and the other tile-scheduling modes (fixed stride; ticket counter
+    in all three tile kernels) meet the same one-substep parity bar as the defaults, and several substeps of them
+    agree with the default build."""
+    monkeypatch.setenv("FLUID_B200_ORDER", order)       # both read by fluid_create
+    monkeypatch.setenv("FLUID_B200_DYN", dyn)
+    sc = scenes.dam_break_3d(48, 32, 40)
+    rec = randomised(sc)
+    check_one_substep(pkg, orc, sc, rec)
+    sim = pkg.Simulation.new(sc.cfg)
+    sim.add_particles(rec)
+    sim.set_rect(sc.rect_min, sc.rect_max)
+    sim.substeps(9)
+    got, _ = sim.read_particles(sort_by_id=True)
+    sim.close()
+    monkeypatch.delenv("FLUID_B200_ORDER")
+    monkeypatch.delenv("FLUID_B200_DYN")
+    ref = pkg.Simulation.new(sc.cfg)
+    ref.add_particles(rec)
+    ref.set_rect(sc.rect_min, sc.rect_max)
+    ref.substeps(9)
+    want, _ = ref.read_particles(sort_by_id=True)
+    ref.close()
+    assert np.abs(got[:, :6] - want[:, :6]).max() < 2e-4
+
+
 def test_tiled_and_generic_paths_agree(pkg, scenes, monkeypatch):
     sc = scenes.dam_break_3d(40, 32, 24)
     rec = randomised(sc)
@@ -849,30 +876,45 @@ def test_slab_entry_points_on_one_gpu(pkg, scenes):
     np.testing.assert_allclose(got[:, :6], want[:, :6], rtol=0, atol=2e-4)   # float atomics: order-dependent sums
 
 
-def test_windows_hold_distinct_columns(pkg, scenes):
-    """The invariant the shared-memory read-modify-writes rely on (sort.cuh, ORDER_CLASS_RR): inside
-    one window of one tile no two particles share an (x,y) cell column, windows are <= 32 particles,
-    and they cover the tile's slots exactly.  Checked on the host from the engine's own tables, on a
-    sloshing scene over several substeps and on a deliberately crowded one."""
-    def check(sim, sc):
+@pytest.mark.parametrize("order", ["rr", "q"])
+def test_windows_hold_distinct_columns(pkg, scenes, order, monkeypatch):
+    """The invariants the shared-memory read-modify-writes rely on (sort.cuh), checked on the host from the engine's
+    own tables and the kernels' own window walk (fluid_debug_windows), for the default window order (ORDER_CLASS_RR)
+    and the alternative (ORDER_CLASS_Q, FLUID_B200_ORDER=q): every sorted slot is claimed by exactly one
+    (window, lane), and inside one window of one tile no two particles share an (x,y) cell column.  ORDER_CLASS_Q
+    also promises that inside one quarter warp no two particles share a bank class (x + 2y) mod 8 of the node tile
+    — its 128-bit accesses are free of bank conflicts — and that a tile occupies as many quarter warps as its
+    fullest class holds particles (the lower bound of any order).  On a sloshing scene over several substeps and on
+    a deliberately crowded one (more than 32 windows: both orders fall back to the plain round robin)."""
+    monkeypatch.setenv("FLUID_B200_ORDER", order)
+
+    def check(sim, sc, expect_quarters=(order == "q")):
         ids, cidx = sim.neighbour_table()
         tiles = sim.debug_tiles()
+        wl = sim.debug_windows()
+        assert len(wl) == len(ids) and (wl >= 0).all()        # every slot claimed
         r = sim.rects()
         sx, sy = int(r["size"][0]), int(r["size"][1])
         x, y = cidx % sx, (cidx // sx) % sy
         col = x.astype(np.int64) + 100000 * y
+        cls = ((x % 8) + 2 * (y % 8)) % 8
         seen = 0
         for t, first, n, w in tiles.tolist():
-            per, extra = divmod(n, w)
-            assert w >= -(-n // 32)
-            off = first
-            for k in range(w):
-                ln = per + (1 if k < extra else 0)
-                assert ln <= 32
-                c = col[off:off + ln]
-                assert len(np.unique(c)) == ln, (t, k)
-                off += ln
-            assert off == first + n
+            if n == 0:
+                continue
+            sl = slice(first, first + n)
+            win, lane = wl[sl] >> 5, wl[sl] & 31
+            assert win.max() < w and len(np.unique(wl[sl])) == n          # (window, lane) pairs are distinct
+            assert len(np.unique(win.astype(np.int64) * 10**7 + col[sl])) == n, t    # one particle per column and window
+            if expect_quarters:
+                quarter = win.astype(np.int64) * 4 + (lane >> 3)
+                assert len(np.unique(quarter * 8 + cls[sl])) == n, t      # one particle per bank class and quarter warp
+                assert len(np.unique(quarter)) == np.bincount(cls[sl], minlength=8).max()
+                # a quarter's lanes are filled from its first lane on, and lane 0 of every window is busy
+                for qd in np.unique(quarter):
+                    ln = np.sort(lane[quarter == qd] & 7)
+                    assert np.array_equal(ln, np.arange(len(ln)))
+                assert len(np.unique(win[lane == 0])) == w
             seen += n
         assert seen == len(ids)
 
@@ -894,9 +936,9 @@ def test_windows_hold_distinct_columns(pkg, scenes):
     sim = pkg.Simulation.new(sc2.cfg)
     sim.add_particles(rec2)
     sim.set_rect(sc2.rect_min, sc2.rect_max)
-    check(sim, sc2)
+    check(sim, sc2, expect_quarters=False)   # more than 32 windows: plain round robin, lanes compact
     sim.substeps(3)
-    check(sim, sc2)
+    check(sim, sc2, expect_quarters=False)
     sim.close()
 
 

@@ -1,4 +1,4 @@
-"""CPU restatement of the tile order arithmetic of fluid-rs_b200/csrc/sort.cuh (ORDER_CLASS_RR).
+"""CPU restatement of the tile order arithmetic of fluid-rs_b200/csrc/sort.cuh (ORDER_CLASS_RR, ORDER_CLASS_Q).
 
 The kernels place a particle with a closed form (k_tile_tables builds per-tile tables, k_build_src turns
 (cell, rank) into a slot).  This file restates both the DEFINITION of the order (deal the class-major
@@ -168,3 +168,129 @@ def test_quarter_warps_see_distinct_bank_classes_when_classes_are_balanced():
         lanes = cls_of_slot[32 * w:32 * w + 32]
         for qd in range(4):
             assert len(set(lanes[8 * qd:8 * qd + 8])) == 8
+
+
+# ---- ORDER_CLASS_Q: rounds on quarter-warp boundaries (the 3D tiled path's default) ---------------------------
+
+def q_windows_of(counts):
+    """W of ORDER_CLASS_Q, or None where k_tile_tables falls back to the plain round robin (W > 32)."""
+    col = counts.reshape(CLASSES * COLS_PER_CLASS, Z).sum(axis=1)
+    n_cls = counts.reshape(CLASSES, -1).sum(axis=1)
+    w = max(int(col.max()), (int(n_cls.max()) + 3) // 4)
+    return w if w <= 32 else None
+
+
+def q_order_by_definition(counts):
+    """{(cell, rank): (slot, window, lane)} from the definition: class b's (column, z) sequence q_b is dealt from
+    window 0 (window = q_b mod W, round = q_b div W); round k of a window is quarter warp k, classes ascending;
+    slots run window after window, lane after lane."""
+    w_count = q_windows_of(counts)
+    n_cls = counts.reshape(CLASSES, -1).sum(axis=1)
+    place = {}
+    for b in range(CLASSES):
+        qb = 0
+        for cell in range(32 * b, 32 * b + 32):
+            for rank in range(counts[cell]):
+                place[(cell, rank)] = (qb % w_count, qb // w_count, b)
+                qb += 1
+    out, slot = {}, 0
+    for w in range(w_count):
+        for k in range(4):
+            present = [b for b in range(CLASSES) if n_cls[b] > w + k * w_count]
+            assert len(present) <= 8
+            for j, b in enumerate(present):
+                key = [kk for kk, v in place.items() if v == (w, k, b)]
+                assert len(key) == 1
+                out[key[0]] = (slot, w, 8 * k + j)
+                slot += 1
+    assert slot == int(counts.sum())
+    return out, w_count
+
+
+def q_order_by_closed_form(counts):
+    """the same slots through the table row of k_tile_tables<ORDER_CLASS_Q> and the formulas of build_src_slot."""
+    w_count = q_windows_of(counts)
+    cell_off = np.concatenate([[0], np.cumsum(counts)])[:-1]
+    n_cls = counts.reshape(CLASSES, -1).sum(axis=1)
+    assert n_cls.max() <= 128                                # one byte each
+    d_cls = np.array([small_div(int(v), w_count) for v in n_cls])
+    m_cls = n_cls - d_cls * w_count
+    assert np.array_equal(d_cls, n_cls // w_count)
+    slot = {}
+    for cell in range(CELLS):
+        for rank in range(counts[cell]):
+            b = cell >> 5
+            qb = cell_off[cell] + rank - cell_off[32 * b]
+            k = small_div(int(qb), w_count)
+            w = qb - k * w_count
+            pos = w * int(d_cls.sum()) + int(np.minimum(m_cls, w).sum())
+            for kk in range(3):
+                if kk < k:
+                    pos += int((n_cls > w + kk * w_count).sum())
+            pos += int((n_cls[:b] > qb).sum())
+            slot[(cell, rank)] = pos
+    return slot, w_count
+
+
+def q_window_lane(n_cls, w_count, lane, w, first):
+    """phases_tiled.cuh::window_lane for ORDER_CLASS_Q: (active, slot, quarter_on, first of the next window)."""
+    m = [int((n_cls > w + k * w_count).sum()) for k in range(4)]
+    k, j = lane >> 3, lane & 7
+    return j < m[k], first + sum(m[:k]) + j, m[k] > 0, first + sum(m)
+
+
+@pytest.mark.parametrize("kind", ["poisson1", "sparse", "one_column", "one_class", "dense"])
+def test_quarter_order_closed_form_matches_definition(kind):
+    rng = np.random.default_rng(7 + hash(kind) % 1000)
+    done = 0
+    for _ in range(8):
+        counts = random_counts(rng, kind).astype(int)
+        if kind == "dense":
+            counts = np.minimum(counts, 3)                  # keep every class below 4 * 32
+        if counts.sum() == 0 or q_windows_of(counts) is None:
+            continue
+        done += 1
+        want, w1 = q_order_by_definition(counts)
+        got, w2 = q_order_by_closed_form(counts)
+        assert w1 == w2 and got == {k: v[0] for k, v in want.items()}
+        n = int(counts.sum())
+        assert sorted(got.values()) == list(range(n))       # a permutation of the tile's slots
+        n_cls = counts.reshape(CLASSES, -1).sum(axis=1)
+        # the kernels' window walk claims every slot exactly once, with the lane the definition gives
+        lane_of = {v[0]: (v[1], v[2]) for v in want.values()}
+        first, claimed = 0, {}
+        for w in range(w1):
+            nxt = first
+            for lane in range(32):
+                active, s, quarter_on, nxt = q_window_lane(n_cls, w1, lane, w, first)
+                if active:
+                    assert s not in claimed
+                    claimed[s] = (w, lane)
+                    assert quarter_on
+                if lane == 0:
+                    assert active                            # idle quarters mirror lane 0: it always holds a particle
+                if (lane & 7) == 0:
+                    assert active == quarter_on              # ... and a quarter's first lane whenever the quarter does
+            first = nxt
+        assert claimed == lane_of
+        # invariants: no two particles of a window share a column; no two of a quarter warp share a bank class;
+        # the quarter warps in use are exactly the fullest class (the lower bound of any order)
+        seen_col, seen_cls, quarters = set(), set(), set()
+        for (cell, _), (s, w, lane) in want.items():
+            assert (w, cell >> 2) not in seen_col
+            seen_col.add((w, cell >> 2))
+            assert (w, lane >> 3, cell >> 5) not in seen_cls
+            seen_cls.add((w, lane >> 3, cell >> 5))
+            quarters.add((w, lane >> 3))
+        assert len(quarters) == int(n_cls.max())
+    assert done >= 3
+
+
+def test_quarter_order_falls_back_when_a_tile_is_too_crowded():
+    counts = np.zeros(CELLS, dtype=int)
+    counts[0:4] = 9                                          # one column of 36: W would be 36
+    assert q_windows_of(counts) is None
+    counts = np.full(CELLS, 4)                               # 128 per class: W = 32, the largest that fits
+    assert q_windows_of(counts) == 32
+    got, _ = q_order_by_closed_form(counts)
+    assert sorted(got.values()) == list(range(1024))
