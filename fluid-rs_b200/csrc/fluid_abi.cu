@@ -121,6 +121,7 @@ struct fluid_sim {
     bool sorted_valid = false;   // arrays are in tile order for the current positions
     bool counts_pending = false; // the last g2p left buckets / ranks / counts for the next sort
     int tile_order = ORDER_CLASS_RR;  // window order of the 3D tiled path (FLUID_B200_ORDER=q: ORDER_CLASS_Q, sort.cuh)
+    int fixed8[3] = {0, 4, 0};        // ... after this many eighths of the list dealt with the fixed stride (FLUID_B200_FIXED8=mpg digits)
     int dyn_tiles = 6;                // tile kernels that take their tiles from a ticket counter: 1 k_mass_tiled, 2 k_p2g_tiled, 4 k_g2p_tiled (FLUID_B200_DYN=mask; 0: fixed stride)
     int sm_count = 148;
     unsigned grid_mass = 0, grid_p2g = 0, grid_g2p = 0;   // persistent grids: SMs x resident CTAs
@@ -676,10 +677,10 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
                                                                                           s->grid);
             else if (s->p2p)
                 k_mass_tiled<true><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                            s->gmass, s->grid, s->peer, s->tex[s->cur], s->tab, (s->dyn_tiles & 1) ? s->scal + SCAL_TICKET : nullptr);
+                                                                                            s->gmass, s->grid, s->peer, s->tex[s->cur], s->tab, (s->dyn_tiles & 1) ? s->scal + SCAL_TICKET : nullptr, s->fixed8[0]);
             else
                 k_mass_tiled<false><<<std::min(tb, s->grid_mass), T3::THREADS, 0, s->stream>>>(s->geo, q.P, s->src, s->tiles, n_act,
-                                                                                             s->gmass, s->grid, s->peer, s->tex[s->cur], s->tab, (s->dyn_tiles & 1) ? s->scal + SCAL_TICKET : nullptr);
+                                                                                             s->gmass, s->grid, s->peer, s->tex[s->cur], s->tab, (s->dyn_tiles & 1) ? s->scal + SCAL_TICKET : nullptr, s->fixed8[0]);
             ++s->launches;
             if (timed) CU_TRY(cudaEventRecord(ev[3], s->stream));
         } else {
@@ -713,7 +714,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
 #define P2G_LAUNCH(PEER, TMA)                                                                                       \
     k_p2g_tiled<PEER, TMA><<<gp, T3::THREADS, sizeof(P2GSmem), s->stream>>>(s->geo, q, s->src, s->tiles, n_act, s->gmass, \
                                                                            s->grid, dd, dp, s->peer, s->tm_grid, s->tm_mass,     \
-                                                                           s->tma_mass ? 1 : 0, s->tex[s->cur], s->tab, (s->dyn_tiles & 2) ? s->scal + SCAL_TICKET + 1 : nullptr)
+                                                                           s->tma_mass ? 1 : 0, s->tex[s->cur], s->tab, (s->dyn_tiles & 2) ? s->scal + SCAL_TICKET + 1 : nullptr, s->fixed8[1])
             if (s->p2p && s->tma) P2G_LAUNCH(true, true);
             else if (s->p2p) P2G_LAUNCH(true, false);
             else if (s->tma) P2G_LAUNCH(false, true);
@@ -753,7 +754,7 @@ fluid_status substep_impl(fluid_sim* s, const float* d_mouse, bool timed, const 
 #define G2P_LAUNCH(TMA)                                                                                                       \
     k_g2p_tiled<true, TMA><<<std::min(tb, s->grid_g2p), T3::THREADS, 0, s->stream>>>(                                          \
         s->geo, q, qn, s->src, s->tiles, n_act, s->grid, d_mouse, sort_tables(s), sb, s->gmass, s->gz, s->d_epoch, s->tm_grid, \
-        s->tex[s->cur], (s->dyn_tiles & 4) ? s->scal + SCAL_TICKET + 2 : nullptr)
+        s->tex[s->cur], (s->dyn_tiles & 4) ? s->scal + SCAL_TICKET + 2 : nullptr, s->fixed8[2])
                 if (s->tma) G2P_LAUNCH(true);
                 else G2P_LAUNCH(false);
 #undef G2P_LAUNCH
@@ -1078,6 +1079,8 @@ fluid_status fluid_create(const fluid_config* cfg, int32_t device, fluid_sim** o
     if (const char* e = std::getenv("FLUID_B200_TEX")) s->tex_on = e[0] != '0';
     if (const char* e = std::getenv("FLUID_B200_ORDER")) s->tile_order = (e[0] == 'q') ? ORDER_CLASS_Q : ORDER_CLASS_RR;
     if (const char* e = std::getenv("FLUID_B200_DYN")) s->dyn_tiles = std::atoi(e) & 7;
+    if (const char* e = std::getenv("FLUID_B200_FIXED8"))
+        for (int k = 0; k < 3 && e[k] >= '0' && e[k] <= '8'; ++k) s->fixed8[k] = e[k] - '0';
     if (const char* e = std::getenv("FLUID_B200_SPARSE_BLOCKS")) {
         if (cfg->dim == 3) s->sparse_blocks = std::max<long long>(std::atoll(e), 0);
     }

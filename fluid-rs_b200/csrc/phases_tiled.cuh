@@ -187,20 +187,42 @@ __device__ __forceinline__ bool in_tile(const Geo& g, const TileCtx& tc, const f
 
 // The tile kernels run one wave of resident warps over the active-tile list.  With a ticket counter (zeroed by the
 // sort) a warp takes the next tile when it is done with one, so a warp that drew light tiles does more of them and
-// the kernel's tail is one tile long; without one the list is dealt out with a fixed stride.  Measured at 2^24
-// particles: k_p2g_tiled -3.5 %, k_g2p_tiled -6 %; k_mass_tiled +70 % (fixed stride kept there); tickets that cover
-// 2 or 4 consecutive tiles are slower than either (g2p 0.60 / 0.66 / 0.73 ms at 1 / 2 / 4: the tail grows with the
-// batch); listing the tiles of 128 or more particles first, the light ones last, so that the tail is made of small
-// pieces: k_p2g_tiled +5 % (light tiles running beside heavy ones is what keeps the pipes mixed) —
-// tools/experiments/README.md.
-// The ticket is drawn at the START of a tile and looked at when the tile is done: the atomic's round trip (which
-// queues behind the reductions the warp's previous flush still has in flight) is hidden behind the tile's work.
-__device__ __forceinline__ int tile_ticket(int* __restrict__ ticket, int lane, int a, int stride) {
-    if (!ticket) return a + stride;
-    return lane == 0 ? atomicAdd(ticket, 1) : 0;      // lane 0 holds the value
+// the kernel's tail is one tile long; without one the list is dealt out with a fixed stride.  The first `fixed8`
+// eighths of the list (rounded to whole rounds of the resident warps) can still be dealt with the fixed stride and
+// only the rest handed out by tickets; in the ticket phase the next ticket is drawn at the START of a tile and looked
+// at when the tile is done.  Measured at 2^24 particles (profiles/r02_scheduling_ab.md): k_g2p_tiled -6 % with tickets
+// throughout; k_p2g_tiled -3.5 % with tickets throughout, -5 % with tickets for the second half of the list;
+// k_mass_tiled gets SLOWER in proportion to the ticketed share (+70 % with tickets throughout, +17 % with tickets for
+// the last eighth) and keeps the fixed stride: a returning atomic in flight shares the warp's load scoreboards, and
+// with its short tiles and 48 warps per SM flushing with reductions every wait for a particle fetch then waits for
+// the ticket as well (ncu: long-scoreboard stalls 2.2 -> 14.5 per issue).  Tickets that cover 2 or 4 consecutive tiles
+// are slower than either (g2p 0.60 / 0.66 / 0.73 ms at 1 / 2 / 4: the tail grows with the batch); listing the tiles of
+// 128 or more particles first, so that the tail is made of small pieces: k_p2g_tiled +5 % (light tiles running beside
+// heavy ones is what keeps the pipes mixed).
+struct TileWalk {
+    int a;         // current list entry
+    int raw;       // lane 0: the ticket drawn for the next entry
+    int n_fixed;   // entries dealt with the fixed stride
+};
+__device__ __forceinline__ int draw_ticket(int* __restrict__ ticket, int lane) { return lane == 0 ? atomicAdd(ticket, 1) : 0; }
+__device__ __forceinline__ void walk_begin(TileWalk& w, int* __restrict__ ticket, int lane, int first, int stride, int n_act, int fixed8) {
+    w.n_fixed = ticket ? ((n_act / stride) * fixed8 / 8) * stride : n_act;
+    w.a = first;
+    w.raw = 0;
+    if (w.a >= w.n_fixed && ticket) w.a = w.n_fixed + __shfl_sync(0xffffffffu, draw_ticket(ticket, lane), 0);
 }
-__device__ __forceinline__ int tile_of_ticket(int* __restrict__ ticket, int raw) {
-    return ticket ? __shfl_sync(0xffffffffu, raw, 0) : raw;
+__device__ __forceinline__ void walk_prefetch(TileWalk& w, int* __restrict__ ticket, int lane) {   // at the top of the loop body
+    if (ticket && w.a >= w.n_fixed) w.raw = draw_ticket(ticket, lane);
+}
+__device__ __forceinline__ void walk_next(TileWalk& w, int* __restrict__ ticket, int lane, int stride) {
+    if (!ticket) {
+        w.a += stride;
+    } else if (w.a >= w.n_fixed) {
+        w.a = w.n_fixed + __shfl_sync(0xffffffffu, w.raw, 0);
+    } else {
+        w.a += stride;
+        if (w.a >= w.n_fixed) w.a = w.n_fixed + __shfl_sync(0xffffffffu, draw_ticket(ticket, lane), 0);   // leaving the fixed part
+    }
 }
 
 // A lane's place in window w of its tile: `active` and the slot (relative to the tile's first).  `first` = slots of
@@ -444,15 +466,16 @@ __global__ void __launch_bounds__(T3::THREADS, 12)   // 40 registers: 12 CTAs pe
 k_mass_tiled(const __grid_constant__ Geo g, const float4* __restrict__ P,
              const int* __restrict__ src, const int4* __restrict__ tiles,
              const int* __restrict__ n_active, float* __restrict__ gmass, float4* __restrict__ grid, PeerHalo ph,
-             ParticleTex tq, const unsigned char* __restrict__ tab, int* __restrict__ ticket) {
+             ParticleTex tq, const unsigned char* __restrict__ tab, int* __restrict__ ticket, int fixed8) {
     __shared__ float4 sm[T3::WARPS * T3::QSLOTS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float4* tile = sm + warp * T3::QSLOTS;
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
-    int a_raw = tile_ticket(ticket, lane, blockIdx.x * T3::WARPS + warp - n_warps, n_warps);
-    for (int a = tile_of_ticket(ticket, a_raw); a < n_act; a = tile_of_ticket(ticket, a_raw)) {
-        a_raw = tile_ticket(ticket, lane, a, n_warps);   // the next tile's ticket: needed only when this one is done
+    TileWalk tw;
+    for (walk_begin(tw, ticket, lane, blockIdx.x * T3::WARPS + warp, n_warps, n_act, fixed8); tw.a < n_act; walk_next(tw, ticket, lane, n_warps)) {
+        walk_prefetch(tw, ticket, lane);
+        const int a = tw.a;
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc, tab, a);
         if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
@@ -565,7 +588,7 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
             const float* __restrict__ gmass, float4* __restrict__ grid,
             float* __restrict__ dbg_density, float* __restrict__ dbg_pressure, PeerHalo ph,
             const __grid_constant__ CUtensorMap tm_grid, const __grid_constant__ CUtensorMap tm_mass, int tma_mass,
-            ParticleTex tq, const unsigned char* __restrict__ tab, int* __restrict__ ticket) {
+            ParticleTex tq, const unsigned char* __restrict__ tab, int* __restrict__ ticket, int fixed8) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     P2GSmem& sm = *reinterpret_cast<P2GSmem*>(smem_raw);
     __shared__ __align__(8) unsigned long long bars[T3::WARPS];
@@ -582,9 +605,10 @@ k_p2g_tiled(const __grid_constant__ Geo g, Particles q, const int* __restrict__ 
     }
     const int n_act = *n_active;
     const int n_warps = gridDim.x * T3::WARPS;
-    int a_raw = tile_ticket(ticket, lane, blockIdx.x * T3::WARPS + warp - n_warps, n_warps);
-    for (int a = tile_of_ticket(ticket, a_raw); a < n_act; a = tile_of_ticket(ticket, a_raw)) {
-        a_raw = tile_ticket(ticket, lane, a, n_warps);   // the next tile's ticket: needed only when this one is done
+    TileWalk tw;
+    for (walk_begin(tw, ticket, lane, blockIdx.x * T3::WARPS + warp, n_warps, n_act, fixed8); tw.a < n_act; walk_next(tw, ticket, lane, n_warps)) {
+        walk_prefetch(tw, ticket, lane);
+        const int a = tw.a;
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc, tab, a);
         if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
@@ -805,7 +829,7 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
             const int4* __restrict__ tiles, const int* __restrict__ n_active,
             const float4* __restrict__ grid, const float* __restrict__ mouse, SortTables st, SlabBufs sb,
             float* __restrict__ gmass, int* __restrict__ gz, const int* __restrict__ epoch_dev,
-            const __grid_constant__ CUtensorMap tm_grid, ParticleTex tq, int* __restrict__ ticket) {
+            const __grid_constant__ CUtensorMap tm_grid, ParticleTex tq, int* __restrict__ ticket, int fixed8) {
     const int epoch = *epoch_dev + 1;   // this substep's number (k_tail advances the counter after this kernel)
     if (mouse && mouse[2] == 0.0f) mouse = nullptr;   // {x, y, present}: the pointer itself never changes (CUDA graphs)
     __shared__ __align__(128) float4 sm[T3::WARPS * T3::SLOTS];
@@ -824,9 +848,10 @@ k_g2p_tiled(const __grid_constant__ Geo g, Particles q, Particles qn, const int*
         }
         __syncwarp();
     }
-    int a_raw = tile_ticket(ticket, lane, blockIdx.x * T3::WARPS + warp - n_warps, n_warps);
-    for (int a = tile_of_ticket(ticket, a_raw); a < n_act; a = tile_of_ticket(ticket, a_raw)) {
-        a_raw = tile_ticket(ticket, lane, a, n_warps);   // the next tile's ticket: needed only when this one is done
+    TileWalk tw;
+    for (walk_begin(tw, ticket, lane, blockIdx.x * T3::WARPS + warp, n_warps, n_act, fixed8); tw.a < n_act; walk_next(tw, ticket, lane, n_warps)) {
+        walk_prefetch(tw, ticket, lane);
+        const int a = tw.a;
         TileCtx tc;
         tile_from_list(g, __ldg(&tiles[a]), tc);
         if (tc.count == 0) {          // a pseudo tile (ignored / dropped / migrated particles)
