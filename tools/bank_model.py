@@ -137,7 +137,9 @@ def main():
             allp = np.ones(32, dtype=bool)
             i4 = cur4[None, :] + O4[:, None]
             isx = curs[None, :] + OS[:, None]
-            tot["rmw_ld"] += wf128(i4, allp).sum()
+            # (since the idle-lane skip of round 2 the loads are executed by the active lanes only, like the stores; before it
+            # the idle lanes executed them at a mirrored address and an LDS.128 cost 4 wavefronts whatever its lanes did)
+            tot["rmw_ld"] += wf128(i4, part).sum()
             tot["rmw_st"] += wf128(i4, part).sum()
             tot["s_ld"] += wf32(isx, allp).sum()
             tot["s_st"] += wf32(isx, part).sum()
